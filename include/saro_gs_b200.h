@@ -1,0 +1,109 @@
+/* saro_gs_b200.h — C ABI of the B200-native differentiable Gaussian rasterizer.
+ *
+ * Drop-in boundary for the hot path of yjb6/SaRO-GS
+ * (submodules/gaussian_rasterization_ch3, cited below as $R).  These entry points are
+ * what the reference's binding layer ($R/rasterize_points.cu, pybind module `_C` in
+ * $R/ext.cpp:15-19) calls into:
+ *
+ *   sgs_forward       replaces CudaRasterizer::Rasterizer::forward      $R/cuda_rasterizer/rasterizer.h:33-56
+ *   sgs_backward      replaces CudaRasterizer::Rasterizer::backward     $R/cuda_rasterizer/rasterizer.h:58-87
+ *   sgs_mark_visible  replaces CudaRasterizer::Rasterizer::markVisible  $R/cuda_rasterizer/rasterizer.h:26-31
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - every data pointer is a DEVICE pointer to float32 / int32 data on the current CUDA
+ *     device, contiguous, row-major; optional inputs are signalled by NULL
+ *     ($R/cuda_rasterizer/forward.cu:205,241);
+ *   - viewmatrix / projmatrix are 4x4 in row-vector convention (world_view_transform =
+ *     W2C^T), campos and background are 3 floats, all on the device;
+ *   - the three state buffers are opaque byte buffers obtained through resize callbacks
+ *     (the C form of the reference's std::function<char*(size_t)>,
+ *     $R/cuda_rasterizer/rasterizer.h:34-36) and handed back unchanged to sgs_backward;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what the
+ *     reference always uses); all work is enqueued on it.  sgs_forward synchronises the
+ *     stream once to learn the number of tile instances, exactly where the reference does
+ *     ($R/cuda_rasterizer/rasterizer_impl.cu:281-282).
+ *
+ * Differences from the reference ABI, all additive:
+ *   - `stream` and `flags` parameters;
+ *   - sgs_backward takes `dL_dacc` ([P][12] float scratch, need not be initialised) where
+ *     the reference takes dL_dconic ([P][2][2], must be zero), and it WRITES every output
+ *     element, so outputs need not be zero-initialised;
+ *   - errors are reported by a negative return code + sgs_last_error() instead of C++
+ *     exceptions.
+ */
+#ifndef SARO_GS_B200_H_
+#define SARO_GS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGS_ABI_VERSION 1
+
+/* sgs_forward flags */
+#define SGS_FLAG_KEEP_FOR_BACKWARD 1 /* write the packed per-tile lists sgs_backward consumes */
+#define SGS_FLAG_NO_TILE_CULL 2      /* validation only: disable the exact tile-level culling */
+
+/* error codes (negative returns) */
+#define SGS_ERR_INVALID_ARGUMENT -1
+#define SGS_ERR_CUDA -2
+#define SGS_ERR_ALLOC -3
+
+/* Resize callback: must return a device pointer to at least `bytes` bytes that stays
+ * valid until the matching sgs_backward has run (or is never called). */
+typedef char* (*sgs_resize_fn)(void* user, size_t bytes);
+
+int sgs_abi_version(void);
+const char* sgs_last_error(void);
+
+/* bool[P] <- (z_view > 0.2).  $R/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153 */
+int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Forward: returns the number of rendered tile instances (>= 0) or a negative error code.
+ * D = active SH degree, M = SH coefficients per Gaussian (0 when shs == NULL).
+ * out_color [3][H][W], out_depth [1][H][W], radii [P] int32 are fully written when P > 0. */
+int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user,
+                    sgs_resize_fn binning_buffer, void* binning_user,
+                    sgs_resize_fn image_buffer, void* image_user,
+                    int P, int D, int M,
+                    const float* background, int width, int height,
+                    const float* means3D, const float* shs, const float* colors_precomp,
+                    const float* opacities, const float* scales, float scale_modifier,
+                    const float* rotations, const float* cov3D_precomp,
+                    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                    float tan_fovx, float tan_fovy, int prefiltered,
+                    float* out_color, float* out_depth, int* radii,
+                    int flags, void* stream);
+
+/* Backward: R is the value sgs_forward returned.  Outputs (all fully written):
+ *   dL_dmean2D [P][3] (z = 0), dL_dopacity [P], dL_dcolor [P][3], dL_dmean3D [P][3],
+ *   dL_dcov3D [P][6], dL_dsh [P][M][3], dL_dscale [P][3], dL_drot [P][4].
+ * dL_dacc: [P][12] float scratch. */
+int sgs_backward(int P, int D, int M, int64_t R,
+                 const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                 const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                 char* geom_buffer, char* binning_buffer, char* image_buffer,
+                 const float* dL_dpix, float* dL_dmean2D, float* dL_dacc, float* dL_dopacity,
+                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                 float* dL_dscale, float* dL_drot, void* stream);
+
+/* Introspection used by the parity tests (bit-exact integer checks against the reference):
+ * copies internal per-Gaussian / per-tile / per-pixel integer state to caller-provided
+ * DEVICE buffers (any of which may be NULL). */
+int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer, char* binning_buffer,
+                     char* image_buffer, uint32_t* tiles_touched /*[P]*/, uint32_t* ranges /*[tiles][2]*/,
+                     uint32_t* n_contrib /*[H*W]*/, float* final_T /*[H*W]*/, float* means2D /*[P][2]*/,
+                     float* conic_opacity /*[P][4]*/, float* rgbd /*[P][4]*/, float* cov3D /*[P][6]*/,
+                     uint32_t* tile_count /*[tiles]*/, uint32_t* point_list /*[R]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARO_GS_B200_H_ */

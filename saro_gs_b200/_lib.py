@@ -1,0 +1,72 @@
+"""ctypes binding of libsaro_gs_b200.so (the C ABI in include/saro_gs_b200.h).
+
+There is NO CPU or PyTorch fallback: if the shared library is missing or does not export
+the full ABI this module raises, loudly, at first use.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsaro_gs_b200.so")
+
+SGS_FLAG_KEEP_FOR_BACKWARD = 1
+SGS_FLAG_NO_TILE_CULL = 2
+
+RESIZE_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_i64 = ctypes.c_int64
+
+# symbol -> (restype, argtypes); must list every symbol include/saro_gs_b200.h declares
+ABI = {
+    "sgs_abi_version": (_i, []),
+    "sgs_last_error": (ctypes.c_char_p, []),
+    "sgs_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_forward": (_i64, [RESIZE_FN, _vp, RESIZE_FN, _vp, RESIZE_FN, _vp,   # resize callbacks
+                           _i, _i, _i,                                        # P, D, M
+                           _vp, _i, _i,                                       # background, width, height
+                           _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp,             # means3D .. cov3D_precomp
+                           _vp, _vp, _vp, _f, _f, _i,                         # view, proj, campos, tanfov, prefiltered
+                           _vp, _vp, _vp, _i, _vp]),                          # out_color, out_depth, radii, flags, stream
+    "sgs_backward": (_i, [_i, _i, _i, _i64, _vp, _i, _i,                      # P, D, M, R, bg, W, H
+                          _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp,
+                          _vp, _vp, _vp,                                      # state buffers
+                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_debug_export": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp] + [_vp] * 10 + [_vp]),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and type the native library. Raises NativeLibraryMissing if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found. Build it with `python -m saro_gs_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for the rasterizer.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in ABI.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryMissing(f"{LIB_PATH} does not export {name}: stale build?") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sgs_abi_version() != 1:
+        raise NativeLibraryMissing(f"ABI version mismatch: library reports {lib.sgs_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().sgs_last_error()
+    return msg.decode() if msg else ""

@@ -1,0 +1,317 @@
+// C-ABI entry points (include/saro_gs_b200.h) and host orchestration.
+//
+// Replaces the host side of $R/cuda_rasterizer/rasterizer_impl.cu:198-436
+// (Rasterizer::forward / backward / markVisible): buffer carving, kernel sequencing, the
+// single device->host read of num_rendered.  No torch types cross this boundary.
+#include "../../include/saro_gs_b200.h"
+#include "sgs_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    g_last_error = buf;
+    return code;
+}
+
+#define SGS_CUDA_OK(expr)                                                        \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) return fail(SGS_ERR_CUDA, #expr, _e);             \
+    } while (0)
+
+// CUB temp-size queries are pure host arithmetic but not free; cache them.
+std::mutex g_cache_mu;
+std::map<int, size_t> g_geom_temp;
+std::map<std::pair<size_t, int>, size_t> g_inst_temp;
+
+size_t geom_temp_bytes(int P) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_geom_temp.find(P);
+    if (it != g_geom_temp.end()) return it->second;
+    size_t b = 0;
+    sgs::binning_geom_temp_bytes(P, &b);
+    if (g_geom_temp.size() > 4096) g_geom_temp.clear();
+    g_geom_temp[P] = b;
+    return b;
+}
+
+size_t inst_temp_bytes(size_t R, int bits) {
+    // CUB's requirement grows monotonically with R: query on R rounded up to 64 Ki so that
+    // frames with slightly different R hit the cache.
+    const size_t Rq = (R + 65535) & ~(size_t)65535;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto key = std::make_pair(Rq, bits);
+    auto it = g_inst_temp.find(key);
+    if (it != g_inst_temp.end()) return it->second;
+    size_t b = 0;
+    sgs::binning_inst_temp_bytes(Rq, bits, &b);
+    if (g_inst_temp.size() > 4096) g_inst_temp.clear();
+    g_inst_temp[key] = b;
+    return b;
+}
+
+sgs::GeomState carve_geom(char*& chunk, size_t P) {
+    sgs::GeomState g;
+    sgs::carve(chunk, g.depths, P);
+    sgs::carve(chunk, g.means2D, P);
+    sgs::carve(chunk, g.conic_opacity, P);
+    sgs::carve(chunk, g.rgbd, P);
+    sgs::carve(chunk, g.cov3D, P * 6);
+    sgs::carve(chunk, g.clamped, P);
+    sgs::carve(chunk, g.tiles_touched, P);
+    sgs::carve(chunk, g.depth_keys[0], P);
+    sgs::carve(chunk, g.depth_keys[1], P);
+    sgs::carve(chunk, g.depth_vals[0], P);
+    sgs::carve(chunk, g.depth_vals[1], P);
+    sgs::carve(chunk, g.sorted_offsets, P);
+    g.temp_bytes = geom_temp_bytes((int)P);
+    sgs::carve(chunk, g.temp, g.temp_bytes);
+    return g;
+}
+
+sgs::ImageState carve_image(char*& chunk, size_t N, size_t tiles) {
+    sgs::ImageState im;
+    sgs::carve(chunk, im.final_T, N);
+    sgs::carve(chunk, im.n_contrib, N);
+    sgs::carve(chunk, im.ranges, tiles);
+    sgs::carve(chunk, im.tile_count, tiles);
+    return im;
+}
+
+struct BinningCarve {
+    sgs::BinningState b;
+    uint32_t* header;  // [32] word 0: selector of the sorted double buffer (byte pattern)
+};
+
+BinningCarve carve_binning(char*& chunk, size_t R, int tile_bits, bool with_packed) {
+    BinningCarve c;
+    sgs::carve(chunk, c.header, 32);
+    sgs::carve(chunk, c.b.tile_keys[0], R);
+    sgs::carve(chunk, c.b.tile_keys[1], R);
+    sgs::carve(chunk, c.b.gauss_vals[0], R);
+    sgs::carve(chunk, c.b.gauss_vals[1], R);
+    c.b.temp_bytes = inst_temp_bytes(R, tile_bits);
+    sgs::carve(chunk, c.b.temp, c.b.temp_bytes);
+    if (with_packed) sgs::carve(chunk, c.b.packed, R);
+    else c.b.packed = nullptr;
+    return c;
+}
+
+template <typename F>
+size_t required_bytes(F f) {
+    char* p = nullptr;
+    f(p);
+    return reinterpret_cast<size_t>(p) + 128;
+}
+
+sgs::ViewParams make_view(int W, int H, const float* view, const float* proj, const float* campos,
+                          const float* bg, float tan_fovx, float tan_fovy, float scale_modifier, int D, int M,
+                          int prefiltered) {
+    sgs::ViewParams vp;
+    vp.view = view;
+    vp.proj = proj;
+    vp.campos = campos;
+    vp.bg = bg;
+    vp.W = W;
+    vp.H = H;
+    vp.tiles_x = (W + SGS_TILE_X - 1) / SGS_TILE_X;
+    vp.tiles_y = (H + SGS_TILE_Y - 1) / SGS_TILE_Y;
+    vp.tan_fovx = tan_fovx;
+    vp.tan_fovy = tan_fovy;
+    // $R/cuda_rasterizer/rasterizer_impl.cu:222-223 (float arithmetic on the host)
+    vp.focal_y = H / (2.0f * tan_fovy);
+    vp.focal_x = W / (2.0f * tan_fovx);
+    vp.scale_modifier = scale_modifier;
+    vp.sh_degree = D;
+    vp.sh_coeffs = M;
+    vp.prefiltered = prefiltered;
+    return vp;
+}
+
+// pinned landing pad for the 4-byte num_rendered read-back
+uint32_t* pinned_slot() {
+    thread_local uint32_t* slot = nullptr;
+    if (!slot) {
+        if (cudaHostAlloc(&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
+    }
+    return slot;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgs_abi_version(void) { return SGS_ABI_VERSION; }
+
+const char* sgs_last_error(void) { return g_last_error.c_str(); }
+
+int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present)))
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_mark_visible: null pointer");
+    sgs::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    SGS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resize_fn binning_buffer,
+                    void* binning_user, sgs_resize_fn image_buffer, void* image_user, int P, int D, int M,
+                    const float* background, int width, int height, const float* means3D, const float* shs,
+                    const float* colors_precomp, const float* opacities, const float* scales,
+                    float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                    const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                    float tan_fovy, int prefiltered, float* out_color, float* out_depth, int* radii, int flags,
+                    void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || width <= 0 || height <= 0) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: bad sizes");
+    if (P == 0) return 0;  // reference binding skips the call entirely ($R/rasterize_points.cu:80)
+    if (!geometry_buffer || !binning_buffer || !image_buffer)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: null resize callback");
+    if (!means3D || !opacities || !viewmatrix || !projmatrix || !cam_pos || !background || !out_color ||
+        !out_depth || !radii)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: null required pointer");
+    if (colors_precomp == nullptr && (shs == nullptr || M <= 0))
+        // $R/cuda_rasterizer/rasterizer_impl.cu:242-245 analogue: colours must come from somewhere
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: provide SHs or precomputed colors");
+    if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: provide scales+rotations or precomputed cov3D");
+    if (colors_precomp == nullptr && (D < 0 || D > 3 || (D + 1) * (D + 1) > M))
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: SH degree/coefficient mismatch");
+
+    const sgs::ViewParams vp = make_view(width, height, viewmatrix, projmatrix, cam_pos, background, tan_fovx,
+                                         tan_fovy, scale_modifier, D, M, prefiltered);
+    const size_t N = (size_t)width * height;
+    const size_t tiles = (size_t)vp.tiles_x * vp.tiles_y;
+
+    const size_t geom_bytes = required_bytes([&](char*& p) { carve_geom(p, (size_t)P); });
+    char* gchunk = geometry_buffer(geometry_user, geom_bytes);
+    if (!gchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: geometry buffer allocation failed");
+    sgs::GeomState g = carve_geom(gchunk, (size_t)P);
+
+    const size_t img_bytes = required_bytes([&](char*& p) { carve_image(p, N, tiles); });
+    char* ichunk = image_buffer(image_user, img_bytes);
+    if (!ichunk) return fail(SGS_ERR_ALLOC, "sgs_forward: image buffer allocation failed");
+    sgs::ImageState img = carve_image(ichunk, N, tiles);
+
+    sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                               radii, g, s);
+    SGS_CUDA_OK(sgs::launch_depth_sort_scan(P, g, s));
+
+    // The one device->host dependency of the path: the instance count sizes the binning buffer
+    // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
+    uint32_t* slot = pinned_slot();
+    uint32_t num_rendered = 0;
+    if (slot) {
+        SGS_CUDA_OK(cudaMemcpyAsync(slot, g.sorted_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        SGS_CUDA_OK(cudaStreamSynchronize(s));
+        num_rendered = *slot;
+    } else {
+        SGS_CUDA_OK(cudaMemcpyAsync(&num_rendered, g.sorted_offsets + (P - 1), sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, s));
+        SGS_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    const size_t R = num_rendered;
+    const int tile_bits = sgs::binning_tile_bits((int)tiles);
+    const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
+
+    const size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, R, tile_bits, keep); });
+    char* bchunk = binning_buffer(binning_user, bin_bytes);
+    if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
+    BinningCarve bc = carve_binning(bchunk, R, tile_bits, keep);
+
+    const uint32_t* point_list = nullptr;
+    SGS_CUDA_OK(sgs::launch_duplicate_sort_ranges(P, R, vp, radii, g, bc.b, img, &point_list, s));
+    SGS_CUDA_OK(cudaMemsetAsync(bc.header, point_list == bc.b.gauss_vals[1] ? 1 : 0, 4, s));
+    if (keep) SGS_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * tiles, s));
+
+    sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1,
+                           out_color, out_depth, s);
+    SGS_CUDA_OK(cudaGetLastError());
+    return (int64_t)R;
+}
+
+int sgs_backward(int P, int D, int M, int64_t R, const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                 float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                 const float* dL_dpix, float* dL_dmean2D, float* dL_dacc, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                 void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || R < 0 || width <= 0 || height <= 0) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: bad sizes");
+    if (P == 0) return 0;
+    if (!geom_buffer || !binning_buffer || !image_buffer)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null state buffer");
+    if (!means3D || !viewmatrix || !projmatrix || !campos || !background || !radii || !dL_dpix || !dL_dmean2D ||
+        !dL_dacc || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null required pointer");
+    if (shs != nullptr && M > 0 && !dL_dsh) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null dL_dsh");
+
+    const sgs::ViewParams vp = make_view(width, height, viewmatrix, projmatrix, campos, background, tan_fovx,
+                                         tan_fovy, scale_modifier, D, shs ? M : 0, 0);
+    const size_t N = (size_t)width * height;
+    const size_t tiles = (size_t)vp.tiles_x * vp.tiles_y;
+    sgs::GeomState g = carve_geom(geom_buffer, (size_t)P);
+    sgs::ImageState img = carve_image(image_buffer, N, tiles);
+    BinningCarve bc = carve_binning(binning_buffer, (size_t)R, sgs::binning_tile_bits((int)tiles), true);
+
+    SGS_CUDA_OK(cudaMemsetAsync(dL_dacc, 0, sizeof(float) * 12 * (size_t)P, s));
+    if (R > 0) sgs::launch_render_bwd(vp, bc.b, img, dL_dpix, dL_dacc, s);
+    const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
+    sgs::launch_preprocess_bwd(P, vp, means3D, radii, shs, cov3D_precomp ? nullptr : scales,
+                               cov3D_precomp ? nullptr : rotations, cov3D, g, dL_dacc, dL_dmean2D, dL_dopacity,
+                               dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, s);
+    (void)colors_precomp;
+    SGS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer, char* binning_buffer,
+                     char* image_buffer, uint32_t* tiles_touched, uint32_t* ranges, uint32_t* n_contrib,
+                     float* final_T, float* means2D, float* conic_opacity, float* rgbd, float* cov3D,
+                     uint32_t* tile_count, uint32_t* point_list, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return 0;
+    const size_t N = (size_t)width * height;
+    const int tx = (width + SGS_TILE_X - 1) / SGS_TILE_X, ty = (height + SGS_TILE_Y - 1) / SGS_TILE_Y;
+    const size_t tiles = (size_t)tx * ty;
+    const auto D2D = cudaMemcpyDeviceToDevice;
+    if (geom_buffer) {
+        sgs::GeomState g = carve_geom(geom_buffer, (size_t)P);
+        if (tiles_touched) SGS_CUDA_OK(cudaMemcpyAsync(tiles_touched, g.tiles_touched, 4 * (size_t)P, D2D, s));
+        if (means2D) SGS_CUDA_OK(cudaMemcpyAsync(means2D, g.means2D, 8 * (size_t)P, D2D, s));
+        if (conic_opacity) SGS_CUDA_OK(cudaMemcpyAsync(conic_opacity, g.conic_opacity, 16 * (size_t)P, D2D, s));
+        if (rgbd) SGS_CUDA_OK(cudaMemcpyAsync(rgbd, g.rgbd, 16 * (size_t)P, D2D, s));
+        if (cov3D) SGS_CUDA_OK(cudaMemcpyAsync(cov3D, g.cov3D, 24 * (size_t)P, D2D, s));
+    }
+    if (image_buffer) {
+        sgs::ImageState img = carve_image(image_buffer, N, tiles);
+        if (ranges) SGS_CUDA_OK(cudaMemcpyAsync(ranges, img.ranges, 8 * tiles, D2D, s));
+        if (n_contrib) SGS_CUDA_OK(cudaMemcpyAsync(n_contrib, img.n_contrib, 4 * N, D2D, s));
+        if (final_T) SGS_CUDA_OK(cudaMemcpyAsync(final_T, img.final_T, 4 * N, D2D, s));
+        if (tile_count) SGS_CUDA_OK(cudaMemcpyAsync(tile_count, img.tile_count, 4 * tiles, D2D, s));
+    }
+    if (binning_buffer && point_list && R > 0) {
+        BinningCarve bc = carve_binning(binning_buffer, (size_t)R, sgs::binning_tile_bits((int)tiles), false);
+        uint32_t sel = 0;
+        SGS_CUDA_OK(cudaMemcpyAsync(&sel, bc.header, 4, cudaMemcpyDeviceToHost, s));
+        SGS_CUDA_OK(cudaStreamSynchronize(s));
+        SGS_CUDA_OK(cudaMemcpyAsync(point_list, bc.b.gauss_vals[(sel & 1) ? 1 : 0], 4 * (size_t)R, D2D, s));
+    }
+    return 0;
+}
+
+}  // extern "C"

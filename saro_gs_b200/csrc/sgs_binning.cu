@@ -1,0 +1,160 @@
+// Tile binning: produces, for every 16x16 tile, the list of Gaussian instances that touch
+// it, ordered by (depth bits, Gaussian index) — the exact order the reference obtains
+// from one stable 64-bit radix sort of  key = tile<<32 | float_bits(depth)
+//   $R/cuda_rasterizer/rasterizer_impl.cu:70-111 (duplicateWithKeys)
+//   $R/cuda_rasterizer/rasterizer_impl.cu:299-309 (SortPairs on bits [0, 32+bit))
+//   $R/cuda_rasterizer/rasterizer_impl.cu:116-138 (identifyTileRanges)
+//
+// B200 design: a TWO-LEVEL sort that moves far fewer bytes through HBM.
+//   1. sort the P Gaussians (not the R >> P instances) by their 32-bit depth bits
+//      (stable => ties keep ascending Gaussian index);
+//   2. scan tiles_touched in that depth order and emit instances in depth order
+//      (key = tile id only, value = Gaussian index);
+//   3. one stable radix sort of the R instances on ceil(log2(#tiles)) bits (13 bits at
+//      1352x1014 => 2 CUB onesweep passes over 8-byte pairs instead of 6 passes over
+//      12-byte pairs).
+// A stable sort by tile of a depth-ordered stream is ordered by (tile, depth, index):
+// identical to the reference order, so tile ranges, n_contrib and compositing order are
+// bit-identical.
+#include "sgs_common.cuh"
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+namespace sgs {
+
+struct TilesInDepthOrder {
+    const uint32_t* tiles_touched;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& gid) const { return tiles_touched[gid]; }
+};
+
+void binning_geom_temp_bytes(int P, size_t* bytes) {
+    size_t a = 0, b = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, P, 0, 32);
+    TilesInDepthOrder op{nullptr};
+    auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, op);
+    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
+    *bytes = (a > b ? a : b) + 256;
+}
+
+void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes) {
+    size_t a = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int64_t)R, 0, tile_bits);
+    *bytes = a + 256;
+}
+
+// Step 1+2a: depth sort of Gaussians, then inclusive scan of tiles_touched in depth order.
+// On return (stream order) g.depth_vals[0] holds the depth-ordered Gaussian indices and
+// g.sorted_offsets the scan; num_rendered = sorted_offsets[P-1].
+cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
+    cub::DoubleBuffer<uint32_t> keys(g.depth_keys[0], g.depth_keys[1]);
+    cub::DoubleBuffer<uint32_t> vals(g.depth_vals[0], g.depth_vals[1]);
+    size_t tb = g.temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(g.temp, tb, keys, vals, P, 0, 32, s);
+    if (e != cudaSuccess) return e;
+    // 4 passes of 8 bits: the result lands back in buffer 0; keep the code robust anyway.
+    if (vals.Current() != g.depth_vals[0])
+        cudaMemcpyAsync(g.depth_vals[0], vals.Current(), sizeof(uint32_t) * (size_t)P, cudaMemcpyDeviceToDevice, s);
+    TilesInDepthOrder op{g.tiles_touched};
+    auto it = thrust::make_transform_iterator((const uint32_t*)g.depth_vals[0], op);
+    tb = g.temp_bytes;
+    return cub::DeviceScan::InclusiveSum(g.temp, tb, it, g.sorted_offsets, P, s);
+}
+
+// Step 2b: emit (tile id, Gaussian index) for every tile of every visible Gaussian, visiting
+// Gaussians in depth order.  Small rects are written by the owning thread; large rects are
+// written by the whole warp (coalesced), which removes the long divergent per-thread loops
+// of the reference's duplicateWithKeys.
+#define SGS_DUP_SMALL 8
+__global__ void __launch_bounds__(256)
+duplicate_kernel(int P, int tiles_x, int tiles_y, const uint32_t* __restrict__ order,
+                 const uint32_t* __restrict__ sorted_offsets, const uint32_t* __restrict__ tiles_touched,
+                 const float2* __restrict__ means2D, const int* __restrict__ radii,
+                 uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_vals) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t n = 0, off = 0, gid = 0;
+    uint2 rmin = {0, 0}, rmax = {0, 0};
+    if (k < P) {
+        gid = order[k];
+        n = tiles_touched[gid];
+        if (n > 0) {
+            off = (k == 0) ? 0u : sorted_offsets[k - 1];
+            get_rect(means2D[gid], radii[gid], rmin, rmax, tiles_x, tiles_y);
+        }
+    }
+    if (n > 0 && n <= SGS_DUP_SMALL) {
+        for (uint32_t y = rmin.y; y < rmax.y; y++)
+            for (uint32_t x = rmin.x; x < rmax.x; x++) {
+                tile_keys[off] = y * tiles_x + x;
+                gauss_vals[off] = gid;
+                off++;
+            }
+    }
+    unsigned big = __ballot_sync(0xFFFFFFFFu, n > SGS_DUP_SMALL);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t sn = __shfl_sync(0xFFFFFFFFu, n, src);
+        const uint32_t soff = __shfl_sync(0xFFFFFFFFu, off, src);
+        const uint32_t sgid = __shfl_sync(0xFFFFFFFFu, gid, src);
+        const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, rmin.x, src);
+        const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, rmin.y, src);
+        const uint32_t sw = __shfl_sync(0xFFFFFFFFu, rmax.x, src) - sx0;
+        for (uint32_t i = lane; i < sn; i += 32) {
+            const uint32_t yy = i / sw, xx = i - yy * sw;
+            tile_keys[soff + i] = (sy0 + yy) * tiles_x + (sx0 + xx);
+            gauss_vals[soff + i] = sgid;
+        }
+    }
+}
+
+// Step 4: per-tile [start,end) in the sorted instance list.
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(uint32_t R, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t cur = sorted_tiles[i];
+    if (i == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = sorted_tiles[i - 1];
+        if (cur != prev) {
+            ranges[prev].y = i;
+            ranges[cur].x = i;
+        }
+    }
+    if (i == R - 1) ranges[cur].y = R;
+}
+
+static int bits_for_tiles(int n_tiles) {
+    int b = 1;
+    while ((1 << b) < n_tiles) b++;
+    return b;
+}
+
+// Returns (through *point_list) the buffer holding the sorted Gaussian indices.
+cudaError_t launch_duplicate_sort_ranges(int P, size_t R, const ViewParams& vp, const int* radii, GeomState g,
+                                         BinningState b, ImageState img, const uint32_t** point_list,
+                                         cudaStream_t s) {
+    const int n_tiles = vp.tiles_x * vp.tiles_y;
+    cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s);
+    if (e != cudaSuccess) return e;
+    *point_list = b.gauss_vals[0];
+    if (R == 0) return cudaSuccess;
+    duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, vp.tiles_y, g.depth_vals[0], g.sorted_offsets,
+                                                    g.tiles_touched, g.means2D, radii, b.tile_keys[0],
+                                                    b.gauss_vals[0]);
+    cub::DoubleBuffer<uint32_t> keys(b.tile_keys[0], b.tile_keys[1]);
+    cub::DoubleBuffer<uint32_t> vals(b.gauss_vals[0], b.gauss_vals[1]);
+    size_t tb = b.temp_bytes;
+    e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
+    if (e != cudaSuccess) return e;
+    *point_list = vals.Current();
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, keys.Current(), img.ranges);
+    return cudaGetLastError();
+}
+
+int binning_tile_bits(int n_tiles) { return bits_for_tiles(n_tiles); }
+
+}  // namespace sgs

@@ -1,0 +1,245 @@
+// Forward per-Gaussian preprocess + markVisible.
+//
+// Follows, rule for rule (not line for line):
+//   near cull  z_view <= 0.2                          $R/cuda_rasterizer/auxiliary.h:139-164
+//   projection p_hom, p_w = 1/(w + 1e-7)              $R/cuda_rasterizer/forward.cu:196-200
+//   cov3D = (S R)^T (S R)                             $R/cuda_rasterizer/forward.cu:118-152
+//   EWA cov2D, +0.3 low-pass                          $R/cuda_rasterizer/forward.cu:74-113
+//   conic, 3-sigma radius, tile rect                  $R/cuda_rasterizer/forward.cu:216-237
+//   SH(deg<=3) -> RGB, +0.5, clamp mask               $R/cuda_rasterizer/forward.cu:20-71
+//
+// B200 design differences: per-view constants come from the kernel-parameter constant
+// bank (no per-thread pointer chasing); SH rows are fetched with 128-bit loads; all
+// outputs are SoA and coalesced; colour+depth are packed into one float4 so the render
+// kernel stages an instance with three 16/8-byte gathers; the depth-sort key of the
+// two-level binning (see sgs_binning.cu) is emitted here.
+#include "sgs_common.cuh"
+#include <cstdio>
+
+namespace sgs {
+
+struct V3 {
+    float x, y, z;
+};
+__forceinline__ __device__ V3 operator+(const V3& a, const V3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__forceinline__ __device__ V3 operator-(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__forceinline__ __device__ V3 operator*(float s, const V3& a) { return {s * a.x, s * a.y, s * a.z}; }
+__forceinline__ __device__ V3 operator+(const V3& a, float s) { return {a.x + s, a.y + s, a.z + s}; }
+
+template <bool VEC_SH>
+struct ShRow {
+    const float* base;  // row of this Gaussian: [M][3]
+    __forceinline__ __device__ V3 get(int k) const { return {base[3 * k], base[3 * k + 1], base[3 * k + 2]}; }
+};
+
+// SH evaluation on a row already held in registers (sh[k] as V3).
+__forceinline__ __device__ V3 eval_sh(int deg, const V3* sh, const V3& pos, const float* campos,
+                                      uint8_t& clamp_mask) {
+    V3 dir = {pos.x - campos[0], pos.y - campos[1], pos.z - campos[2]};
+    float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir = {dir.x / len, dir.y / len, dir.z / len};
+
+    V3 result = SGS_SH_C0 * sh[0];
+    if (deg > 0) {
+        float x = dir.x, y = dir.y, z = dir.z;
+        result = result - SGS_SH_C1 * y * sh[1] + SGS_SH_C1 * z * sh[2] - SGS_SH_C1 * x * sh[3];
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z;
+            float xy = x * y, yz = y * z, xz = x * z;
+            result = result + SGS_SH_C2_0 * xy * sh[4] + SGS_SH_C2_1 * yz * sh[5] +
+                     SGS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[6] + SGS_SH_C2_3 * xz * sh[7] +
+                     SGS_SH_C2_4 * (xx - yy) * sh[8];
+            if (deg > 2) {
+                result = result + SGS_SH_C3_0 * y * (3.0f * xx - yy) * sh[9] + SGS_SH_C3_1 * xy * z * sh[10] +
+                         SGS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[11] +
+                         SGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12] +
+                         SGS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[13] + SGS_SH_C3_5 * z * (xx - yy) * sh[14] +
+                         SGS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[15];
+            }
+        }
+    }
+    result = result + 0.5f;
+    clamp_mask = (uint8_t)((result.x < 0 ? 1 : 0) | (result.y < 0 ? 2 : 0) | (result.z < 0 ? 4 : 0));
+    return {fmaxf(result.x, 0.0f), fmaxf(result.y, 0.0f), fmaxf(result.z, 0.0f)};
+}
+
+__forceinline__ __device__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
+    Mat3 S = mat3_cols(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+    S.c[0][0] = mod * scale.x;
+    S.c[1][1] = mod * scale.y;
+    S.c[2][2] = mod * scale.z;
+    // quaternion used as given (callers normalise): (r, x, y, z)
+    float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+    Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                       2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                       2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    Mat3 M = mat3_mul(S, R);
+    Mat3 Sigma = mat3_mul(mat3_T(M), M);
+    cov3D[0] = Sigma.c[0][0];
+    cov3D[1] = Sigma.c[0][1];
+    cov3D[2] = Sigma.c[0][2];
+    cov3D[3] = Sigma.c[1][1];
+    cov3D[4] = Sigma.c[1][2];
+    cov3D[5] = Sigma.c[2][2];
+}
+
+__forceinline__ __device__ float3 cov2d_from_cov3d(const float3& mean, float focal_x, float focal_y, float tan_fovx,
+                                                   float tan_fovy, const float* cov3D, const float* view) {
+    float3 t = xform_point_4x3(mean, view);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+
+    Mat3 J = mat3_cols(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z),
+                       0.0f, focal_y / t.z, -(focal_y * t.y) / (t.z * t.z),
+                       0, 0, 0);
+    Mat3 Wm = mat3_cols(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
+    Mat3 T = mat3_mul(Wm, J);
+    Mat3 Vrk = mat3_cols(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+    Mat3 cov = mat3_mul(mat3_mul(mat3_T(T), mat3_T(Vrk)), T);
+    cov.c[0][0] += 0.3f;
+    cov.c[1][1] += 0.3f;
+    return {cov.c[0][0], cov.c[0][1], cov.c[1][1]};
+}
+
+template <bool VEC_SH>
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float* __restrict__ means3D,
+                      const float* __restrict__ scales, const float* __restrict__ rotations,
+                      const float* __restrict__ opacities, const float* __restrict__ shs,
+                      const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+                      int* __restrict__ radii, GeomState g) {
+    __shared__ ViewSmem cam;
+    stage_view(cam, vp);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+
+    // defaults for a Gaussian that takes no further part
+    int out_radius = 0;
+    uint32_t out_tiles = 0;
+    uint32_t out_key = 0xFFFFFFFFu;
+
+    const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    const float3 p_view = xform_point_4x3(p_orig, cam.view);
+
+    bool alive = !(p_view.z <= 0.2f);
+    if (!alive && vp.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+    }
+
+    if (alive) {
+        float4 p_hom = xform_point_4x4(p_orig, cam.proj);
+        float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+
+        float cov3D[6];
+        if (cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
+        } else {
+            const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+            cov3d_from_scale_rot(sc, vp.scale_modifier, q, cov3D);
+#pragma unroll
+            for (int i = 0; i < 6; i++) g.cov3D[6 * idx + i] = cov3D[i];
+        }
+
+        float3 cov = cov2d_from_cov3d(p_orig, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cov3D, cam.view);
+
+        float det = (cov.x * cov.z - cov.y * cov.y);
+        if (det != 0.0f) {
+            float det_inv = 1.f / det;
+            float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+            float mid = 0.5f * (cov.x + cov.z);
+            float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+            float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+            float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+            float2 point_image = {ndc2pix(p_proj.x, vp.W), ndc2pix(p_proj.y, vp.H)};
+            uint2 rmin, rmax;
+            get_rect(point_image, (int)my_radius, rmin, rmax, vp.tiles_x, vp.tiles_y);
+            uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
+            if (ntiles != 0) {
+                float3 rgb;
+                uint8_t cmask = 0;
+                if (colors_precomp == nullptr) {
+                    V3 sh[16];
+                    const int M = vp.sh_coeffs;
+                    if (VEC_SH) {
+                        // M == 16, row is 192 B and 16-B aligned: twelve 128-bit loads
+                        const float4* row = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
+                        float f[48];
+#pragma unroll
+                        for (int k = 0; k < 12; k++) {
+                            float4 v = __ldg(row + k);
+                            f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; k++) sh[k] = {f[3 * k], f[3 * k + 1], f[3 * k + 2]};
+                    } else {
+                        const float* row = shs + (size_t)idx * M * 3;
+                        const int ncoef = (vp.sh_degree + 1) * (vp.sh_degree + 1);
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            if (k < ncoef) sh[k] = {row[3 * k], row[3 * k + 1], row[3 * k + 2]};
+                            else sh[k] = {0.f, 0.f, 0.f};
+                        }
+                    }
+                    V3 c = eval_sh(vp.sh_degree, sh, V3{p_orig.x, p_orig.y, p_orig.z}, cam.campos, cmask);
+                    rgb = {c.x, c.y, c.z};
+                } else {
+                    rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
+                }
+                g.depths[idx] = p_view.z;
+                g.means2D[idx] = point_image;
+                g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
+                g.rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, p_view.z);
+                g.clamped[idx] = cmask;
+                out_radius = (int)my_radius;
+                out_tiles = ntiles;
+                out_key = __float_as_uint(p_view.z);
+            }
+        }
+    }
+    radii[idx] = out_radius;
+    g.tiles_touched[idx] = out_tiles;
+    g.depth_keys[0][idx] = out_key;
+    g.depth_vals[0][idx] = (uint32_t)idx;
+}
+
+void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
+                           const float* rotations, const float* opacities, const float* shs,
+                           const float* cov3D_precomp, const float* colors_precomp, int* radii, GeomState g,
+                           cudaStream_t s) {
+    if (P <= 0) return;
+    const int block = 256;
+    const int grid = (P + block - 1) / block;
+    const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0);
+    if (vec)
+        preprocess_fwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
+                                                          cov3D_precomp, colors_precomp, radii, g);
+    else
+        preprocess_fwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
+                                                           cov3D_precomp, colors_precomp, radii, g);
+}
+
+// markVisible: bool per point = (z_view > 0.2).  $R/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    const float3 pv = xform_point_4x3(p, view);
+    present[idx] = (pv.z <= 0.2f) ? 0 : 1;
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s) {
+    if (P <= 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+}
+
+}  // namespace sgs
