@@ -93,9 +93,11 @@ def config1_scene(P=10_000, seed=0):
     return Scene(means.float(), scales, rotations, opacities, shs, 3), cam
 
 
-def config2_scene(P=300_000, seed=0, width=1352, height=1014, fx=729.0, log_scale_mean=-3.6, log_scale_std=0.9):
+def config2_scene(P=300_000, seed=0, width=1352, height=1014, fx=729.0, log_scale_mean=-3.0, log_scale_std=0.9):
     """BASELINE.json configs[1] (headline): ~300k Gaussians @1352x1014, N3D-like, identity pose.
-    95% of the means uniform in the view frustum (z in [4.5, 40]), 5% behind/near the camera."""
+    95% of the means uniform in the view frustum (z in [4.5, 40]), 5% behind/near the camera.
+    log_scale_mean was tuned once (R/P ~ 10-15) and is frozen at -3.0:
+    num_rendered R = 3,927,052 (R/P = 13.1), 253,700 visible, mean n_contrib 359/pixel."""
     gen = torch.Generator().manual_seed(seed)
     tanx, tany = width / (2.0 * fx), height / (2.0 * fx)
     n_front = int(P * 0.95)
