@@ -103,6 +103,23 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
                      float* conic_opacity /*[P][4]*/, float* rgbd /*[P][4]*/, float* cov3D /*[P][6]*/,
                      uint32_t* tile_count /*[tiles]*/, uint32_t* point_list /*[R]*/, void* stream);
 
+/* Stage profiler (off by default): CUDA events on the launching stream around every stage.
+ * sgs_profile_read synchronises the device, returns the summed milliseconds and call counts per
+ * stage since the previous read, and the number of hand-written kernels this library launched. */
+#define SGS_STAGE_PREPROCESS_FWD 0
+#define SGS_STAGE_DEPTH_SORT_SCAN 1 /* CUB radix sort of P depth keys + CUB scan */
+#define SGS_STAGE_DUPLICATE 2
+#define SGS_STAGE_TILE_SORT 3       /* CUB radix sort of R tile keys */
+#define SGS_STAGE_TILE_RANGES 4
+#define SGS_STAGE_RENDER_FWD 5
+#define SGS_STAGE_BWD_ZERO 6        /* memset of the [P][12] accumulator */
+#define SGS_STAGE_RENDER_BWD 7
+#define SGS_STAGE_PREPROCESS_BWD 8
+#define SGS_PROFILE_STAGES 9
+void sgs_profile_enable(int on);
+int sgs_profile_read(float* stage_ms /*[SGS_PROFILE_STAGES]*/, int* stage_calls /*[SGS_PROFILE_STAGES]*/,
+                     uint64_t* own_kernel_launches);
+
 #ifdef __cplusplus
 }
 #endif

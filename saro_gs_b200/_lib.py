@@ -35,7 +35,12 @@ ABI = {
                           _vp, _vp, _vp,                                      # state buffers
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_debug_export": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp] + [_vp] * 10 + [_vp]),
+    "sgs_profile_enable": (None, [_i]),
+    "sgs_profile_read": (_i, [_vp, _vp, _vp]),
 }
+
+STAGES = ["preprocess_fwd", "depth_sort_scan", "duplicate", "tile_sort", "tile_ranges", "render_fwd", "bwd_zero",
+          "render_bwd", "preprocess_bwd"]
 
 _lib = None
 

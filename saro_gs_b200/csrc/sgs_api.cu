@@ -148,6 +148,46 @@ uint32_t* pinned_slot() {
     return slot;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stage profiler: CUDA events recorded on the launching stream around every stage, summed per
+// stage by sgs_profile_read().  Off by default; bench.py turns it on to obtain the per-kernel
+// durations behind its `roofline` object.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages = SGS_PROFILE_STAGES;
+constexpr int kPool = 8192;
+struct Profiler {
+    bool enabled = false;
+    cudaEvent_t ev[kPool][2];
+    int stage_of[kPool];
+    int created = 0;
+    int used = 0;
+    uint64_t own_launches = 0;  // hand-written kernels launched by this library since the last read
+};
+Profiler g_prof;
+std::mutex g_prof_mu;
+
+struct StageScope {
+    int slot = -1;
+    cudaStream_t s;
+    StageScope(int stage, cudaStream_t stream, int own_kernel_launches) : s(stream) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.own_launches += (uint64_t)own_kernel_launches;
+        if (!g_prof.enabled || g_prof.used >= kPool) return;
+        if (g_prof.used >= g_prof.created) {
+            if (cudaEventCreate(&g_prof.ev[g_prof.created][0]) != cudaSuccess) return;
+            if (cudaEventCreate(&g_prof.ev[g_prof.created][1]) != cudaSuccess) return;
+            g_prof.created++;
+        }
+        slot = g_prof.used++;
+        g_prof.stage_of[slot] = stage;
+        cudaEventRecord(g_prof.ev[slot][0], s);
+    }
+    ~StageScope() {
+        if (slot >= 0) cudaEventRecord(g_prof.ev[slot][1], s);
+    }
+};
+
 }  // namespace
 
 extern "C" {
@@ -205,9 +245,15 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (!ichunk) return fail(SGS_ERR_ALLOC, "sgs_forward: image buffer allocation failed");
     sgs::ImageState img = carve_image(ichunk, N, tiles);
 
-    sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
-                               radii, g, s);
-    SGS_CUDA_OK(sgs::launch_depth_sort_scan(P, g, s));
+    {
+        StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
+        sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                                   radii, g, s);
+    }
+    {
+        StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 0);
+        SGS_CUDA_OK(sgs::launch_depth_sort_scan(P, g, s));
+    }
 
     // The one device->host dependency of the path: the instance count sizes the binning buffer
     // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
@@ -231,13 +277,30 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
     BinningCarve bc = carve_binning(bchunk, R, tile_bits, keep);
 
-    const uint32_t* point_list = nullptr;
-    SGS_CUDA_OK(sgs::launch_duplicate_sort_ranges(P, R, vp, radii, g, bc.b, img, &point_list, s));
-    SGS_CUDA_OK(cudaMemsetAsync(bc.header, point_list == bc.b.gauss_vals[1] ? 1 : 0, 4, s));
+    const uint32_t* point_list = bc.b.gauss_vals[0];
+    const uint32_t* sorted_tiles = bc.b.tile_keys[0];
+    SGS_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, s));
     if (keep) SGS_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * tiles, s));
-
-    sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1,
-                           out_color, out_depth, s);
+    if (R > 0) {
+        {
+            StageScope sc(SGS_STAGE_DUPLICATE, s, 1);
+            SGS_CUDA_OK(sgs::launch_duplicate(P, vp, radii, g, bc.b, s));
+        }
+        {
+            StageScope sc(SGS_STAGE_TILE_SORT, s, 0);
+            SGS_CUDA_OK(sgs::launch_tile_sort(R, (int)tiles, bc.b, &point_list, &sorted_tiles, s));
+        }
+        {
+            StageScope sc(SGS_STAGE_TILE_RANGES, s, 1);
+            SGS_CUDA_OK(sgs::launch_tile_ranges(R, sorted_tiles, img, s));
+        }
+    }
+    SGS_CUDA_OK(cudaMemsetAsync(bc.header, point_list == bc.b.gauss_vals[1] ? 1 : 0, 4, s));
+    {
+        StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
+        sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1,
+                               out_color, out_depth, s);
+    }
     SGS_CUDA_OK(cudaGetLastError());
     return (int64_t)R;
 }
@@ -268,12 +331,21 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     sgs::ImageState img = carve_image(image_buffer, N, tiles);
     BinningCarve bc = carve_binning(binning_buffer, (size_t)R, sgs::binning_tile_bits((int)tiles), true);
 
-    SGS_CUDA_OK(cudaMemsetAsync(dL_dacc, 0, sizeof(float) * 12 * (size_t)P, s));
-    if (R > 0) sgs::launch_render_bwd(vp, bc.b, img, dL_dpix, dL_dacc, s);
+    {
+        StageScope sc(SGS_STAGE_BWD_ZERO, s, 0);
+        SGS_CUDA_OK(cudaMemsetAsync(dL_dacc, 0, sizeof(float) * 12 * (size_t)P, s));
+    }
+    if (R > 0) {
+        StageScope sc(SGS_STAGE_RENDER_BWD, s, 1);
+        sgs::launch_render_bwd(vp, bc.b, img, dL_dpix, dL_dacc, s);
+    }
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
-    sgs::launch_preprocess_bwd(P, vp, means3D, radii, shs, cov3D_precomp ? nullptr : scales,
-                               cov3D_precomp ? nullptr : rotations, cov3D, g, dL_dacc, dL_dmean2D, dL_dopacity,
-                               dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, s);
+    {
+        StageScope sc(SGS_STAGE_PREPROCESS_BWD, s, 1);
+        sgs::launch_preprocess_bwd(P, vp, means3D, radii, shs, cov3D_precomp ? nullptr : scales,
+                                   cov3D_precomp ? nullptr : rotations, cov3D, g, dL_dacc, dL_dmean2D, dL_dopacity,
+                                   dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, s);
+    }
     (void)colors_precomp;
     SGS_CUDA_OK(cudaGetLastError());
     return 0;
@@ -311,6 +383,30 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
         SGS_CUDA_OK(cudaStreamSynchronize(s));
         SGS_CUDA_OK(cudaMemcpyAsync(point_list, bc.b.gauss_vals[(sel & 1) ? 1 : 0], 4 * (size_t)R, D2D, s));
     }
+    return 0;
+}
+
+void sgs_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.enabled = on != 0;
+}
+
+int sgs_profile_read(float* stage_ms, int* stage_calls, uint64_t* own_kernel_launches) {
+    SGS_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < kStages; i++) {
+        if (stage_ms) stage_ms[i] = 0.f;
+        if (stage_calls) stage_calls[i] = 0;
+    }
+    for (int k = 0; k < g_prof.used; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[k][0], g_prof.ev[k][1]) != cudaSuccess) continue;
+        if (stage_ms) stage_ms[g_prof.stage_of[k]] += ms;
+        if (stage_calls) stage_calls[g_prof.stage_of[k]] += 1;
+    }
+    if (own_kernel_launches) *own_kernel_launches = g_prof.own_launches;
+    g_prof.used = 0;
+    g_prof.own_launches = 0;
     return 0;
 }
 

@@ -133,25 +133,31 @@ static int bits_for_tiles(int n_tiles) {
     return b;
 }
 
-// Returns (through *point_list) the buffer holding the sorted Gaussian indices.
-cudaError_t launch_duplicate_sort_ranges(int P, size_t R, const ViewParams& vp, const int* radii, GeomState g,
-                                         BinningState b, ImageState img, const uint32_t** point_list,
-                                         cudaStream_t s) {
-    const int n_tiles = vp.tiles_x * vp.tiles_y;
-    cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s);
-    if (e != cudaSuccess) return e;
-    *point_list = b.gauss_vals[0];
-    if (R == 0) return cudaSuccess;
+// Step 2b launcher: emit the depth-ordered (tile, Gaussian) stream.
+cudaError_t launch_duplicate(int P, const ViewParams& vp, const int* radii, GeomState g, BinningState b,
+                             cudaStream_t s) {
     duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, vp.tiles_y, g.depth_vals[0], g.sorted_offsets,
                                                     g.tiles_touched, g.means2D, radii, b.tile_keys[0],
                                                     b.gauss_vals[0]);
+    return cudaGetLastError();
+}
+
+// Step 3: stable sort by tile id.  Returns (through *point_list / *sorted_tiles) the buffers
+// holding the sorted Gaussian indices and tile ids.
+cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
+                             const uint32_t** sorted_tiles, cudaStream_t s) {
     cub::DoubleBuffer<uint32_t> keys(b.tile_keys[0], b.tile_keys[1]);
     cub::DoubleBuffer<uint32_t> vals(b.gauss_vals[0], b.gauss_vals[1]);
     size_t tb = b.temp_bytes;
-    e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
     *point_list = vals.Current();
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, keys.Current(), img.ranges);
+    *sorted_tiles = keys.Current();
+    return e;
+}
+
+// Step 4 launcher.
+cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, cudaStream_t s) {
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, sorted_tiles, img.ranges);
     return cudaGetLastError();
 }
 

@@ -213,9 +213,11 @@ void binning_geom_temp_bytes(int P, size_t* bytes);
 cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s);
 int  binning_tile_bits(int n_tiles);
 void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes);
-cudaError_t launch_duplicate_sort_ranges(int P, size_t R, const ViewParams& vp, const int* radii, GeomState g,
-                                         BinningState b, ImageState img, const uint32_t** point_list,
-                                         cudaStream_t s);
+cudaError_t launch_duplicate(int P, const ViewParams& vp, const int* radii, GeomState g, BinningState b,
+                             cudaStream_t s);
+cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
+                             const uint32_t** sorted_tiles, cudaStream_t s);
+cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,

@@ -69,6 +69,7 @@ def main():
     ap.add_argument("--configs", default="small,c1,c2")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--oracle", action="store_true", help="arbitrate gradients with the float64 CPU oracle")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     have_ref = ref_loader.available() and not args.no_ref
@@ -137,6 +138,25 @@ def main():
             res["depth_mismatch_px"] = int((d_n != d_r).sum().item())
             res["grads"] = {k: {"normrel": normrel(g_n[k], g_r[k]), "maxabs_rel": relerr(g_n[k], g_r[k])}
                             for k in g_n}
+
+        if args.oracle:
+            import numpy as np
+            from oracle import oracle
+            t0 = time.time()
+            orc = oracle.forward_scene(scene, cam, bg, precision="f64")
+            og = orc.backward(cot.cpu())
+            res["oracle_seconds"] = time.time() - t0
+            res["oracle_num_rendered"] = orc.num_rendered
+            res["oracle_radii_mismatch"] = int((orc.radii != r_n.cpu().numpy()).sum())
+            res["oracle_color_maxabs"] = float(np.abs(orc.color - c_n.cpu().numpy()).max())
+            res["oracle_depth_mismatch_px"] = int((orc.depth.astype(np.float32) != d_n.cpu().numpy()).sum())
+
+            def nrel(t, o):
+                t = t.cpu().numpy().astype(np.float64).reshape(o.shape)
+                return float(np.linalg.norm(t - o) / max(np.linalg.norm(o), 1e-300))
+            res["grads_vs_oracle_native"] = {k: nrel(g_n[k], og[k]) for k in g_n}
+            if have_ref:
+                res["grads_vs_oracle_ref"] = {k: nrel(g_r[k], og[k]) for k in g_r}
 
         # timings (fwd+bwd through the Python API)
         leaves = {k: getattr(scene, k).to(dev).clone().requires_grad_(True)
