@@ -9,6 +9,7 @@ and the current stream.
     mark_visible                   <- markVisible                     $R/rasterize_points.cu:196-215
 """
 import ctypes
+import threading
 
 import torch
 
@@ -34,21 +35,25 @@ def _f32c(t, dev):
     return t.contiguous()
 
 
-class _Resizer:
-    """Python side of sgs_resize_fn: grows a uint8 CUDA tensor, like resizeFunctional
-    ($R/rasterize_points.cu:27-33)."""
+# One persistent ctypes callback (creating CFUNCTYPE objects per call is slow and a bound-method
+# callback forms a reference cycle that keeps 100s of MB of state buffers alive until Python's
+# cyclic GC runs).  `user` carries the buffer slot; per-thread state makes it re-entrant.
+_tls = threading.local()
 
-    def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _lib.RESIZE_FN(self._resize)
 
-    def _resize(self, _user, nbytes):
-        try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
-        except Exception:  # out of memory: signal allocation failure through the ABI
-            return 0
+def _resize_dispatch(user, nbytes):
+    """Python side of sgs_resize_fn: like resizeFunctional ($R/rasterize_points.cu:27-33), but a
+    fresh uint8 CUDA tensor per call (the state must outlive the call for backward)."""
+    try:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=_tls.device)
+        _tls.bufs[int(user or 0)] = t
+        return t.data_ptr()
+    except Exception:  # e.g. out of memory: report allocation failure through the ABI
+        return 0
+
+
+_RESIZE_CB = _lib.RESIZE_FN(_resize_dispatch)
+_GEOM, _BINNING, _IMAGE = 1, 2, 3
 
 
 def _check(code, what):
@@ -80,13 +85,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     P = int(means3D.shape[0])
     H, W = int(image_height), int(image_width)
 
-    geom, binning, img = _Resizer(dev), _Resizer(dev), _Resizer(dev)
     if P == 0:
-        # $R/rasterize_points.cu:67-69,80: zero-filled outputs, nothing launched
+        # $R/rasterize_points.cu:67-69,80: zero-filled outputs, empty state buffers, nothing launched
         out_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.zeros((0,), dtype=torch.int32, device=dev)
         out_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
-        return 0, out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+        e = lambda: torch.empty(0, dtype=torch.uint8, device=dev)
+        return 0, out_color, radii, e(), e(), e(), out_depth
 
     means3D = _f32c(means3D, dev)
     colors = _f32c(colors, dev)
@@ -109,10 +114,12 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
     flags = (_lib.SGS_FLAG_KEEP_FOR_BACKWARD if keep_for_backward else 0) | \
             (_lib.SGS_FLAG_NO_TILE_CULL if _no_tile_cull else 0)
+    _tls.device = dev
+    _tls.bufs = bufs = {}
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rendered = lib.sgs_forward(
-            geom.cb, None, binning.cb, None, img.cb, None,
+            _RESIZE_CB, _GEOM, _RESIZE_CB, _BINNING, _RESIZE_CB, _IMAGE,
             P, int(degree), M,
             _ptr(background), W, H,
             _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier),
@@ -120,8 +127,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
             1 if prefiltered else 0,
             _ptr(out_color), _ptr(out_depth), _ptr(radii), flags, ctypes.c_void_p(stream))
+    _tls.bufs = None
     _check(rendered, "sgs_forward")
-    return int(rendered), out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+    return int(rendered), out_color, radii, bufs[_GEOM], bufs[_BINNING], bufs[_IMAGE], out_depth
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,

@@ -11,6 +11,8 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <chrono>
+#include <cstdlib>
 
 namespace {
 
@@ -139,6 +141,19 @@ sgs::ViewParams make_view(int W, int H, const float* view, const float* proj, co
     return vp;
 }
 
+// SGS_TRACE=1: print host-side timestamps (us) of sgs_forward phases to stderr (debug aid)
+bool trace_on() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SGS_TRACE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // pinned landing pad for the 4-byte num_rendered read-back
 uint32_t* pinned_slot() {
     thread_local uint32_t* slot = nullptr;
@@ -234,6 +249,8 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
                                          tan_fovy, scale_modifier, D, M, prefiltered);
     const size_t N = (size_t)width * height;
     const size_t tiles = (size_t)vp.tiles_x * vp.tiles_y;
+    const bool tr = trace_on();
+    const double t_enter = tr ? now_us() : 0;
 
     const size_t geom_bytes = required_bytes([&](char*& p) { carve_geom(p, (size_t)P); });
     char* gchunk = geometry_buffer(geometry_user, geom_bytes);
@@ -255,6 +272,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
         SGS_CUDA_OK(sgs::launch_depth_sort_scan(P, g, s));
     }
 
+    const double t_presync = tr ? now_us() : 0;
     // The one device->host dependency of the path: the instance count sizes the binning buffer
     // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
     uint32_t* slot = pinned_slot();
@@ -271,11 +289,13 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     const size_t R = num_rendered;
     const int tile_bits = sgs::binning_tile_bits((int)tiles);
     const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
+    const double t_synced = tr ? now_us() : 0;
 
     const size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, R, tile_bits, keep); });
     char* bchunk = binning_buffer(binning_user, bin_bytes);
     if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
     BinningCarve bc = carve_binning(bchunk, R, tile_bits, keep);
+    const double t_alloc = tr ? now_us() : 0;
 
     const uint32_t* point_list = bc.b.gauss_vals[0];
     const uint32_t* sorted_tiles = bc.b.tile_keys[0];
@@ -302,6 +322,9 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
                                out_color, out_depth, s);
     }
     SGS_CUDA_OK(cudaGetLastError());
+    if (tr)
+        fprintf(stderr, "[sgs_forward] pre-sync launches %.1f us | wait %.1f us | binning alloc %.1f us | post-sync launches %.1f us\n",
+                t_presync - t_enter, t_synced - t_presync, t_alloc - t_synced, now_us() - t_alloc);
     return (int64_t)R;
 }
 

@@ -56,6 +56,8 @@ def make_api(backend, supports_keep_flag=False):
 
             ctx.raster_settings = rs
             ctx.num_rendered = num_rendered
+            # radii/depth never receive a gradient: do not let autograd zero-fill [P] + [1,H,W] for them
+            ctx.set_materialize_grads(False)
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                                   binningBuffer, imgBuffer)
             return color, radii, depth
@@ -66,6 +68,9 @@ def make_api(backend, supports_keep_flag=False):
             rs = ctx.raster_settings
             (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
              imgBuffer) = ctx.saved_tensors
+            if grad_out_color is None:   # only depth was used downstream: depth carries no gradient
+                grad_out_color = torch.zeros((3, rs.image_height, rs.image_width), dtype=means3D.dtype,
+                                             device=means3D.device)
             args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                     rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos,
                     geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer)

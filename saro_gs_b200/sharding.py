@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing for the one place this path shards: independent views.
+
+Frames/cameras of one scene are independent units: the Gaussians are replicated
+on every rank, rank r renders views r, r+world, ... and the only collective is one all-reduce of a
+small metrics vector at the end (NCCL on GPUs, gloo in the CPU tests).  There is deliberately no
+data-path collective.  The reference has no distributed code at all.
+"""
+from typing import Callable, Iterable, List, Sequence
+
+import torch
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> range:
+    """Round-robin partition: every index in [0, n_items) belongs to exactly one rank."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    return range(rank, n_items, world)
+
+
+def render_shard(views: Sequence, rank: int, world: int, render_fn: Callable, metric_fn: Callable) -> torch.Tensor:
+    """Render this rank's share of `views` and return local sums [sum_metric..., count] (float64).
+
+    render_fn(view) -> outputs ; metric_fn(view, outputs) -> 1-D tensor/list of per-view metrics."""
+    acc = None
+    count = 0
+    for i in shard_indices(len(views), rank, world):
+        m = torch.as_tensor(metric_fn(views[i], render_fn(views[i])), dtype=torch.float64).flatten().cpu()
+        acc = m.clone() if acc is None else acc + m
+        count += 1
+    if acc is None:
+        acc = torch.zeros(0, dtype=torch.float64)
+    return torch.cat([acc, torch.tensor([float(count)], dtype=torch.float64)])
+
+
+def reduce_metrics(local: torch.Tensor, n_metrics: int, device=None) -> torch.Tensor:
+    """SUM all-reduce of [metrics..., count] across ranks (no-op when not distributed).
+    Ranks with no views contribute zeros of the right length."""
+    import torch.distributed as dist
+    vec = torch.zeros(n_metrics + 1, dtype=torch.float64)
+    if local.numel() == n_metrics + 1:
+        vec = local.clone()
+    elif local.numel() == 1:
+        vec[-1] = local[0]
+    else:
+        raise ValueError("metric vector length mismatch")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if device is not None:
+            vec = vec.to(device)
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        vec = vec.cpu()
+    return vec
+
+
+def mean_metrics(total: torch.Tensor) -> List[float]:
+    """[sum..., count] -> per-view means."""
+    n = max(float(total[-1]), 1.0)
+    return [float(v) / n for v in total[:-1]]

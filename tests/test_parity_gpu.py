@@ -1,0 +1,268 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(libsaro_gs_b200.so via saro_gs_b200.backend); three independent checkers:
+  1. golden fixtures = outputs of the compiled unmodified reference (tests/golden/*.npz);
+  2. the compiled reference itself, live, when oracle/_ref travelled to the box;
+  3. the float64 CPU oracle (oracle/splat_oracle.c).
+Bars: integer state (radii, tiles_touched, ranges, point_list, n_contrib) bit-exact; forward
+colour/depth/final_T bit-exact against the reference (the kernels reproduce its float expression
+trees); gradients within 1e-4 of the max entry (float atomics in the reference make element-wise
+bit equality impossible — the float64 oracle arbitrates)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import SMALL_CASES, inputs_of, load, maxrel, normrel
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-4          # north_star: "within 1e-4 relative"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def sgs(native_lib):
+    import saro_gs_b200
+    return saro_gs_b200
+
+
+def settings_from(sgs, d, dev, prefiltered=False):
+    t = lambda k: torch.from_numpy(np.asarray(d[k])).to(dev)
+    return sgs.GaussianRasterizationSettings(int(d["height"]), int(d["width"]), float(d["tanfovx"]),
+                                             float(d["tanfovy"]), t("bg"), float(d["scale_modifier"]),
+                                             t("viewmatrix"), t("projmatrix"), int(d["sh_degree"]), t("campos"),
+                                             prefiltered)
+
+
+def run_native(sgs, d, dev, Rast=None):
+    ins = inputs_of(d)
+    leaves = {k: v.to(dev).clone().requires_grad_(True) for k, v in ins.items()}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    rs = settings_from(sgs, d, dev)
+    kw = {("cov3D_precomp" if k == "cov3D_precomp" else k): v for k, v in leaves.items()}
+    color, radii, depth = (Rast or sgs.GaussianRasterizer)(rs)(means2D=means2D, **kw)
+    color.backward(torch.from_numpy(d["cotangent"]).to(dev))
+    torch.cuda.synchronize()
+    grads = {k: v.grad.cpu().numpy() for k, v in leaves.items()}
+    grads["means2D"] = means2D.grad.cpu().numpy()
+    return color.detach().cpu().numpy(), radii.cpu().numpy(), depth.detach().cpu().numpy(), grads, leaves, rs
+
+
+def native_state(sgs, d, dev, **kw):
+    ins = {k: v.to(dev) for k, v in inputs_of(d).items()}
+    rs = settings_from(sgs, d, dev)
+    e = torch.Tensor([])
+    out = sgs._C.rasterize_gaussians(rs.bg, ins["means3D"], ins.get("colors_precomp", e), ins["opacities"],
+                                     ins.get("scales", e), ins.get("rotations", e), rs.scale_modifier,
+                                     ins.get("cov3D_precomp", e), rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                                     rs.tanfovy, rs.image_height, rs.image_width, ins.get("shs", e), rs.sh_degree,
+                                     rs.campos, False, **kw)
+    R, color, radii, gb, bb, ib, depth = out
+    st = sgs._C.debug_export(ins["means3D"].shape[0], rs.image_width, rs.image_height, R, gb, bb, ib)
+    return R, color, radii, depth, {k: v.cpu().numpy() for k, v in st.items()}
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_forward_bit_exact_vs_reference_golden(sgs, dev, name):
+    d = load(name)
+    R, color, radii, depth, st = native_state(sgs, d, dev)
+    assert R == int(d["num_rendered"])
+    assert np.array_equal(radii.cpu().numpy(), d["out_radii"])
+    assert np.array_equal(st["tiles_touched"], d["tiles_touched"])
+    assert np.array_equal(st["ranges"], d["ranges"])
+    assert np.array_equal(st["point_list"], d["point_list"])
+    assert np.array_equal(st["n_contrib"], d["n_contrib"])
+    assert np.array_equal(st["final_T"], d["final_T"])
+    assert np.array_equal(color.cpu().numpy(), d["out_color"])       # bit-exact image
+    assert np.array_equal(depth.cpu().numpy(), d["out_depth"])
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_backward_vs_reference_golden_and_oracle(sgs, dev, oracle_mod, name):
+    d = load(name)
+    color, radii, depth, grads, _, _ = run_native(sgs, d, dev)
+    assert np.array_equal(color, d["out_color"])
+    ins = inputs_of(d)
+    orc = oracle_mod.forward(ins["means3D"], ins["opacities"], d["viewmatrix"], d["projmatrix"], d["campos"],
+                             d["bg"], int(d["width"]), int(d["height"]), float(d["tanfovx"]), float(d["tanfovy"]),
+                             sh_degree=int(d["sh_degree"]), shs=ins.get("shs"),
+                             colors_precomp=ins.get("colors_precomp"), scales=ins.get("scales"),
+                             rotations=ins.get("rotations"), cov3D_precomp=ins.get("cov3D_precomp"),
+                             scale_modifier=float(d["scale_modifier"]), precision="f64")
+    og = orc.backward(d["cotangent"])
+    okey = {"colors_precomp": "colors", "cov3D_precomp": "cov3D"}
+    for k, got in grads.items():
+        ref = d["grad_" + k]
+        assert maxrel(got, ref) < GRAD_TOL, (k, "vs reference golden", maxrel(got, ref))
+        o = og[okey.get(k, k)].reshape(ref.shape)
+        assert maxrel(got, o) < GRAD_TOL, (k, "vs float64 oracle", maxrel(got, o))
+        assert normrel(got, o) < 1e-3, (k, normrel(got, o))
+
+
+@pytest.mark.parametrize("name", ["small_sh3", "small_big_splats", "small_precomp_color"])
+def test_tile_culling_is_exact(sgs, dev, name):
+    """The staged ellipse/tile cull and the exp() short-circuit must not change a single bit."""
+    d = load(name)
+    _, c0, r0, d0, s0 = native_state(sgs, d, dev)
+    _, c1, r1, d1, s1 = native_state(sgs, d, dev, _no_tile_cull=True)
+    assert torch.equal(c0, c1) and torch.equal(d0, d1) and torch.equal(r0, r1)
+    assert np.array_equal(s0["n_contrib"], s1["n_contrib"]) and np.array_equal(s0["final_T"], s1["final_T"])
+    assert s0["tile_count"].sum() <= s1["tile_count"].sum()
+
+
+def test_inference_forward_equals_training_forward(sgs, dev):
+    d = load("small_sh3")
+    _, c0, _, d0, _ = native_state(sgs, d, dev, keep_for_backward=True)
+    _, c1, _, d1, _ = native_state(sgs, d, dev, keep_for_backward=False)
+    assert torch.equal(c0, c1) and torch.equal(d0, d1)
+    with torch.no_grad():
+        ins = {k: v.to(dev) for k, v in inputs_of(d).items()}
+        rs = settings_from(sgs, d, dev)
+        c2, _, d2 = sgs.GaussianRasterizer(rs)(means2D=torch.zeros_like(ins["means3D"]), **ins)
+    assert torch.equal(c0, c2) and torch.equal(d0, d2)
+
+
+def test_live_reference_ab(sgs, dev):
+    """Same inputs through the compiled unmodified reference, when it travelled to this box."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not present")
+    RefRast = ref_loader.ref_api()[1]
+    for name in ("small_sh3", "small_precomp_cov"):
+        d = load(name)
+        cn, rn, dn, gn, _, _ = run_native(sgs, d, dev)
+        cr, rr, dr, gr, _, _ = run_native(sgs, d, dev, Rast=RefRast)
+        assert np.array_equal(cn, cr) and np.array_equal(rn, rr) and np.array_equal(dn, dr)
+        for k in gn:
+            assert maxrel(gn[k], gr[k]) < GRAD_TOL, (name, k, maxrel(gn[k], gr[k]))
+
+
+def _sha(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("cfg", ["config1_fwd", "config2_fwd"])
+def test_full_size_bit_exact_tile_counts(sgs, dev, cfg):
+    """BASELINE.json configs[0]/[1] at full size: radii, tile counts, n_contrib, image and depth hash-equal
+    to the reference (north_star: 'bit-exact tile counts')."""
+    from saro_gs_b200 import synthetic
+    d = load(cfg)
+    scene, cam = synthetic.config1_scene() if cfg == "config1_fwd" else synthetic.config2_scene()
+    e = torch.Tensor([])
+    args = (torch.zeros(3, device=dev), scene.means3D.to(dev), e, scene.opacities.to(dev), scene.scales.to(dev),
+            scene.rotations.to(dev), 1.0, e, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.tanfovx, cam.tanfovy,
+            cam.height, cam.width, scene.shs.to(dev), scene.sh_degree, cam.campos.to(dev), False)
+    R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(*args)
+    st = sgs._C.debug_export(scene.means3D.shape[0], cam.width, cam.height, R, gb, bb, ib)
+    assert R == int(d["num_rendered"])
+    assert _sha(radii) == str(d["sha_radii"])
+    assert _sha(st["tiles_touched"]) == str(d["sha_tiles_touched"])
+    assert _sha(st["n_contrib"]) == str(d["sha_n_contrib"])
+    assert _sha(color) == str(d["sha_color"])
+    assert _sha(depth) == str(d["sha_depth"])
+    # size-independent properties
+    rng = st["ranges"].long()
+    assert int((rng[:, 1] - rng[:, 0]).sum()) == R == int(st["tiles_touched"].long().sum())
+    assert bool((st["tile_count"].long() <= (rng[:, 1] - rng[:, 0])).all())
+
+
+def test_full_size_backward_properties(sgs, dev):
+    """configs[1] backward at full size: linear in the cotangent, zero for culled Gaussians,
+    deterministic forward."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene()
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), scene.sh_degree,
+                                           cam.campos.to(dev), False)
+    leaves = {k: getattr(scene, k).to(dev).requires_grad_(True)
+              for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+
+    def grads(cot):
+        for p in list(leaves.values()) + [m2d]:
+            p.grad = None
+        color, radii, depth = sgs.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d,
+                                                        opacities=leaves["opacities"], shs=leaves["shs"],
+                                                        scales=leaves["scales"], rotations=leaves["rotations"])
+        color.backward(cot)
+        return color.detach(), radii, {k: v.grad.clone() for k, v in leaves.items()}
+
+    gen = torch.Generator().manual_seed(3)
+    a = (torch.randn(3, cam.height, cam.width, generator=gen) / (3 * cam.height * cam.width)).to(dev)
+    b = (torch.randn(3, cam.height, cam.width, generator=gen) / (3 * cam.height * cam.width)).to(dev)
+    c1, radii, ga = grads(a)
+    c2, _, gb = grads(b)
+    _, _, gab = grads(2.0 * a - 0.5 * b)
+    assert torch.equal(c1, c2)                                   # forward is deterministic
+    culled = radii == 0
+    assert int(culled.sum()) > 0
+    for k in ga:
+        want = 2.0 * ga[k] - 0.5 * gb[k]
+        assert maxrel(gab[k].cpu().numpy(), want.cpu().numpy()) < GRAD_TOL, k
+        assert not gab[k][culled].any(), k                       # culled Gaussians get exact zeros
+    assert not m2d.grad[:, 2].any()                              # dL/dmean2D.z is always 0
+
+
+def test_edge_cases(sgs, dev):
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.small_scene(P=64, seed=9)
+    bg = torch.tensor([0.2, 0.4, 0.6], device=dev)
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, bg, 1.0,
+                                           cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    rast = sgs.GaussianRasterizer(rs)
+    # P == 0: zeros (not background), empty radii — SURVEY.md Appendix A.2
+    z = lambda *s: torch.zeros(*s, device=dev)
+    color, radii, depth = rast(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), shs=z(0, 16, 3), scales=z(0, 3),
+                               rotations=z(0, 4))
+    assert color.shape == (3, cam.height, cam.width) and not color.any() and not depth.any() and radii.numel() == 0
+    # everything culled: background, depth 15, radii 0, zero grads
+    m = z(8, 3).requires_grad_(True)
+    color, radii, depth = rast(means3D=m, means2D=z(8, 3), opacities=torch.ones(8, 1, device=dev),
+                               colors_precomp=torch.ones(8, 3, device=dev), scales=torch.ones(8, 3, device=dev) * .1,
+                               rotations=torch.tensor([[1.0, 0, 0, 0]], device=dev).repeat(8, 1))
+    color.sum().backward()
+    assert torch.equal(color, bg[:, None, None].expand_as(color)) and (depth == 15.0).all() and not radii.any()
+    assert not m.grad.any()
+    # markVisible == (z_view > 0.2)
+    vis = rast.markVisible(scene.means3D.to(dev))
+    assert vis.dtype == torch.bool and torch.equal(vis.cpu(), scene.means3D[:, 2] > 0.2)
+    # non-contiguous / strided inputs are accepted like the reference's .contiguous()
+    big = torch.randn(64, 6, device=dev)
+    color2, _, _ = rast(means3D=scene.means3D.to(dev), means2D=z(64, 3), opacities=scene.opacities.to(dev),
+                        colors_precomp=big[:, ::2].abs(), scales=scene.scales.to(dev), rotations=scene.rotations.to(dev))
+    color3, _, _ = rast(means3D=scene.means3D.to(dev), means2D=z(64, 3), opacities=scene.opacities.to(dev),
+                        colors_precomp=big[:, ::2].abs().contiguous(), scales=scene.scales.to(dev),
+                        rotations=scene.rotations.to(dev))
+    assert torch.equal(color2, color3)
+
+
+def test_unmodified_reference_style_caller(sgs, dev):
+    """The call pattern of renderer/__init__.py:119-127,191-226 of the reference: keyword call,
+    screenspace_points.retain_grad(), second pass with colors_precomp, through the drop-in module name."""
+    from diff_gaussian_rasterization_ch3 import GaussianRasterizationSettings, GaussianRasterizer
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.small_scene(P=256, seed=11)
+    rs = GaussianRasterizationSettings(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx,
+                                       tanfovy=cam.tanfovy, bg=torch.zeros(3, device=dev), scale_modifier=1.0,
+                                       viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev),
+                                       sh_degree=3, campos=cam.campos.to(dev), prefiltered=False)
+    rasterizer = GaussianRasterizer(raster_settings=rs)
+    means3D = scene.means3D.to(dev).requires_grad_(True)
+    screenspace_points = torch.zeros_like(means3D, requires_grad=True) + 0
+    screenspace_points.retain_grad()
+    rendered_image, radii, depth = rasterizer(means3D=means3D, means2D=screenspace_points, shs=scene.shs.to(dev),
+                                              colors_precomp=None, opacities=scene.opacities.to(dev),
+                                              scales=scene.scales.to(dev), rotations=scene.rotations.to(dev),
+                                              cov3D_precomp=None)
+    rendered_image.mean().backward()
+    assert screenspace_points.grad is not None and screenspace_points.grad[radii > 0].abs().sum() > 0
+    lifespan = torch.rand(256, 1, device=dev)
+    img2, _, _ = rasterizer(means3D=means3D, means2D=screenspace_points, shs=None,
+                            colors_precomp=lifespan.expand(-1, 3), opacities=scene.opacities.to(dev),
+                            scales=scene.scales.to(dev), rotations=scene.rotations.to(dev), cov3D_precomp=None)
+    assert img2.shape == rendered_image.shape and torch.isfinite(img2).all()
