@@ -69,6 +69,16 @@ __forceinline__ __device__ float power_threshold(float o) {
     return -logf(255.f * o) - 1e-3f;
 }
 
+__forceinline__ __device__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__forceinline__ __device__ float pin_reg(float v) {
+    asm volatile("" : "+f"(v));
+    return v;
+}
+
 template <bool WRITE_PACKED, bool TILE_CULL>
 __global__ void __launch_bounds__(SGS_TILE_PIX)
 render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
@@ -77,9 +87,10 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                   float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                   uint32_t* __restrict__ tile_count, PackedInst* __restrict__ packed,
                   float* __restrict__ out_color, float* __restrict__ out_depth) {
-    __shared__ float4 s_a[SGS_TILE_PIX];  // x, y, A, B
-    __shared__ float4 s_b[SGS_TILE_PIX];  // C, opacity, thr, list_pos(bits)
-    __shared__ float4 s_c[SGS_TILE_PIX];  // r, g, b, depth
+    __shared__ float4 s_stage[3 * SGS_TILE_PIX];
+    float4* const s_a = s_stage;                     // x, y, A, B
+    float4* const s_b = s_stage + SGS_TILE_PIX;      // C, opacity, thr, list_pos(bits)
+    float4* const s_c = s_stage + 2 * SGS_TILE_PIX;  // r, g, b, depth
     __shared__ uint32_t s_wcount[SGS_TILE_PIX / 32];
 
     const int tid = threadIdx.x;
@@ -92,7 +103,10 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const uint32_t py = ty0 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
-    const float2 pixf = {(float)px, (float)py};
+    const float2 pixf = {pin_reg((float)px), pin_reg((float)py)};
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(s_stage);
+    asm volatile("" : "+r"(sa));   // keep the shared-window base in a register (no re-derivation in the loop)
+    constexpr uint32_t kB = SGS_TILE_PIX * 16u, kC = 2u * SGS_TILE_PIX * 16u;
 
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -149,9 +163,9 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
         __syncthreads();
 
         // ---- composite -------------------------------------------------------------------
-        for (uint32_t j = 0; !done && j < total; j++) {
-            const float4 a = s_a[j];
-            const float4 b = s_b[j];
+        for (uint32_t j = 0, off = 0; !done && j < total; j++, off += 16u) {
+            const float4 a = lds128(sa + off);
+            const float4 b = lds128(sa + off + kB);
             const float2 d = {a.x - pixf.x, a.y - pixf.y};
             const float power = -0.5f * (a.z * d.x * d.x + b.x * d.y * d.y) - a.w * d.x * d.y;
             if (power > 0.0f) continue;
@@ -163,7 +177,7 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 done = true;
                 continue;
             }
-            const float4 c = s_c[j];
+            const float4 c = lds128(sa + off + kC);
             C[0] += c.x * alpha * T;
             C[1] += c.y * alpha * T;
             C[2] += c.z * alpha * T;

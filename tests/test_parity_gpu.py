@@ -203,7 +203,8 @@ def test_full_size_backward_properties(sgs, dev):
     assert int(culled.sum()) > 0
     for k in ga:
         want = 2.0 * ga[k] - 0.5 * gb[k]
-        assert maxrel(gab[k].cpu().numpy(), want.cpu().numpy()) < GRAD_TOL, k
+        # property check (two float-atomic sums + a float32 linear combination): looser than the parity bar
+        assert maxrel(gab[k].cpu().numpy(), want.cpu().numpy()) < 5e-4, k
         assert not gab[k][culled].any(), k                       # culled Gaussians get exact zeros
     assert not m2d.grad[:, 2].any()                              # dL/dmean2D.z is always 0
 
