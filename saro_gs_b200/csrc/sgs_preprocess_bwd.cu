@@ -7,8 +7,11 @@
 //   SH backward (clamp mask, dL/dsh, view-direction term into dL/dmean3D)       $R/cuda_rasterizer/backward.cu:20-139
 //   dL/dcov3D -> dL/dscale, dL/dquaternion (no normalisation Jacobian)          $R/cuda_rasterizer/backward.cu:278-341
 //
-// Inputs: `acc` [P][12] = per-Gaussian sums produced by the backward render kernel
-// (slots: 0,1 dmean2D.xy | 2,3,4 dconic A,B,C | 5 dopacity | 6,7,8 dcolour).
+// Inputs: `acc` [P][12] = per-Gaussian MOMENT sums produced by the backward render kernel over all
+// blended pixel x instance pairs, with g = G dL/dalpha, w = alpha T, d = mean2D - pixel:
+//   slots 0..5 = sum g dx, sum g dy, sum g dx^2, sum g dx dy, sum g dy^2, sum g ; 6..8 = sum w dL/dpix[c].
+// The per-Gaussian factors of $R/cuda_rasterizer/backward.cu:536-554 (opacity, conic, 0.5W/0.5H, -0.5) are
+// applied here, once per Gaussian, instead of once per pair.
 // Every output element is written here (zeros for culled Gaussians), so callers pass
 // uninitialised tensors — no memset traffic for the ~300 B/Gaussian of outputs.
 #include "sgs_common.cuh"
@@ -39,7 +42,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       const int* __restrict__ radii, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ cov3Ds, const uint8_t* __restrict__ clamped,
-                      const float* __restrict__ acc, float* __restrict__ dL_dmean2D,
+                      const float4* __restrict__ conic_opacity, const float* __restrict__ acc, float* __restrict__ dL_dmean2D,
                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
@@ -64,9 +67,14 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     if (visible) {
         const float4* arow = reinterpret_cast<const float4*>(acc + (size_t)idx * 12);
         const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
-        o_mean2D[0] = a0.x;
-        o_mean2D[1] = a0.y;
-        const float3 dL_dconic = {a0.z, a0.w, a1.x};
+        const float4 co = conic_opacity[idx];   // A, B, C, opacity
+        // $R/cuda_rasterizer/backward.cu:460-461 (double product rounded to float once)
+        const float ddelx_dx = (float)(0.5 * vp.W), ddely_dy = (float)(0.5 * vp.H);
+        const float Sx = a0.x, Sy = a0.y, Sxx = a0.z, Sxy = a0.w, Syy = a1.x;
+        o_mean2D[0] = -co.w * ddelx_dx * (co.x * Sx + co.y * Sy);
+        o_mean2D[1] = -co.w * ddely_dy * (co.z * Sy + co.y * Sx);
+        const float hw = -0.5f * co.w;
+        const float3 dL_dconic = {hw * Sxx, hw * Sxy, hw * Syy};
         o_opacity = a1.y;
         o_color[0] = a1.z;
         o_color[1] = a1.w;
@@ -338,11 +346,11 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
                      ((reinterpret_cast<size_t>(dL_dsh) & 15) == 0);
     if (vec)
         preprocess_bwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
-                                                          g.clamped, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
+                                                          g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
     else
         preprocess_bwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
-                                                           g.clamped, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
+                                                           g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
                                                            dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
 }
 

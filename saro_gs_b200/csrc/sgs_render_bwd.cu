@@ -7,25 +7,26 @@
 //   dL/dmean2D (scaled by 0.5W, 0.5H), dL/dconic (A,B,C), dL/dopacity.
 //
 // B200 design (the reference issues 9 global float atomics per contributing pixel x instance,
-// SURVEY.md §2.1):
-//   * reads the dense tile-ordered `PackedInst` list written by the forward kernel with
-//     coalesced 16-byte loads (no index gathers, tile-culled instances never appear);
-//   * each warp owns an 8x4 pixel patch and walks the staged batch on its own: it starts at the
-//     last record that any of its pixels blended (binary search on the sorted list positions),
-//     so records behind every pixel's last contributor cost nothing;
-//   * the 9 partial derivatives of an instance are reduced across the 32 pixels of a warp
-//     with a 12-shuffle "transposing" butterfly (values are split between lane halves at
-//     every step instead of reducing each value with 5 shuffles), only when at least one
-//     lane contributes;
-//   * one RED per value per (warp, instance) lands in a [P][12] accumulator (48-byte rows)
-//     => 32x fewer L2 atomics than the reference.
-//   The kernel is FP32-issue bound (ncu: issue active 90%), so the inner loop is written to keep
-//   the not-contributing path at ~a dozen instructions.
-#include "sgs_common.cuh"
+// SURVEY.md §2.1; the kernel is FP32-issue bound, so everything below is about instructions per
+// blended pair):
+//   * reads the dense tile-ordered `PackedInst` list written by the forward kernel with coalesced
+//     16-byte loads (no index gathers, culled instances never appear);
+//   * 128 threads per tile, 2 vertically adjacent pixels per thread, warp = 8x8 quadrant; packed f32x2
+//     evaluation of the quadratic form (sgs_render_common.cuh);
+//   * per-warp visit bitmaps: a warp only visits instances whose quadrant mask has its bit AND whose
+//     list position is below the last contributor of some pixel of the warp;
+//   * per pair only what depends on the pixel is computed:  g = G dL/dalpha  and  w = alpha T ;
+//     the warp accumulates the MOMENTS  sum g, sum g dx, sum g dy, sum g dx^2, sum g dx dy, sum g dy^2
+//     and  sum w dL/dpix[c]  — the multiplications by opacity, conic and 0.5W/0.5H happen once per
+//     Gaussian in the fused backward-preprocess kernel;
+//   * the accum_rec recursion is carried as ONE scalar  a = sum_c accum_rec[c] dL/dpix[c]  (the
+//     reference carries 3 colours and re-dots them with dL/dpix for every pair);
+//   * the 9 sums are reduced across the warp's 64 pixels with a 12-shuffle "transposing" butterfly,
+//     then one RED.ADD.F32 per value per (warp, instance) into a [P][12] accumulator
+//     => 64x fewer L2 atomics than the reference.
+#include "sgs_render_common.cuh"
 
 namespace sgs {
-
-#define SGS_BWD_BATCH 256
 
 // send `hi` to the partner if this lane keeps `lo`, and vice versa; returns kept + received
 __forceinline__ __device__ float xsplit(float lo, float hi, bool upper, int xorm) {
@@ -34,67 +35,90 @@ __forceinline__ __device__ float xsplit(float lo, float hi, bool upper, int xorm
     return keep + __shfl_xor_sync(0xFFFFFFFFu, send, xorm);
 }
 
-// 128-bit / 32-bit shared-memory loads from a 32-bit shared-window address.  Using explicit
-// shared addresses keeps nvcc from re-deriving the generic->shared base (S2R SR_CgaCtaId + LEA)
-// inside the hot loop.
-__forceinline__ __device__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
+struct BwdPix {
+    float T;           // transmittance in front of the instance being visited
+    float a_rec;       // sum_c accum_rec[c] * dL/dpix[c]
+    float last_alpha;  // alpha of the previously visited (= next deeper) blended instance
+    float last_cd;     // its colour . dL/dpix
+    float last_om;     // 1 - last_alpha
+    float d0, d1, d2;  // dL/dpix
+    float bgT;         // -T_final * (bg . dL/dpix)
+    uint32_t lc;       // n_contrib of the pixel
+};
+
+// one pixel x one instance: returns g = G * dL/dalpha and w = alpha * T (0, 0 when the pair did not blend)
+__forceinline__ __device__ void grad_pixel(BwdPix& s, float power, float o, const float4 c, float& g, float& w) {
+    const float G = expf(power);
+    const float alpha = min(0.99f, o * G);
+    if (alpha < 1.0f / 255.0f) return;
+    const float om = 1.f - alpha;       // in [0.01, 1]: the approximate reciprocal is safe (<= 1 ulp)
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
+    s.T *= inv;                          // $R/.../backward.cu:503
+    s.a_rec = fmaf(s.last_alpha, s.last_cd, s.last_om * s.a_rec);   // :515-519, dotted with dL/dpix
+    const float cd = fmaf(c.z, s.d2, fmaf(c.y, s.d1, c.x * s.d0));
+    const float dL_dalpha = fmaf(cd - s.a_rec, s.T, s.bgT * inv);   // :519-534
+    g = G * dL_dalpha;
+    w = alpha * s.T;
+    s.last_alpha = alpha;
+    s.last_cd = cd;
+    s.last_om = om;
 }
 
-// keep a loop-invariant value in a register (stops nvcc from rematerialising it inside the loop)
-__forceinline__ __device__ float pin_reg(float v) {
-    asm volatile("" : "+f"(v));
-    return v;
-}
-
-__global__ void __launch_bounds__(SGS_TILE_PIX, 3)
+__global__ void __launch_bounds__(SGS_R_THREADS)
 render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
                   const uint32_t* __restrict__ tile_count, const PackedInst* __restrict__ packed,
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dpix, float* __restrict__ acc) {
-    __shared__ float4 s_rec[SGS_BWD_BATCH * 3];
+    __shared__ float4 s_g0[SGS_R_BATCH];   // x, y, A, -B
+    __shared__ float4 s_g1[SGS_R_BATCH];   // C, thr, list_pos(bits), opacity
+    __shared__ float4 s_g2[SGS_R_BATCH];   // r, g, b, gid(bits)
+    __shared__ uint32_t s_mask[SGS_R_BATCH];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int W = vp.W, H = vp.H;
     const uint32_t tile = blockIdx.y * vp.tiles_x + blockIdx.x;
     const uint32_t tx0 = blockIdx.x * SGS_TILE_X, ty0 = blockIdx.y * SGS_TILE_Y;
-    const uint32_t px = tx0 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = ty0 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-    const uint32_t pix_id = (uint32_t)W * py + px;
-    const float pixx = pin_reg((float)px), pixy = pin_reg((float)py);
+    const uint32_t px = tx0 + (warp & 1) * SGS_Q + (lane & 7);
+    const uint32_t py0 = ty0 + (warp >> 1) * SGS_Q + 2 * (lane >> 3);
+    const uint32_t py1 = py0 + 1;
+    const bool in0 = px < (uint32_t)W && py0 < (uint32_t)H;
+    const bool in1 = px < (uint32_t)W && py1 < (uint32_t)H;
+    const float pxf = pin_reg((float)px);
+    const float2 npy = {pin_reg(-(float)py0), pin_reg(-(float)py1)};
 
     const uint32_t start = ranges[tile].x;
     const int count = (int)tile_count[tile];
     if (count == 0) return;
 
-    const float T_final = inside ? final_T[pix_id] : 0.f;
-    float T = T_final;
-    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
-    // warp-uniform bound: records at list positions >= this were blended by no pixel of the warp
-    const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, last_contributor);
-
-    float accum_rec[SGS_CH] = {0.f, 0.f, 0.f};
-    float dL_dpixel[SGS_CH] = {0.f, 0.f, 0.f};
-    if (inside) {
+    BwdPix p0, p1;
+    {
         const size_t HW = (size_t)H * W;
-#pragma unroll
-        for (int ch = 0; ch < SGS_CH; ch++) dL_dpixel[ch] = dL_dpix[ch * HW + pix_id];
+        const uint32_t id0 = (uint32_t)W * py0 + px, id1 = (uint32_t)W * py1 + px;
+        const float Tf0 = in0 ? final_T[id0] : 0.f, Tf1 = in1 ? final_T[id1] : 0.f;
+        p0.T = Tf0;
+        p1.T = Tf1;
+        p0.lc = in0 ? n_contrib[id0] : 0u;
+        p1.lc = in1 ? n_contrib[id1] : 0u;
+        p0.d0 = in0 ? dL_dpix[id0] : 0.f;
+        p0.d1 = in0 ? dL_dpix[HW + id0] : 0.f;
+        p0.d2 = in0 ? dL_dpix[2 * HW + id0] : 0.f;
+        p1.d0 = in1 ? dL_dpix[id1] : 0.f;
+        p1.d1 = in1 ? dL_dpix[HW + id1] : 0.f;
+        p1.d2 = in1 ? dL_dpix[2 * HW + id1] : 0.f;
+        const float b0 = vp.bg[0], b1 = vp.bg[1], b2 = vp.bg[2];
+        p0.bgT = -Tf0 * (b0 * p0.d0 + b1 * p0.d1 + b2 * p0.d2);   // :531-534
+        p1.bgT = -Tf1 * (b0 * p1.d0 + b1 * p1.d1 + b2 * p1.d2);
+        p0.a_rec = p1.a_rec = 0.f;
+        p0.last_alpha = p1.last_alpha = 0.f;
+        p0.last_cd = p1.last_cd = 0.f;
+        p0.last_om = p1.last_om = 1.f;
     }
-    float last_alpha = 0.f;
-    float last_color[SGS_CH] = {0.f, 0.f, 0.f};
-    // $R/cuda_rasterizer/backward.cu:460-461 (double product rounded to float once)
-    const float ddelx_dx = pin_reg((float)(0.5 * W));
-    const float ddely_dy = pin_reg((float)(0.5 * H));
-    float bg_dot_dpixel = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < SGS_CH; ch++) bg_dot_dpixel += vp.bg[ch] * dL_dpixel[ch];
-    const float neg_Tfinal_bg = pin_reg(-T_final * bg_dot_dpixel);
+    // warp-uniform bound: records at list positions >= this were blended by no pixel of the warp
+    const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(p0.lc, p1.lc));
 
-    // which accumulator slot this lane owns after the butterfly (see reduce below)
+    // which accumulator slot this lane owns after the butterfly (see the reduction below)
     //   bit1 set -> value 4 ; else value = (bit4 ? 5 : 0) + (bit2 ? 2 : 0) + (bit3 ? 1 : 0)
     const int my_slot = (lane & 2) ? 4 : (((lane & 16) ? 5 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 8) ? 1 : 0));
     const bool writer = (lane & 1) == 0 && ((lane & 2) == 0 || lane == 2);
@@ -102,105 +126,95 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     float* const acc_lane = acc + my_slot;
 
     const float4* src = reinterpret_cast<const float4*>(packed + start);
-    uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_rec);
-    asm volatile("" : "+r"(s_base));
+    uint32_t a0 = (uint32_t)__cvta_generic_to_shared(s_g0);
+    uint32_t a1 = (uint32_t)__cvta_generic_to_shared(s_g1);
+    uint32_t a2 = (uint32_t)__cvta_generic_to_shared(s_g2);
+    asm volatile("" : "+r"(a0), "+r"(a1), "+r"(a2));
 
-    for (int hi = count; hi > 0; hi -= SGS_BWD_BATCH) {
-        const int lo = max(0, hi - SGS_BWD_BATCH);
+    for (int hi = count; hi > 0; hi -= SGS_R_BATCH) {
+        const int lo = max(0, hi - SGS_R_BATCH);
         const int nrec = hi - lo;
         __syncthreads();
-        for (int k = tid; k < nrec * 3; k += SGS_TILE_PIX) s_rec[k] = src[(size_t)lo * 3 + k];
+        if (tid < nrec) {
+            const float4* r = src + (size_t)(lo + tid) * 3;
+            const float4 ra = r[0];   // x, y, A, B
+            const float4 rb = r[1];   // C, opacity, thr, list_pos
+            const float4 rc = r[2];   // r, g, b, gid
+            s_g0[tid] = make_float4(ra.x, ra.y, ra.z, -ra.w);
+            s_g1[tid] = make_float4(rb.x, rb.z, rb.w, rb.y);
+            s_g2[tid] = rc;
+            s_mask[tid] = quadrant_mask(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, (float)tx0, (float)ty0);
+        }
         __syncthreads();
 
-        // first record (from the back) that some pixel of this warp blended: list positions are
-        // strictly increasing within the batch -> binary search for the count of records < warp_last
-        int nvalid;
-        {
-            int a0 = 0, a1 = nrec;
-            while (a0 < a1) {
-                const int mid = (a0 + a1) >> 1;
-                if (__float_as_uint(s_rec[3 * mid + 1].w) < warp_last) a0 = mid + 1;
-                else a1 = mid;
-            }
-            nvalid = a0;
+        // visit bitmap of this warp: quadrant bit set and list position below the warp's last contributor
+        uint32_t mywords = 0;
+#pragma unroll
+        for (int k = 0; k < SGS_R_BATCH / 32; k++) {
+            const int slot = k * 32 + lane;
+            bool v = false;
+            if (slot < nrec) v = ((s_mask[slot] >> warp) & 1u) && (__float_as_uint(s_g1[slot].z) < warp_last);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, v);
+            if (lane == k) mywords = b;
         }
 
-        uint32_t rec = s_base + (uint32_t)nvalid * 48u;   // one past the first record to visit
-        for (int j = nvalid; j > 0; j--) {
-            rec -= 48u;
-            const float4 a = lds128(rec);         // x, y, A, B
-            const float4 b = lds128(rec + 16u);   // C, opacity, thr, list_pos
-            const float dx = a.x - pixx, dy = a.y - pixy;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            // same tests as forward: power > 0 -> skip; power < thr -> provably alpha < 1/255
-            bool active = (__float_as_uint(b.w) < last_contributor) && !(power > 0.0f) && !(power < b.z);
-            float G = 0.f, alpha = 0.f;
-            if (active) {
-                G = expf(power);
-                alpha = min(0.99f, b.y * G);
-                active = !(alpha < 1.0f / 255.0f);
+        for (int k = SGS_R_BATCH / 32 - 1; k >= 0; k--) {
+            uint32_t word = __shfl_sync(0xFFFFFFFFu, mywords, k);
+            while (word) {
+                const uint32_t bit = 31u - __clz(word);
+                word ^= 1u << bit;
+                const uint32_t j = k * 32 + bit;
+                const float4 g0 = lds128(a0 + j * 16u);
+                const float4 g1 = lds128(a1 + j * 16u);
+                float dx;
+                float2 dy;
+                const float2 pw = power2(g0, g1.x, pxf, npy, dx, dy);
+                const uint32_t pos = __float_as_uint(g1.z);
+                // same tests as forward: power > 0 -> skip; power < thr -> provably alpha < 1/255
+                // (a separate cheaper warp-level pre-test was measured slower: with the visit bitmaps
+                // nearly every visit blends something, so the exact tests are needed anyway)
+                const bool act0 = (pos < p0.lc) && !(pw.x > 0.0f) && !(pw.x < g1.y);
+                const bool act1 = (pos < p1.lc) && !(pw.y > 0.0f) && !(pw.y < g1.y);
+                if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;
+
+                const float4 c = lds128(a2 + j * 16u);   // r, g, b, gid
+                float g_0 = 0.f, w_0 = 0.f, g_1 = 0.f, w_1 = 0.f;
+                if (act0) grad_pixel(p0, pw.x, g1.w, c, g_0, w_0);
+                if (act1) grad_pixel(p1, pw.y, g1.w, c, g_1, w_1);
+
+                // moments of g over this thread's two pixels (dx shared)
+                const float gy0 = g_0 * dy.x, gy1 = g_1 * dy.y;
+                float v5 = g_0 + g_1;                       // sum g            -> dL/dopacity
+                float v0 = v5 * dx;                         // sum g dx
+                float v1 = gy0 + gy1;                       // sum g dy
+                float v2 = v0 * dx;                         // sum g dx^2
+                float v3 = v1 * dx;                         // sum g dx dy
+                float v4 = fmaf(gy1, dy.y, gy0 * dy.x);     // sum g dy^2
+                float v6 = fmaf(w_1, p1.d0, w_0 * p0.d0);   // sum alpha T dL/dpix[c]  -> dL/dcolour
+                float v7 = fmaf(w_1, p1.d1, w_0 * p0.d1);
+                float v8 = fmaf(w_1, p1.d2, w_0 * p0.d2);
+
+                // transposing butterfly: 9 values x 32 lanes -> one value per writer lane
+                // step 1 (xor 16): pairs (v0,v5) (v1,v6) (v2,v7) (v3,v8); v4 reduced plainly
+                float w0 = xsplit(v0, v5, b16, 16);
+                float w1 = xsplit(v1, v6, b16, 16);
+                float w2 = xsplit(v2, v7, b16, 16);
+                float w3 = xsplit(v3, v8, b16, 16);
+                v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 16);
+                // step 2 (xor 8): pairs (w0,w1) (w2,w3)
+                float u0 = xsplit(w0, w1, b8, 8);
+                float u1 = xsplit(w2, w3, b8, 8);
+                v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 8);
+                // step 3 (xor 4): pair (u0,u1)
+                float t0 = xsplit(u0, u1, b4, 4);
+                v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 4);
+                // step 4 (xor 2): pair (t0, v4)
+                float r = xsplit(t0, v4, b2, 2);
+                // step 5 (xor 1)
+                r += __shfl_xor_sync(0xFFFFFFFFu, r, 1);
+
+                if (writer) atomicAdd(acc_lane + (size_t)__float_as_uint(c.w) * 12, r);
             }
-            if (!__any_sync(0xFFFFFFFFu, active)) continue;
-
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
-            const float4 c4 = lds128(rec + 32u);  // r, g, b, gid
-            if (active) {
-                // 1/(1-alpha) once (IEEE reciprocal), shared by the T recovery and the background term;
-                // the reference divides twice ($R/cuda_rasterizer/backward.cu:503,534): <= 1 ulp apart
-                const float inv = __frcp_rn(1.f - alpha);
-                T = T * inv;
-                const float dchannel_dcolor = alpha * T;
-                const float om = 1.f - last_alpha;
-                accum_rec[0] = last_alpha * last_color[0] + om * accum_rec[0];
-                accum_rec[1] = last_alpha * last_color[1] + om * accum_rec[1];
-                accum_rec[2] = last_alpha * last_color[2] + om * accum_rec[2];
-                last_color[0] = c4.x;
-                last_color[1] = c4.y;
-                last_color[2] = c4.z;
-                float dL_dalpha = (c4.x - accum_rec[0]) * dL_dpixel[0];
-                dL_dalpha += (c4.y - accum_rec[1]) * dL_dpixel[1];
-                dL_dalpha += (c4.z - accum_rec[2]) * dL_dpixel[2];
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += neg_Tfinal_bg * inv;
-
-                const float dL_dG = b.y * dL_dalpha;
-                const float gdx = G * dx;
-                const float gdy = G * dy;
-                const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                const float dG_ddely = -gdy * b.x - gdx * a.w;
-                v0 = dL_dG * dG_ddelx * ddelx_dx;
-                v1 = dL_dG * dG_ddely * ddely_dy;
-                const float h = -0.5f * dL_dG;
-                v2 = h * gdx * dx;
-                v3 = h * gdx * dy;
-                v4 = h * gdy * dy;
-                v5 = G * dL_dalpha;
-                v6 = dchannel_dcolor * dL_dpixel[0];
-                v7 = dchannel_dcolor * dL_dpixel[1];
-                v8 = dchannel_dcolor * dL_dpixel[2];
-            }
-
-            // transposing butterfly: 9 values x 32 lanes -> one value per writer lane
-            // step 1 (xor 16): pairs (v0,v5) (v1,v6) (v2,v7) (v3,v8); v4 reduced plainly
-            float w0 = xsplit(v0, v5, b16, 16);
-            float w1 = xsplit(v1, v6, b16, 16);
-            float w2 = xsplit(v2, v7, b16, 16);
-            float w3 = xsplit(v3, v8, b16, 16);
-            v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 16);
-            // step 2 (xor 8): pairs (w0,w1) (w2,w3)
-            float u0 = xsplit(w0, w1, b8, 8);
-            float u1 = xsplit(w2, w3, b8, 8);
-            v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 8);
-            // step 3 (xor 4): pair (u0,u1)
-            float t0 = xsplit(u0, u1, b4, 4);
-            v4 += __shfl_xor_sync(0xFFFFFFFFu, v4, 4);
-            // step 4 (xor 2): pair (t0, v4)
-            float r = xsplit(t0, v4, b2, 2);
-            // step 5 (xor 1)
-            r += __shfl_xor_sync(0xFFFFFFFFu, r, 1);
-
-            if (writer) atomicAdd(acc_lane + (size_t)__float_as_uint(c4.w) * 12, r);
         }
     }
 }
@@ -208,8 +222,8 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
 void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, const float* dL_dpix, float* acc,
                        cudaStream_t s) {
     dim3 grid(vp.tiles_x, vp.tiles_y, 1);
-    render_bwd_kernel<<<grid, SGS_TILE_PIX, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, img.final_T,
-                                                   img.n_contrib, dL_dpix, acc);
+    render_bwd_kernel<<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, img.final_T,
+                                                    img.n_contrib, dL_dpix, acc);
 }
 
 }  // namespace sgs
