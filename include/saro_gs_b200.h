@@ -45,7 +45,8 @@ extern "C" {
 
 /* sgs_forward flags */
 #define SGS_FLAG_KEEP_FOR_BACKWARD 1 /* write the packed per-tile lists sgs_backward consumes */
-#define SGS_FLAG_NO_TILE_CULL 2      /* validation only: disable the exact tile-level culling */
+#define SGS_FLAG_NO_TILE_CULL 2      /* validation only: disable the exact tile/quadrant culling, so that the
+                                        internal lists (ranges, point_list, n_contrib) equal the reference's */
 
 /* error codes (negative returns) */
 #define SGS_ERR_INVALID_ARGUMENT -1
@@ -63,7 +64,9 @@ const char* sgs_last_error(void);
 int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);
 
-/* Forward: returns the number of rendered tile instances (>= 0) or a negative error code.
+/* Forward: returns the number of rendered tile instances as the reference counts them (sum over Gaussians
+ * of the tiles of their 3-sigma rect, >= 0) or a negative error code.  Internally only the instances that
+ * can reach alpha >= 1/255 somewhere in their tile are binned, sorted and composited (bit-identical output).
  * D = active SH degree, M = SH coefficients per Gaussian (0 when shs == NULL).
  * out_color [3][H][W], out_depth [1][H][W], radii [P] int32 are fully written when P > 0. */
 int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user,
@@ -101,12 +104,17 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
                      char* image_buffer, uint32_t* tiles_touched /*[P]*/, uint32_t* ranges /*[tiles][2]*/,
                      uint32_t* n_contrib /*[H*W]*/, float* final_T /*[H*W]*/, float* means2D /*[P][2]*/,
                      float* conic_opacity /*[P][4]*/, float* rgbd /*[P][4]*/, float* cov3D /*[P][6]*/,
-                     uint32_t* tile_count /*[tiles]*/, uint32_t* point_list /*[R]*/, void* stream);
+                     uint32_t* tile_count /*[tiles]*/, uint32_t* point_list /*[>= sgs_debug_kept()]*/, void* stream);
+
+/* Number of tile instances that survived the exact tile-level cull in the forward call that filled
+ * `binning_buffer` (= length of point_list; equals the value sgs_forward returned under SGS_FLAG_NO_TILE_CULL).
+ * Synchronises the stream. */
+int64_t sgs_debug_kept(char* binning_buffer, void* stream);
 
 /* Stage profiler (off by default): CUDA events on the launching stream around every stage.
  * sgs_profile_read synchronises the device, returns the summed milliseconds and call counts per
  * stage since the previous read, and the number of hand-written kernels this library launched. */
-#define SGS_STAGE_PREPROCESS_FWD 0
+#define SGS_STAGE_PREPROCESS_FWD 0   /* per-Gaussian preprocess + exact tile-cull count */
 #define SGS_STAGE_DEPTH_SORT_SCAN 1 /* CUB radix sort of P depth keys + CUB scan */
 #define SGS_STAGE_DUPLICATE 2
 #define SGS_STAGE_TILE_SORT 3       /* CUB radix sort of R tile keys */

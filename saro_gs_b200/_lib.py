@@ -35,6 +35,7 @@ ABI = {
                           _vp, _vp, _vp,                                      # state buffers
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_debug_export": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp] + [_vp] * 10 + [_vp]),
+    "sgs_debug_kept": (_i64, [_vp, _vp]),
     "sgs_profile_enable": (None, [_i]),
     "sgs_profile_read": (_i, [_vp, _vp, _vp]),
 }

@@ -225,5 +225,7 @@ def debug_export(P, W, H, R, geomBuffer, binningBuffer, imageBuffer):
                                     _ptr(out["final_T"]), _ptr(out["means2D"]), _ptr(out["conic_opacity"]),
                                     _ptr(out["rgbd"]), _ptr(out["cov3D"]), _ptr(out["tile_count"]),
                                     _ptr(out["point_list"]), ctypes.c_void_p(stream)), "sgs_debug_export")
-    out["point_list"] = out["point_list"][:int(R)]
+        kept = _check(lib.sgs_debug_kept(_ptr(binningBuffer), ctypes.c_void_p(stream)), "sgs_debug_kept")
+    out["point_list"] = out["point_list"][:int(kept)]
+    out["kept"] = int(kept)
     return out

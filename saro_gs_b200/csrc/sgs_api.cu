@@ -72,6 +72,8 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.cov3D, P * 6);
     sgs::carve(chunk, g.clamped, P);
     sgs::carve(chunk, g.tiles_touched, P);
+    sgs::carve(chunk, g.rect_kept, P);
+    sgs::carve(chunk, g.counters, 32);
     sgs::carve(chunk, g.depth_keys[0], P);
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);
@@ -93,20 +95,27 @@ sgs::ImageState carve_image(char*& chunk, size_t N, size_t tiles) {
 
 struct BinningCarve {
     sgs::BinningState b;
-    uint32_t* header;  // [32] word 0: selector of the sorted double buffer (byte pattern)
+    uint32_t* header;  // [32] word 0: selector of the sorted double buffer; word 1: kept instances; word 2: packed?
 };
 
-BinningCarve carve_binning(char*& chunk, size_t R, int tile_bits, bool with_packed) {
+// Layout: header | packed records (only if backward will run) | sort double buffers | CUB temp.
+// `packed` comes right after the header so that sgs_backward — which knows only the API-visible
+// num_rendered, not the number of kept instances — can find it without a device->host read.
+BinningCarve carve_binning(char*& chunk, size_t Rk, int tile_bits, bool with_packed, bool header_and_packed_only = false) {
     BinningCarve c;
     sgs::carve(chunk, c.header, 32);
-    sgs::carve(chunk, c.b.tile_keys[0], R);
-    sgs::carve(chunk, c.b.tile_keys[1], R);
-    sgs::carve(chunk, c.b.gauss_vals[0], R);
-    sgs::carve(chunk, c.b.gauss_vals[1], R);
-    c.b.temp_bytes = inst_temp_bytes(R, tile_bits);
-    sgs::carve(chunk, c.b.temp, c.b.temp_bytes);
-    if (with_packed) sgs::carve(chunk, c.b.packed, R);
+    if (with_packed) sgs::carve(chunk, c.b.packed, Rk);
     else c.b.packed = nullptr;
+    c.b.tile_keys[0] = c.b.tile_keys[1] = c.b.gauss_vals[0] = c.b.gauss_vals[1] = nullptr;
+    c.b.temp = nullptr;
+    c.b.temp_bytes = 0;
+    if (header_and_packed_only) return c;
+    sgs::carve(chunk, c.b.tile_keys[0], Rk);
+    sgs::carve(chunk, c.b.tile_keys[1], Rk);
+    sgs::carve(chunk, c.b.gauss_vals[0], Rk);
+    sgs::carve(chunk, c.b.gauss_vals[1], Rk);
+    c.b.temp_bytes = inst_temp_bytes(Rk, tile_bits);
+    sgs::carve(chunk, c.b.temp, c.b.temp_bytes);
     return c;
 }
 
@@ -230,7 +239,8 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
                     float tan_fovy, int prefiltered, float* out_color, float* out_depth, int* radii, int flags,
                     void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || width <= 0 || height <= 0) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: bad sizes");
+    if (P < 0 || width <= 0 || height <= 0 || width > 16 * 65535 || height > 16 * 65535)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: bad sizes");
     if (P == 0) return 0;  // reference binding skips the call entirely ($R/rasterize_points.cu:80)
     if (!geometry_buffer || !binning_buffer || !image_buffer)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: null resize callback");
@@ -262,10 +272,12 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (!ichunk) return fail(SGS_ERR_ALLOC, "sgs_forward: image buffer allocation failed");
     sgs::ImageState img = carve_image(ichunk, N, tiles);
 
+    const int cull = (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1;
     {
         StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
+        SGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), s));
         sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
-                                   radii, g, s);
+                                   radii, g, cull, s);
     }
     {
         StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 0);
@@ -273,53 +285,52 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     }
 
     const double t_presync = tr ? now_us() : 0;
-    // The one device->host dependency of the path: the instance count sizes the binning buffer
+    // The one device->host dependency of the path: the instance counts.  `kept` sizes the binning
+    // buffer; `num_rendered` (sum of tiles_touched) is what the reference returns to Python
     // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
     uint32_t* slot = pinned_slot();
-    uint32_t num_rendered = 0;
-    if (slot) {
-        SGS_CUDA_OK(cudaMemcpyAsync(slot, g.sorted_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        SGS_CUDA_OK(cudaStreamSynchronize(s));
-        num_rendered = *slot;
-    } else {
-        SGS_CUDA_OK(cudaMemcpyAsync(&num_rendered, g.sorted_offsets + (P - 1), sizeof(uint32_t),
-                                    cudaMemcpyDeviceToHost, s));
-        SGS_CUDA_OK(cudaStreamSynchronize(s));
-    }
-    const size_t R = num_rendered;
+    uint32_t local[2] = {0, 0};
+    uint32_t* dst = slot ? slot : local;
+    SGS_CUDA_OK(cudaMemcpyAsync(dst, g.sorted_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SGS_CUDA_OK(cudaMemcpyAsync(dst + 1, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SGS_CUDA_OK(cudaStreamSynchronize(s));
+    const size_t Rk = dst[0];              // kept instances (what is binned, sorted and rendered)
+    const size_t R = dst[1];               // the reference's num_rendered
     const int tile_bits = sgs::binning_tile_bits((int)tiles);
     const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
     const double t_synced = tr ? now_us() : 0;
 
-    const size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, R, tile_bits, keep); });
+    const size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, Rk, tile_bits, keep); });
     char* bchunk = binning_buffer(binning_user, bin_bytes);
     if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
-    BinningCarve bc = carve_binning(bchunk, R, tile_bits, keep);
+    BinningCarve bc = carve_binning(bchunk, Rk, tile_bits, keep);
     const double t_alloc = tr ? now_us() : 0;
 
     const uint32_t* point_list = bc.b.gauss_vals[0];
     const uint32_t* sorted_tiles = bc.b.tile_keys[0];
     SGS_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, s));
     if (keep) SGS_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * tiles, s));
-    if (R > 0) {
+    if (Rk > 0) {
         {
             StageScope sc(SGS_STAGE_DUPLICATE, s, 1);
-            SGS_CUDA_OK(sgs::launch_duplicate(P, vp, radii, g, bc.b, s));
+            SGS_CUDA_OK(sgs::launch_duplicate(P, vp, g, bc.b, s));
         }
         {
             StageScope sc(SGS_STAGE_TILE_SORT, s, 0);
-            SGS_CUDA_OK(sgs::launch_tile_sort(R, (int)tiles, bc.b, &point_list, &sorted_tiles, s));
+            SGS_CUDA_OK(sgs::launch_tile_sort(Rk, (int)tiles, bc.b, &point_list, &sorted_tiles, s));
         }
         {
             StageScope sc(SGS_STAGE_TILE_RANGES, s, 1);
-            SGS_CUDA_OK(sgs::launch_tile_ranges(R, sorted_tiles, img, s));
+            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, sorted_tiles, img, s));
         }
     }
-    SGS_CUDA_OK(cudaMemsetAsync(bc.header, point_list == bc.b.gauss_vals[1] ? 1 : 0, 4, s));
+    {
+        const uint32_t hdr[3] = {point_list == bc.b.gauss_vals[1] ? 1u : 0u, (uint32_t)Rk, keep ? 1u : 0u};
+        SGS_CUDA_OK(cudaMemcpyAsync(bc.header, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+    }
     {
         StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
-        sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1,
-                               out_color, out_depth, s);
+        sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
     }
     SGS_CUDA_OK(cudaGetLastError());
     if (tr)
@@ -352,7 +363,8 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     const size_t tiles = (size_t)vp.tiles_x * vp.tiles_y;
     sgs::GeomState g = carve_geom(geom_buffer, (size_t)P);
     sgs::ImageState img = carve_image(image_buffer, N, tiles);
-    BinningCarve bc = carve_binning(binning_buffer, (size_t)R, sgs::binning_tile_bits((int)tiles), true);
+    // only the header + packed records are needed: their position does not depend on the kept count
+    BinningCarve bc = carve_binning(binning_buffer, 0, 0, true, /*header_and_packed_only=*/true);
 
     {
         StageScope sc(SGS_STAGE_BWD_ZERO, s, 0);
@@ -400,13 +412,27 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
         if (tile_count) SGS_CUDA_OK(cudaMemcpyAsync(tile_count, img.tile_count, 4 * tiles, D2D, s));
     }
     if (binning_buffer && point_list && R > 0) {
-        BinningCarve bc = carve_binning(binning_buffer, (size_t)R, sgs::binning_tile_bits((int)tiles), false);
-        uint32_t sel = 0;
-        SGS_CUDA_OK(cudaMemcpyAsync(&sel, bc.header, 4, cudaMemcpyDeviceToHost, s));
+        uint32_t hdr[3] = {0, 0, 0};
+        SGS_CUDA_OK(cudaMemcpyAsync(hdr, binning_buffer + ((128 - (reinterpret_cast<size_t>(binning_buffer) & 127)) & 127),
+                                    sizeof(hdr), cudaMemcpyDeviceToHost, s));
         SGS_CUDA_OK(cudaStreamSynchronize(s));
-        SGS_CUDA_OK(cudaMemcpyAsync(point_list, bc.b.gauss_vals[(sel & 1) ? 1 : 0], 4 * (size_t)R, D2D, s));
+        const size_t Rk = hdr[1];
+        if (Rk > 0) {
+            BinningCarve bc = carve_binning(binning_buffer, Rk, sgs::binning_tile_bits((int)tiles), hdr[2] != 0);
+            SGS_CUDA_OK(cudaMemcpyAsync(point_list, bc.b.gauss_vals[(hdr[0] & 1) ? 1 : 0], 4 * Rk, D2D, s));
+        }
     }
     return 0;
+}
+
+int64_t sgs_debug_kept(char* binning_buffer, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!binning_buffer) return 0;
+    uint32_t hdr[3] = {0, 0, 0};
+    SGS_CUDA_OK(cudaMemcpyAsync(hdr, binning_buffer + ((128 - (reinterpret_cast<size_t>(binning_buffer) & 127)) & 127),
+                                sizeof(hdr), cudaMemcpyDeviceToHost, s));
+    SGS_CUDA_OK(cudaStreamSynchronize(s));
+    return (int64_t)hdr[1];
 }
 
 void sgs_profile_enable(int on) {

@@ -5,33 +5,42 @@
 //   $R/cuda_rasterizer/rasterizer_impl.cu:299-309 (SortPairs on bits [0, 32+bit))
 //   $R/cuda_rasterizer/rasterizer_impl.cu:116-138 (identifyTileRanges)
 //
-// B200 design: a TWO-LEVEL sort that moves far fewer bytes through HBM.
+// B200 design: a TWO-LEVEL sort over a CULLED instance set — far fewer bytes through HBM.
+//   0. (in the preprocess kernel) the reference's 3-sigma tile rect of every Gaussian is clipped to
+//      the exact axis-aligned bounding box of its  alpha >= 1/255  ellipse (`rect_kept`, with
+//      explicit rounding margins).  The reference's own count (`tiles_touched`, rect area) is
+//      kept for the API-visible num_rendered and the bit-exact tile-count checks; at config 2
+//      the clipped rects sum to ~55 % of it.  A dropped instance would `continue` on all 256
+//      pixels of its tile in the reference, so the image, depth and gradients are unchanged bit
+//      for bit.  (SGS_FLAG_NO_TILE_CULL keeps the full rect: then ranges / point_list /
+//      n_contrib equal the reference's bit for bit.)
 //   1. sort the P Gaussians (not the R >> P instances) by their 32-bit depth bits
 //      (stable => ties keep ascending Gaussian index);
-//   2. scan tiles_touched in that depth order and emit instances in depth order
+//   2. scan area(rect_kept) in that depth order and emit the instances in depth order
 //      (key = tile id only, value = Gaussian index);
-//   3. one stable radix sort of the R instances on ceil(log2(#tiles)) bits (13 bits at
-//      1352x1014 => 2 CUB onesweep passes over 8-byte pairs instead of 6 passes over
-//      12-byte pairs).
-// A stable sort by tile of a depth-ordered stream is ordered by (tile, depth, index):
-// identical to the reference order, so tile ranges, n_contrib and compositing order are
-// bit-identical.
+//   3. one stable radix sort of the instances on ceil(log2(#tiles)) bits (13 bits at
+//      1352x1014 => 2 CUB onesweep passes over 8-byte pairs instead of 6 passes over 12-byte pairs).
+// A stable sort by tile of a depth-ordered stream is ordered by (tile, depth, index): the
+// reference order restricted to the kept instances.
 #include "sgs_common.cuh"
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
 namespace sgs {
 
-struct TilesInDepthOrder {
-    const uint32_t* tiles_touched;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& gid) const { return tiles_touched[gid]; }
+struct KeptInDepthOrder {
+    const ushort4* rect_kept;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& gid) const {
+        const ushort4 r = rect_kept[gid];
+        return (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
+    }
 };
 
 void binning_geom_temp_bytes(int P, size_t* bytes) {
     size_t a = 0, b = 0;
     cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, P, 0, 32);
-    TilesInDepthOrder op{nullptr};
+    KeptInDepthOrder op{nullptr};
     auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, op);
     cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
     *bytes = (a > b ? a : b) + 256;
@@ -44,9 +53,11 @@ void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes) {
     *bytes = a + 256;
 }
 
-// Step 1+2a: depth sort of Gaussians, then inclusive scan of tiles_touched in depth order.
+#define SGS_DUP_SMALL 8
+
+// Step 1+2a: depth sort of Gaussians, then inclusive scan of tiles_kept in depth order.
 // On return (stream order) g.depth_vals[0] holds the depth-ordered Gaussian indices and
-// g.sorted_offsets the scan; num_rendered = sorted_offsets[P-1].
+// g.sorted_offsets the scan; the number of kept instances = sorted_offsets[P-1].
 cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
     cub::DoubleBuffer<uint32_t> keys(g.depth_keys[0], g.depth_keys[1]);
     cub::DoubleBuffer<uint32_t> vals(g.depth_vals[0], g.depth_vals[1]);
@@ -56,37 +67,33 @@ cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
     // 4 passes of 8 bits: the result lands back in buffer 0; keep the code robust anyway.
     if (vals.Current() != g.depth_vals[0])
         cudaMemcpyAsync(g.depth_vals[0], vals.Current(), sizeof(uint32_t) * (size_t)P, cudaMemcpyDeviceToDevice, s);
-    TilesInDepthOrder op{g.tiles_touched};
+    KeptInDepthOrder op{g.rect_kept};
     auto it = thrust::make_transform_iterator((const uint32_t*)g.depth_vals[0], op);
     tb = g.temp_bytes;
     return cub::DeviceScan::InclusiveSum(g.temp, tb, it, g.sorted_offsets, P, s);
 }
 
-// Step 2b: emit (tile id, Gaussian index) for every tile of every visible Gaussian, visiting
-// Gaussians in depth order.  Small rects are written by the owning thread; large rects are
+// Step 2b: emit (tile id, Gaussian index) for every tile of rect_kept of every visible Gaussian,
+// visiting Gaussians in depth order.  Small rects are written by the owning thread; large rects are
 // written by the whole warp (coalesced), which removes the long divergent per-thread loops
 // of the reference's duplicateWithKeys.
-#define SGS_DUP_SMALL 8
 __global__ void __launch_bounds__(256)
-duplicate_kernel(int P, int tiles_x, int tiles_y, const uint32_t* __restrict__ order,
-                 const uint32_t* __restrict__ sorted_offsets, const uint32_t* __restrict__ tiles_touched,
-                 const float2* __restrict__ means2D, const int* __restrict__ radii,
-                 uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ gauss_vals) {
+duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const uint32_t* __restrict__ sorted_offsets,
+                 const ushort4* __restrict__ rect_kept, uint32_t* __restrict__ tile_keys,
+                 uint32_t* __restrict__ gauss_vals) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     uint32_t n = 0, off = 0, gid = 0;
-    uint2 rmin = {0, 0}, rmax = {0, 0};
+    ushort4 r = {0, 0, 0, 0};
     if (k < P) {
         gid = order[k];
-        n = tiles_touched[gid];
-        if (n > 0) {
-            off = (k == 0) ? 0u : sorted_offsets[k - 1];
-            get_rect(means2D[gid], radii[gid], rmin, rmax, tiles_x, tiles_y);
-        }
+        r = rect_kept[gid];
+        n = (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
+        if (n > 0) off = (k == 0) ? 0u : sorted_offsets[k - 1];
     }
     if (n > 0 && n <= SGS_DUP_SMALL) {
-        for (uint32_t y = rmin.y; y < rmax.y; y++)
-            for (uint32_t x = rmin.x; x < rmax.x; x++) {
+        for (uint32_t y = r.z; y < r.w; y++)
+            for (uint32_t x = r.x; x < r.y; x++) {
                 tile_keys[off] = y * tiles_x + x;
                 gauss_vals[off] = gid;
                 off++;
@@ -99,9 +106,9 @@ duplicate_kernel(int P, int tiles_x, int tiles_y, const uint32_t* __restrict__ o
         const uint32_t sn = __shfl_sync(0xFFFFFFFFu, n, src);
         const uint32_t soff = __shfl_sync(0xFFFFFFFFu, off, src);
         const uint32_t sgid = __shfl_sync(0xFFFFFFFFu, gid, src);
-        const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, rmin.x, src);
-        const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, rmin.y, src);
-        const uint32_t sw = __shfl_sync(0xFFFFFFFFu, rmax.x, src) - sx0;
+        const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.x, src);
+        const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.z, src);
+        const uint32_t sw = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.y, src) - sx0;
         for (uint32_t i = lane; i < sn; i += 32) {
             const uint32_t yy = i / sw, xx = i - yy * sw;
             tile_keys[soff + i] = (sy0 + yy) * tiles_x + (sx0 + xx);
@@ -134,11 +141,9 @@ static int bits_for_tiles(int n_tiles) {
 }
 
 // Step 2b launcher: emit the depth-ordered (tile, Gaussian) stream.
-cudaError_t launch_duplicate(int P, const ViewParams& vp, const int* radii, GeomState g, BinningState b,
-                             cudaStream_t s) {
-    duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, vp.tiles_y, g.depth_vals[0], g.sorted_offsets,
-                                                    g.tiles_touched, g.means2D, radii, b.tile_keys[0],
-                                                    b.gauss_vals[0]);
+cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s) {
+    duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, g.depth_vals[0], g.sorted_offsets, g.rect_kept,
+                                                    b.tile_keys[0], b.gauss_vals[0]);
     return cudaGetLastError();
 }
 

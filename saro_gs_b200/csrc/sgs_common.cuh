@@ -81,10 +81,13 @@ struct GeomState {
     float4*   rgbd;           // [P]   (r, g, b, depth): colour after SH eval / precomputed copy
     float*    cov3D;          // [6P]  upper triangle of world covariance
     uint8_t*  clamped;        // [P]   bit c set  <=>  channel c was clamped at 0
-    uint32_t* tiles_touched;  // [P]
+    uint32_t* tiles_touched;  // [P]   tiles of the 3-sigma rect (the reference's count; sums to num_rendered)
+    ushort4*  rect_kept;      // [P]   tile rect [x0,x1) x [y0,y1) actually binned: the reference's 3-sigma rect
+                              //       clipped to the exact bounding box of the alpha >= 1/255 ellipse
+    uint32_t* counters;       // [32]  word 0: sum of tiles_touched (= the reference's num_rendered)
     uint32_t* depth_keys[2];  // [P]   float bits of depth (0xFFFFFFFF when culled); CUB double buffer
     uint32_t* depth_vals[2];  // [P]   Gaussian index; CUB double buffer
-    uint32_t* sorted_offsets; // [P]   inclusive scan of tiles_touched in depth order
+    uint32_t* sorted_offsets; // [P]   inclusive scan of area(rect_kept) in depth order
     char*     temp;           // CUB temp storage
     size_t    temp_bytes;
 };
@@ -206,15 +209,14 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii,
-                           GeomState g, cudaStream_t s);
+                           GeomState g, int cull, cudaStream_t s);
 
-// depth sort of Gaussians + scan of tiles_touched in depth order; num_rendered = sorted_offsets[P-1]
+// depth sort of Gaussians + scan of area(rect_kept) in depth order; kept instances = sorted_offsets[P-1]
 void binning_geom_temp_bytes(int P, size_t* bytes);
 cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s);
 int  binning_tile_bits(int n_tiles);
 void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes);
-cudaError_t launch_duplicate(int P, const ViewParams& vp, const int* radii, GeomState g, BinningState b,
-                             cudaStream_t s);
+cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s);
 cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
                              const uint32_t** sorted_tiles, cudaStream_t s);
 cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, cudaStream_t s);

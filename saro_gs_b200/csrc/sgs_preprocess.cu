@@ -105,22 +105,67 @@ __forceinline__ __device__ float3 cov2d_from_cov3d(const float3& mean, float foc
     return {cov.c[0][0], cov.c[0][1], cov.c[1][1]};
 }
 
+// Clip the reference's tile rect [rmin, rmax) to the tiles that contain at least one pixel able to reach
+// alpha >= 1/255 (the reference `continue`s on every other pixel, $R/cuda_rasterizer/forward.cu:342-352).
+//   alpha = o exp(power) >= 1/255  <=>  q(d) = -power <= tau = ln(255 o)
+//   max |dx| on the ellipse q(d) <= tau is sqrt(2 tau / (A - B^2/C)), max |dy| = sqrt(2 tau / (C - B^2/A)).
+// Everything is conservative: tau is inflated by a bound on the float error of `power` anywhere inside the
+// rect, the Schur complements are deflated by their own rounding error, the extents get a relative and an
+// absolute margin, and anything numerically unusual keeps the full rect.
+__forceinline__ __device__ void clip_rect_to_alpha_box(float2 p, float3 conic, float o, float radius, uint2& rmin,
+                                                       uint2& rmax) {
+    const float A = conic.x, B = conic.y, C = conic.z;
+    if (!(A > 0.f && C > 0.f) || !(fabsf(p.x) < 1e6f && fabsf(p.y) < 1e6f) || !(fabsf(B) < 1e15f)) return;
+    if (!(o > 0.f)) {
+        if (o == o) rmax = rmin;          // alpha <= 0 < 1/255 everywhere (NaN opacity: keep)
+        return;
+    }
+    const float ext = radius + 32.f;      // |dx|, |dy| of any pixel of any tile of the rect
+    const float tau = logf(255.f * o) + 2e-5f * (A + C) * ext * ext + 1e-3f;
+    if (!(tau < 1e30f)) return;           // NaN / inf
+    if (tau < 0.f) {                      // o exp(power <= 0) < 1/255: no pixel can blend
+        rmax = rmin;
+        return;
+    }
+    const float Sx = A - B * (B / C) - 1e-6f * A;
+    const float Sy = C - B * (B / A) - 1e-6f * C;
+    if (Sx > 0.f) {
+        const float ex = sqrtf(2.f * tau / Sx) * 1.00001f + 1e-2f;
+        if (ex < 1e6f) {
+            const float lo = floorf((p.x - ex) * (1.f / SGS_TILE_X)), hi = floorf((p.x + ex) * (1.f / SGS_TILE_X)) + 1.f;
+            rmin.x = max(rmin.x, (uint32_t)fminf(fmaxf(lo, 0.f), 65535.f));
+            rmax.x = min(rmax.x, (uint32_t)fminf(fmaxf(hi, 0.f), 65535.f));
+        }
+    }
+    if (Sy > 0.f) {
+        const float ey = sqrtf(2.f * tau / Sy) * 1.00001f + 1e-2f;
+        if (ey < 1e6f) {
+            const float lo = floorf((p.y - ey) * (1.f / SGS_TILE_Y)), hi = floorf((p.y + ey) * (1.f / SGS_TILE_Y)) + 1.f;
+            rmin.y = max(rmin.y, (uint32_t)fminf(fmaxf(lo, 0.f), 65535.f));
+            rmax.y = min(rmax.y, (uint32_t)fminf(fmaxf(hi, 0.f), 65535.f));
+        }
+    }
+    if (rmax.x <= rmin.x || rmax.y <= rmin.y) rmax = rmin;
+}
+
 template <bool VEC_SH>
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
-                      int* __restrict__ radii, GeomState g) {
+                      int* __restrict__ radii, GeomState g, int cull) {
     __shared__ ViewSmem cam;
     stage_view(cam, vp);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned live = __ballot_sync(0xFFFFFFFFu, idx < P);
     if (idx >= P) return;
 
     // defaults for a Gaussian that takes no further part
     int out_radius = 0;
     uint32_t out_tiles = 0;
     uint32_t out_key = 0xFFFFFFFFu;
+    ushort4 out_rect = {0, 0, 0, 0};
 
     const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
     const float3 p_view = xform_point_4x3(p_orig, cam.view);
@@ -201,12 +246,19 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                 g.clamped[idx] = cmask;
                 out_radius = (int)my_radius;
                 out_tiles = ntiles;
+                if (cull) clip_rect_to_alpha_box(point_image, conic, opacities[idx], my_radius, rmin, rmax);
+                out_rect = make_ushort4((unsigned short)rmin.x, (unsigned short)rmax.x, (unsigned short)rmin.y,
+                                        (unsigned short)rmax.y);
                 out_key = __float_as_uint(p_view.z);
             }
         }
     }
     radii[idx] = out_radius;
     g.tiles_touched[idx] = out_tiles;
+    g.rect_kept[idx] = out_rect;
+    // the reference's num_rendered = sum of tiles_touched: one integer atomic per warp
+    const uint32_t wsum = __reduce_add_sync(live, out_tiles);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&g.counters[0], wsum);
     g.depth_keys[0][idx] = out_key;
     g.depth_vals[0][idx] = (uint32_t)idx;
 }
@@ -214,17 +266,17 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii, GeomState g,
-                           cudaStream_t s) {
+                           int cull, cudaStream_t s) {
     if (P <= 0) return;
     const int block = 256;
     const int grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0);
     if (vec)
         preprocess_fwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
-                                                          cov3D_precomp, colors_precomp, radii, g);
+                                                          cov3D_precomp, colors_precomp, radii, g, cull);
     else
         preprocess_fwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
-                                                           cov3D_precomp, colors_precomp, radii, g);
+                                                           cov3D_precomp, colors_precomp, radii, g, cull);
 }
 
 // markVisible: bool per point = (z_view > 0.2).  $R/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153

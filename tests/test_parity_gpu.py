@@ -64,21 +64,29 @@ def native_state(sgs, d, dev, **kw):
                                      rs.campos, False, **kw)
     R, color, radii, gb, bb, ib, depth = out
     st = sgs._C.debug_export(ins["means3D"].shape[0], rs.image_width, rs.image_height, R, gb, bb, ib)
-    return R, color, radii, depth, {k: v.cpu().numpy() for k, v in st.items()}
+    return R, color, radii, depth, {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in st.items()}
 
 
 @pytest.mark.parametrize("name", SMALL_CASES)
 def test_forward_bit_exact_vs_reference_golden(sgs, dev, name):
     d = load(name)
+    # product mode (exact tile/quadrant culling): everything API-visible + per-pixel transmittance
     R, color, radii, depth, st = native_state(sgs, d, dev)
-    assert R == int(d["num_rendered"])
+    assert R == int(d["num_rendered"])                                # bit-exact tile counts
     assert np.array_equal(radii.cpu().numpy(), d["out_radii"])
     assert np.array_equal(st["tiles_touched"], d["tiles_touched"])
+    assert np.array_equal(st["final_T"], d["final_T"])
+    assert np.array_equal(color.cpu().numpy(), d["out_color"])       # bit-exact image
+    assert np.array_equal(depth.cpu().numpy(), d["out_depth"])
+    assert st["kept"] <= R
+    # validation mode (no culling): the internal per-tile lists are the reference's, bit for bit
+    R, color, radii, depth, st = native_state(sgs, d, dev, _no_tile_cull=True)
+    assert R == int(d["num_rendered"]) == st["kept"]
     assert np.array_equal(st["ranges"], d["ranges"])
     assert np.array_equal(st["point_list"], d["point_list"])
     assert np.array_equal(st["n_contrib"], d["n_contrib"])
     assert np.array_equal(st["final_T"], d["final_T"])
-    assert np.array_equal(color.cpu().numpy(), d["out_color"])       # bit-exact image
+    assert np.array_equal(color.cpu().numpy(), d["out_color"])
     assert np.array_equal(depth.cpu().numpy(), d["out_depth"])
 
 
@@ -111,8 +119,9 @@ def test_tile_culling_is_exact(sgs, dev, name):
     _, c0, r0, d0, s0 = native_state(sgs, d, dev)
     _, c1, r1, d1, s1 = native_state(sgs, d, dev, _no_tile_cull=True)
     assert torch.equal(c0, c1) and torch.equal(d0, d1) and torch.equal(r0, r1)
-    assert np.array_equal(s0["n_contrib"], s1["n_contrib"]) and np.array_equal(s0["final_T"], s1["final_T"])
-    assert s0["tile_count"].sum() <= s1["tile_count"].sum()
+    assert np.array_equal(s0["final_T"], s1["final_T"]) and np.array_equal(s0["tiles_touched"], s1["tiles_touched"])
+    assert (s0["n_contrib"] <= s1["n_contrib"]).all()      # list positions in the culled lists can only shrink
+    assert s0["kept"] <= s1["kept"] and s0["tile_count"].sum() <= s1["tile_count"].sum()
 
 
 def test_inference_forward_equals_training_forward(sgs, dev):
@@ -157,18 +166,24 @@ def test_full_size_bit_exact_tile_counts(sgs, dev, cfg):
     args = (torch.zeros(3, device=dev), scene.means3D.to(dev), e, scene.opacities.to(dev), scene.scales.to(dev),
             scene.rotations.to(dev), 1.0, e, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.tanfovx, cam.tanfovy,
             cam.height, cam.width, scene.shs.to(dev), scene.sh_degree, cam.campos.to(dev), False)
-    R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(*args)
-    st = sgs._C.debug_export(scene.means3D.shape[0], cam.width, cam.height, R, gb, bb, ib)
-    assert R == int(d["num_rendered"])
-    assert _sha(radii) == str(d["sha_radii"])
-    assert _sha(st["tiles_touched"]) == str(d["sha_tiles_touched"])
-    assert _sha(st["n_contrib"]) == str(d["sha_n_contrib"])
-    assert _sha(color) == str(d["sha_color"])
-    assert _sha(depth) == str(d["sha_depth"])
-    # size-independent properties
-    rng = st["ranges"].long()
-    assert int((rng[:, 1] - rng[:, 0]).sum()) == R == int(st["tiles_touched"].long().sum())
-    assert bool((st["tile_count"].long() <= (rng[:, 1] - rng[:, 0])).all())
+    for no_cull in (False, True):
+        R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(*args, _no_tile_cull=no_cull)
+        st = sgs._C.debug_export(scene.means3D.shape[0], cam.width, cam.height, R, gb, bb, ib)
+        assert R == int(d["num_rendered"])
+        assert _sha(radii) == str(d["sha_radii"])
+        assert _sha(st["tiles_touched"]) == str(d["sha_tiles_touched"])
+        assert _sha(color) == str(d["sha_color"])
+        assert _sha(depth) == str(d["sha_depth"])
+        # size-independent properties
+        rng = st["ranges"].long()
+        assert R == int(st["tiles_touched"].long().sum())
+        assert int((rng[:, 1] - rng[:, 0]).sum()) == st["kept"] == st["point_list"].numel()
+        assert bool((st["tile_count"].long() <= (rng[:, 1] - rng[:, 0])).all())
+        if no_cull:
+            assert st["kept"] == R
+            assert _sha(st["n_contrib"]) == str(d["sha_n_contrib"])     # the reference's per-pixel list positions
+        else:
+            assert st["kept"] < R
 
 
 def test_full_size_backward_properties(sgs, dev):
