@@ -73,7 +73,6 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.clamped, P);
     sgs::carve(chunk, g.tiles_touched, P);
     sgs::carve(chunk, g.rect_kept, P);
-    sgs::carve(chunk, g.counters, 32);
     sgs::carve(chunk, g.depth_keys[0], P);
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);
@@ -275,7 +274,6 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     const int cull = (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1;
     {
         StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
-        SGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), s));
         sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
                                    radii, g, cull, s);
     }
@@ -288,11 +286,16 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     // The one device->host dependency of the path: the instance counts.  `kept` sizes the binning
     // buffer; `num_rendered` (sum of tiles_touched) is what the reference returns to Python
     // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
+    // (ranges + tile_count are zeroed here, off the critical path that follows the read-back)
+    {
+        char* z0 = reinterpret_cast<char*>(img.ranges);
+        char* z1 = reinterpret_cast<char*>(img.tile_count + tiles);
+        SGS_CUDA_OK(cudaMemsetAsync(z0, 0, (size_t)(z1 - z0), s));
+    }
     uint32_t* slot = pinned_slot();
     uint32_t local[2] = {0, 0};
     uint32_t* dst = slot ? slot : local;
-    SGS_CUDA_OK(cudaMemcpyAsync(dst, g.sorted_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    SGS_CUDA_OK(cudaMemcpyAsync(dst + 1, g.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SGS_CUDA_OK(cudaMemcpyAsync(dst, g.sorted_offsets + (P - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     SGS_CUDA_OK(cudaStreamSynchronize(s));
     const size_t Rk = dst[0];              // kept instances (what is binned, sorted and rendered)
     const size_t R = dst[1];               // the reference's num_rendered
@@ -308,8 +311,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
 
     const uint32_t* point_list = bc.b.gauss_vals[0];
     const uint32_t* sorted_tiles = bc.b.tile_keys[0];
-    SGS_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, s));
-    if (keep) SGS_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * tiles, s));
+    const uint32_t hdr[4] = {0u, (uint32_t)Rk, keep ? 1u : 0u, 0u};   // word 0 is fixed up below
     if (Rk > 0) {
         {
             StageScope sc(SGS_STAGE_DUPLICATE, s, 1);
@@ -321,11 +323,10 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
         }
         {
             StageScope sc(SGS_STAGE_TILE_RANGES, s, 1);
-            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, sorted_tiles, img, s));
+            const uint32_t hw[4] = {point_list == bc.b.gauss_vals[1] ? 1u : 0u, hdr[1], hdr[2], 0u};
+            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, sorted_tiles, img, bc.header, hw, s));
         }
-    }
-    {
-        const uint32_t hdr[3] = {point_list == bc.b.gauss_vals[1] ? 1u : 0u, (uint32_t)Rk, keep ? 1u : 0u};
+    } else {
         SGS_CUDA_OK(cudaMemcpyAsync(bc.header, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
     }
     {

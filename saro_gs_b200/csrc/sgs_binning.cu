@@ -28,11 +28,14 @@
 
 namespace sgs {
 
+// One scan yields both counts: low word = instances kept (area of rect_kept), high word = the reference's
+// tiles_touched.  Both totals are < 2^32 (checked on the host), so the words never interfere.
 struct KeptInDepthOrder {
     const ushort4* rect_kept;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& gid) const {
+    const uint32_t* tiles_touched;
+    __host__ __device__ __forceinline__ uint64_t operator()(const uint32_t& gid) const {
         const ushort4 r = rect_kept[gid];
-        return (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
+        return (uint64_t)((uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z)) | ((uint64_t)tiles_touched[gid] << 32);
     }
 };
 
@@ -40,9 +43,9 @@ void binning_geom_temp_bytes(int P, size_t* bytes) {
     size_t a = 0, b = 0;
     cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, P, 0, 32);
-    KeptInDepthOrder op{nullptr};
+    KeptInDepthOrder op{nullptr, nullptr};
     auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, op);
-    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
+    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint64_t*)nullptr, P);
     *bytes = (a > b ? a : b) + 256;
 }
 
@@ -67,7 +70,7 @@ cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
     // 4 passes of 8 bits: the result lands back in buffer 0; keep the code robust anyway.
     if (vals.Current() != g.depth_vals[0])
         cudaMemcpyAsync(g.depth_vals[0], vals.Current(), sizeof(uint32_t) * (size_t)P, cudaMemcpyDeviceToDevice, s);
-    KeptInDepthOrder op{g.rect_kept};
+    KeptInDepthOrder op{g.rect_kept, g.tiles_touched};
     auto it = thrust::make_transform_iterator((const uint32_t*)g.depth_vals[0], op);
     tb = g.temp_bytes;
     return cub::DeviceScan::InclusiveSum(g.temp, tb, it, g.sorted_offsets, P, s);
@@ -78,7 +81,7 @@ cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
 // written by the whole warp (coalesced), which removes the long divergent per-thread loops
 // of the reference's duplicateWithKeys.
 __global__ void __launch_bounds__(256)
-duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const uint32_t* __restrict__ sorted_offsets,
+duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const uint64_t* __restrict__ sorted_offsets,
                  const ushort4* __restrict__ rect_kept, uint32_t* __restrict__ tile_keys,
                  uint32_t* __restrict__ gauss_vals) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +92,7 @@ duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const u
         gid = order[k];
         r = rect_kept[gid];
         n = (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
-        if (n > 0) off = (k == 0) ? 0u : sorted_offsets[k - 1];
+        if (n > 0) off = (k == 0) ? 0u : (uint32_t)sorted_offsets[k - 1];
     }
     if (n > 0 && n <= SGS_DUP_SMALL) {
         for (uint32_t y = r.z; y < r.w; y++)
@@ -119,8 +122,10 @@ duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const u
 
 // Step 4: per-tile [start,end) in the sorted instance list.
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t R, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges) {
+tile_ranges_kernel(uint32_t R, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges,
+                   uint32_t* __restrict__ header, uint4 header_words) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *reinterpret_cast<uint4*>(header) = header_words;   // binning-buffer header rides along
     if (i >= R) return;
     const uint32_t cur = sorted_tiles[i];
     if (i == 0) ranges[cur].x = 0;
@@ -161,8 +166,10 @@ cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32
 }
 
 // Step 4 launcher.
-cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, cudaStream_t s) {
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, sorted_tiles, img.ranges);
+cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
+                               const uint32_t header_words[4], cudaStream_t s) {
+    const uint4 hw = make_uint4(header_words[0], header_words[1], header_words[2], header_words[3]);
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, sorted_tiles, img.ranges, header, hw);
     return cudaGetLastError();
 }
 

@@ -84,10 +84,9 @@ struct GeomState {
     uint32_t* tiles_touched;  // [P]   tiles of the 3-sigma rect (the reference's count; sums to num_rendered)
     ushort4*  rect_kept;      // [P]   tile rect [x0,x1) x [y0,y1) actually binned: the reference's 3-sigma rect
                               //       clipped to the exact bounding box of the alpha >= 1/255 ellipse
-    uint32_t* counters;       // [32]  word 0: sum of tiles_touched (= the reference's num_rendered)
     uint32_t* depth_keys[2];  // [P]   float bits of depth (0xFFFFFFFF when culled); CUB double buffer
     uint32_t* depth_vals[2];  // [P]   Gaussian index; CUB double buffer
-    uint32_t* sorted_offsets; // [P]   inclusive scan of area(rect_kept) in depth order
+    uint64_t* sorted_offsets; // [P]   inclusive scan in depth order of (area(rect_kept) | tiles_touched << 32)
     char*     temp;           // CUB temp storage
     size_t    temp_bytes;
 };
@@ -219,7 +218,8 @@ void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes);
 cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s);
 cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
                              const uint32_t** sorted_tiles, cudaStream_t s);
-cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, cudaStream_t s);
+cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
+                               const uint32_t header_words[4], cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,

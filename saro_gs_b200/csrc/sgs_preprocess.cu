@@ -148,117 +148,153 @@ __forceinline__ __device__ void clip_rect_to_alpha_box(float2 p, float3 conic, f
     if (rmax.x <= rmin.x || rmax.y <= rmin.y) rmax = rmin;
 }
 
+#define SGS_PRE_THREADS 128
+#define SGS_SH_ROW4 12          // float4 per 16-coefficient SH row (192 B)
+#define SGS_SH_PAD4 13          // padded row stride in shared memory (conflict-free 128-bit accesses)
+
+// Warp-cooperative, fully coalesced load of the 32 SH rows of a warp (6 KB contiguous) into shared memory.
+__forceinline__ __device__ void load_sh_rows(float4* s_rows, const float* __restrict__ shs, int first_row, int nrows) {
+    const int lane = threadIdx.x & 31;
+    const float4* src = reinterpret_cast<const float4*>(shs + (size_t)first_row * 48);
+    const int total = nrows * SGS_SH_ROW4;
+#pragma unroll
+    for (int it = 0; it < SGS_SH_ROW4; it++) {
+        const int e = it * 32 + lane;
+        if (e < total) {
+            const int row = e / SGS_SH_ROW4, c = e - row * SGS_SH_ROW4;
+            s_rows[row * SGS_SH_PAD4 + c] = __ldg(src + e);
+        }
+    }
+    __syncwarp();
+}
+
 template <bool VEC_SH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SGS_PRE_THREADS)
 preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float* __restrict__ means3D,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
                       int* __restrict__ radii, GeomState g, int cull) {
     __shared__ ViewSmem cam;
+    __shared__ float4 s_sh[VEC_SH ? (SGS_PRE_THREADS / 32) * 32 * SGS_SH_PAD4 : 1];
     stage_view(cam, vp);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned live = __ballot_sync(0xFFFFFFFFu, idx < P);
-    if (idx >= P) return;
+    const bool valid = idx < P;
 
     // defaults for a Gaussian that takes no further part
     int out_radius = 0;
     uint32_t out_tiles = 0;
     uint32_t out_key = 0xFFFFFFFFu;
     ushort4 out_rect = {0, 0, 0, 0};
+    bool visible = false;
+    float3 p_orig = {0.f, 0.f, 0.f};
+    float depth = 0.f;
 
-    const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-    const float3 p_view = xform_point_4x3(p_orig, cam.view);
+    if (valid) {
+        p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        const float3 p_view = xform_point_4x3(p_orig, cam.view);
+        depth = p_view.z;
 
-    bool alive = !(p_view.z <= 0.2f);
-    if (!alive && vp.prefiltered) {
-        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-        __trap();
-    }
-
-    if (alive) {
-        float4 p_hom = xform_point_4x4(p_orig, cam.proj);
-        float p_w = 1.0f / (p_hom.w + 0.0000001f);
-        float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
-
-        float cov3D[6];
-        if (cov3D_precomp != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
-        } else {
-            const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
-            cov3d_from_scale_rot(sc, vp.scale_modifier, q, cov3D);
-#pragma unroll
-            for (int i = 0; i < 6; i++) g.cov3D[6 * idx + i] = cov3D[i];
+        bool alive = !(p_view.z <= 0.2f);
+        if (!alive && vp.prefiltered) {
+            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+            __trap();
         }
 
-        float3 cov = cov2d_from_cov3d(p_orig, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cov3D, cam.view);
+        if (alive) {
+            float4 p_hom = xform_point_4x4(p_orig, cam.proj);
+            float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
 
-        float det = (cov.x * cov.z - cov.y * cov.y);
-        if (det != 0.0f) {
-            float det_inv = 1.f / det;
-            float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+            float cov3D[6];
+            if (cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
+            } else {
+                const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+                const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+                cov3d_from_scale_rot(sc, vp.scale_modifier, q, cov3D);
+#pragma unroll
+                for (int i = 0; i < 6; i++) g.cov3D[6 * idx + i] = cov3D[i];
+            }
 
-            float mid = 0.5f * (cov.x + cov.z);
-            float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
-            float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
-            float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
-            float2 point_image = {ndc2pix(p_proj.x, vp.W), ndc2pix(p_proj.y, vp.H)};
-            uint2 rmin, rmax;
-            get_rect(point_image, (int)my_radius, rmin, rmax, vp.tiles_x, vp.tiles_y);
-            uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
-            if (ntiles != 0) {
-                float3 rgb;
-                uint8_t cmask = 0;
-                if (colors_precomp == nullptr) {
-                    V3 sh[16];
-                    const int M = vp.sh_coeffs;
-                    if (VEC_SH) {
-                        // M == 16, row is 192 B and 16-B aligned: twelve 128-bit loads
-                        const float4* row = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
-                        float f[48];
-#pragma unroll
-                        for (int k = 0; k < 12; k++) {
-                            float4 v = __ldg(row + k);
-                            f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 16; k++) sh[k] = {f[3 * k], f[3 * k + 1], f[3 * k + 2]};
-                    } else {
-                        const float* row = shs + (size_t)idx * M * 3;
-                        const int ncoef = (vp.sh_degree + 1) * (vp.sh_degree + 1);
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            if (k < ncoef) sh[k] = {row[3 * k], row[3 * k + 1], row[3 * k + 2]};
-                            else sh[k] = {0.f, 0.f, 0.f};
-                        }
-                    }
-                    V3 c = eval_sh(vp.sh_degree, sh, V3{p_orig.x, p_orig.y, p_orig.z}, cam.campos, cmask);
-                    rgb = {c.x, c.y, c.z};
-                } else {
-                    rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
+            float3 cov = cov2d_from_cov3d(p_orig, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cov3D, cam.view);
+
+            float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det != 0.0f) {
+                float det_inv = 1.f / det;
+                float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+                float mid = 0.5f * (cov.x + cov.z);
+                float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+                float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+                float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+                float2 point_image = {ndc2pix(p_proj.x, vp.W), ndc2pix(p_proj.y, vp.H)};
+                uint2 rmin, rmax;
+                get_rect(point_image, (int)my_radius, rmin, rmax, vp.tiles_x, vp.tiles_y);
+                uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
+                if (ntiles != 0) {
+                    visible = true;
+                    const float o = opacities[idx];
+                    g.depths[idx] = p_view.z;
+                    g.means2D[idx] = point_image;
+                    g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, o);
+                    out_radius = (int)my_radius;
+                    out_tiles = ntiles;
+                    if (cull) clip_rect_to_alpha_box(point_image, conic, o, my_radius, rmin, rmax);
+                    out_rect = make_ushort4((unsigned short)rmin.x, (unsigned short)rmax.x, (unsigned short)rmin.y,
+                                            (unsigned short)rmax.y);
+                    out_key = __float_as_uint(p_view.z);
                 }
-                g.depths[idx] = p_view.z;
-                g.means2D[idx] = point_image;
-                g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
-                g.rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, p_view.z);
-                g.clamped[idx] = cmask;
-                out_radius = (int)my_radius;
-                out_tiles = ntiles;
-                if (cull) clip_rect_to_alpha_box(point_image, conic, opacities[idx], my_radius, rmin, rmax);
-                out_rect = make_ushort4((unsigned short)rmin.x, (unsigned short)rmax.x, (unsigned short)rmin.y,
-                                        (unsigned short)rmax.y);
-                out_key = __float_as_uint(p_view.z);
             }
         }
     }
+
+    // ---- colour: SH rows are fetched by the whole warp (coalesced) when any of its Gaussians is visible
+    if (colors_precomp == nullptr) {
+        V3 sh[16];
+        if (VEC_SH) {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            float4* rows = s_sh + warp * 32 * SGS_SH_PAD4;
+            const int first_row = blockIdx.x * blockDim.x + warp * 32;
+            if (__any_sync(0xFFFFFFFFu, visible)) {
+                load_sh_rows(rows, shs, first_row, min(32, P - first_row));
+                if (visible) {
+                    float f[48];
+#pragma unroll
+                    for (int k = 0; k < SGS_SH_ROW4; k++) {
+                        const float4 v = rows[lane * SGS_SH_PAD4 + k];
+                        f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) sh[k] = {f[3 * k], f[3 * k + 1], f[3 * k + 2]};
+                }
+            }
+        } else if (visible) {
+            const int M = vp.sh_coeffs;
+            const float* row = shs + (size_t)idx * M * 3;
+            const int ncoef = (vp.sh_degree + 1) * (vp.sh_degree + 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < ncoef) sh[k] = {row[3 * k], row[3 * k + 1], row[3 * k + 2]};
+                else sh[k] = {0.f, 0.f, 0.f};
+            }
+        }
+        if (visible) {
+            uint8_t cmask = 0;
+            V3 c = eval_sh(vp.sh_degree, sh, V3{p_orig.x, p_orig.y, p_orig.z}, cam.campos, cmask);
+            g.rgbd[idx] = make_float4(c.x, c.y, c.z, depth);
+            g.clamped[idx] = cmask;
+        }
+    } else if (visible) {
+        g.rgbd[idx] = make_float4(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2], depth);
+        g.clamped[idx] = 0;
+    }
+
+    if (!valid) return;
     radii[idx] = out_radius;
     g.tiles_touched[idx] = out_tiles;
     g.rect_kept[idx] = out_rect;
-    // the reference's num_rendered = sum of tiles_touched: one integer atomic per warp
-    const uint32_t wsum = __reduce_add_sync(live, out_tiles);
-    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&g.counters[0], wsum);
     g.depth_keys[0][idx] = out_key;
     g.depth_vals[0][idx] = (uint32_t)idx;
 }
@@ -268,7 +304,7 @@ void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, co
                            const float* cov3D_precomp, const float* colors_precomp, int* radii, GeomState g,
                            int cull, cudaStream_t s) {
     if (P <= 0) return;
-    const int block = 256;
+    const int block = SGS_PRE_THREADS;
     const int grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0);
     if (vec)

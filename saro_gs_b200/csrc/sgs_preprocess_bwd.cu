@@ -36,8 +36,12 @@ __forceinline__ __device__ float3 dnormvdv3(float3 v, float3 dv) {
     return r;
 }
 
+#define SGS_PRE_THREADS 128
+#define SGS_SH_ROW4 12          // float4 per 16-coefficient SH row (192 B)
+#define SGS_SH_PAD4 13          // padded row stride in shared memory (conflict-free 128-bit accesses)
+
 template <bool VEC_SH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SGS_PRE_THREADS)
 preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -47,11 +51,31 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
     __shared__ ViewSmem cam;
+    // SH rows travel through shared memory so that both the 192-B reads and the 192-B gradient writes of a
+    // warp are fully coalesced (32 consecutive rows = 6 KB contiguous)
+    __shared__ float4 s_sh[VEC_SH ? (SGS_PRE_THREADS / 32) * 32 * SGS_SH_PAD4 : 1];
     stage_view(cam, vp);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    const bool valid = idx < P;
     const int M = vp.sh_coeffs;
-    const bool visible = radii[idx] > 0;
+    const bool visible = valid && radii[idx] > 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* rows = s_sh + (VEC_SH ? warp * 32 * SGS_SH_PAD4 : 0);
+    const int first_row = blockIdx.x * blockDim.x + warp * 32;
+    const int nrows = min(32, P - first_row);
+    if (VEC_SH && shs != nullptr && __any_sync(0xFFFFFFFFu, visible)) {
+        const float4* src = reinterpret_cast<const float4*>(shs + (size_t)first_row * 48);
+        const int total = nrows * SGS_SH_ROW4;
+#pragma unroll
+        for (int it = 0; it < SGS_SH_ROW4; it++) {
+            const int e = it * 32 + lane;
+            if (e < total) {
+                const int row = e / SGS_SH_ROW4, c = e - row * SGS_SH_ROW4;
+                rows[row * SGS_SH_PAD4 + c] = __ldg(src + e);
+            }
+        }
+        __syncwarp();
+    }
 
     float o_mean2D[3] = {0.f, 0.f, 0.f};
     float o_opacity = 0.f;
@@ -173,11 +197,10 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
 
             F3 sh[16];
             if (VEC_SH) {
-                const float4* row = reinterpret_cast<const float4*>(shs + (size_t)idx * 48);
                 float f[48];
 #pragma unroll
                 for (int k = 0; k < 12; k++) {
-                    const float4 v = __ldg(row + k);
+                    const float4 v = rows[lane * SGS_SH_PAD4 + k];
                     f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
                 }
 #pragma unroll
@@ -299,28 +322,45 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     }
 
     // ---- write everything (zeros when culled) --------------------------------------------------
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        dL_dmean2D[3 * idx + i] = o_mean2D[i];
-        dL_dcolor[3 * idx + i] = o_color[i];
-        dL_dmean3D[3 * idx + i] = o_mean3D[i];
-        dL_dscale[3 * idx + i] = o_scale[i];
+        for (int i = 0; i < 3; i++) {
+            dL_dmean2D[3 * idx + i] = o_mean2D[i];
+            dL_dcolor[3 * idx + i] = o_color[i];
+            dL_dmean3D[3 * idx + i] = o_mean3D[i];
+            dL_dscale[3 * idx + i] = o_scale[i];
+        }
+        dL_dopacity[idx] = o_opacity;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = o_cov[i];
+        reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
     }
-    dL_dopacity[idx] = o_opacity;
-#pragma unroll
-    for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = o_cov[i];
-    reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
     if (M > 0) {
         if (VEC_SH) {
+            // every lane has consumed its input row: reuse the buffer for the gradient rows
+            __syncwarp();
             float f[48];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 f[3 * k] = o_sh[k].x; f[3 * k + 1] = o_sh[k].y; f[3 * k + 2] = o_sh[k].z;
             }
-            float4* row = reinterpret_cast<float4*>(dL_dsh + (size_t)idx * 48);
 #pragma unroll
-            for (int k = 0; k < 12; k++) row[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-        } else {
+            for (int k = 0; k < 12; k++)
+                rows[lane * SGS_SH_PAD4 + k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+            __syncwarp();
+            if (nrows > 0) {
+                float4* dst = reinterpret_cast<float4*>(dL_dsh + (size_t)first_row * 48);
+                const int total = nrows * SGS_SH_ROW4;
+#pragma unroll
+                for (int it = 0; it < SGS_SH_ROW4; it++) {
+                    const int e = it * 32 + lane;
+                    if (e < total) {
+                        const int row = e / SGS_SH_ROW4, c = e - row * SGS_SH_ROW4;
+                        dst[e] = rows[row * SGS_SH_PAD4 + c];
+                    }
+                }
+            }
+        } else if (valid) {
             float* row = dL_dsh + (size_t)idx * M * 3;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
@@ -341,7 +381,7 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                            cudaStream_t s) {
     if (P <= 0) return;
-    const int block = 256, grid = (P + block - 1) / block;
+    const int block = SGS_PRE_THREADS, grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0) &&
                      ((reinterpret_cast<size_t>(dL_dsh) & 15) == 0);
     if (vec)
