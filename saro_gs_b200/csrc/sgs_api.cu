@@ -241,6 +241,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (P < 0 || width <= 0 || height <= 0 || width > 16 * 65535 || height > 16 * 65535)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: bad sizes");
     if (P == 0) return 0;  // reference binding skips the call entirely ($R/rasterize_points.cu:80)
+    if (P >= (1 << 28)) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: more than 2^28 - 1 Gaussians");
     if (!geometry_buffer || !binning_buffer || !image_buffer)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: null resize callback");
     if (!means3D || !opacities || !viewmatrix || !projmatrix || !cam_pos || !background || !out_color ||

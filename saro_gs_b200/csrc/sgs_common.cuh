@@ -106,7 +106,7 @@ struct __align__(16) PackedInst {
     float C, opacity, thr;     // conic C, opacity, skip threshold on `power`
     uint32_t list_pos;         // 0-based position in the tile's original sorted list
     float r, g, b;             // colour
-    uint32_t gid;              // Gaussian index
+    uint32_t gid;              // Gaussian index (low 28 bits) | quadrant visit mask (top 4 bits)
 };
 static_assert(sizeof(PackedInst) == 48, "PackedInst must be 48 bytes");
 

@@ -9,12 +9,15 @@
 // B200 design (the reference issues 9 global float atomics per contributing pixel x instance,
 // SURVEY.md §2.1; the kernel is FP32-issue bound, so everything below is about instructions per
 // blended pair):
-//   * reads the dense tile-ordered `PackedInst` list written by the forward kernel with coalesced
-//     16-byte loads (no index gathers, culled instances never appear);
+//   * streams the dense tile-ordered `PackedInst` list written by the forward kernel through a 4-stage
+//     shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier): no index gathers, no staging
+//     instructions, and NO block-wide barrier in the main loop — a warp whose quadrant is cheap runs ahead of
+//     its neighbours by up to 3 batches, and the last warp to leave a stage refills it;
 //   * 128 threads per tile, 2 vertically adjacent pixels per thread, warp = 8x8 quadrant; packed f32x2
 //     evaluation of the quadratic form (sgs_render_common.cuh);
-//   * per-warp visit bitmaps: a warp only visits instances whose quadrant mask has its bit AND whose
-//     list position is below the last contributor of some pixel of the warp;
+//   * per-warp visit bitmaps: a warp only visits instances whose quadrant mask (computed once by the forward
+//     kernel, stored in the top 4 bits of the record's Gaussian-id word) has its bit AND whose list position is
+//     below the last contributor of some pixel of the warp;
 //   * per pair only what depends on the pixel is computed:  g = G dL/dalpha  and  w = alpha T ;
 //     the warp accumulates the MOMENTS  sum g, sum g dx, sum g dy, sum g dx^2, sum g dx dy, sum g dy^2
 //     and  sum w dL/dpix[c]  — the multiplications by opacity, conic and 0.5W/0.5H happen once per
@@ -48,8 +51,17 @@ struct BwdPix {
 
 // one pixel x one instance: returns g = G * dL/dalpha and w = alpha * T (0, 0 when the pair did not blend)
 __forceinline__ __device__ void grad_pixel(BwdPix& s, float power, float o, const float4 c, float& g, float& w) {
-    const float G = expf(power);
-    const float alpha = min(0.99f, o * G);
+    // exp(): forward uses the accurate expf() because its image must equal the reference's bit for bit.  Here
+    // only the DECISION  alpha >= 1/255  has to agree with forward; the value of G may carry a few ulp.
+    // ex2.approx(power * log2 e) is within ~1e-6 relative of expf(power) on [-6, 0]; when alpha lands within
+    // 1e-5 relative of the threshold the accurate expf() arbitrates (rare), so the decision is always forward's.
+    float G;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
+    float alpha = min(0.99f, o * G);
+    if (fabsf(alpha - 1.0f / 255.0f) < 4e-8f) {
+        G = expf(power);
+        alpha = min(0.99f, o * G);
+    }
     if (alpha < 1.0f / 255.0f) return;
     const float om = 1.f - alpha;       // in [0.01, 1]: the approximate reciprocal is safe (<= 1 ulp)
     float inv;
@@ -65,15 +77,48 @@ __forceinline__ __device__ void grad_pixel(BwdPix& s, float power, float o, cons
     s.last_om = om;
 }
 
+// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UBLKCP + SYNCS) ---------------------------------------
+__forceinline__ __device__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__forceinline__ __device__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__forceinline__ __device__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes: multiple of 16, 16-B aligned)
+__forceinline__ __device__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__forceinline__ __device__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+#define SGS_B_STAGES 4
+#define SGS_B_STAGE_BYTES (SGS_R_BATCH * 48)
+
 __global__ void __launch_bounds__(SGS_R_THREADS)
 render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
                   const uint32_t* __restrict__ tile_count, const PackedInst* __restrict__ packed,
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dpix, float* __restrict__ acc) {
-    __shared__ float4 s_g0[SGS_R_BATCH];   // x, y, A, -B
-    __shared__ float4 s_g1[SGS_R_BATCH];   // C, thr, list_pos(bits), opacity
-    __shared__ float4 s_g2[SGS_R_BATCH];   // r, g, b, gid(bits)
-    __shared__ uint32_t s_mask[SGS_R_BATCH];
+    // ring of record batches filled by TMA bulk copies; no block-wide barrier in the main loop
+    __shared__ __align__(128) unsigned char s_rec[SGS_B_STAGES * SGS_B_STAGE_BYTES];
+    __shared__ __align__(8) uint64_t s_full[SGS_B_STAGES];   // mbarriers: "batch has landed"
+    __shared__ uint32_t s_done[SGS_B_STAGES];                // warps that finished the batch in this stage
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -91,6 +136,29 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const uint32_t start = ranges[tile].x;
     const int count = (int)tile_count[tile];
     if (count == 0) return;
+    const int nb = (count + SGS_R_BATCH - 1) / SGS_R_BATCH;      // batches, walked from the back of the list
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(packed + start);
+    uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
+    const uint32_t full_base = (uint32_t)__cvta_generic_to_shared(s_full);
+    asm volatile("" : "+r"(rec_base));
+
+    // batch j covers records [lo, hi) with hi = count - 128 j
+    auto issue = [&](int j) {
+        const int hi = count - j * SGS_R_BATCH, lo = max(0, hi - SGS_R_BATCH);
+        const uint32_t bytes = (uint32_t)(hi - lo) * 48u;
+        const int stage = j % SGS_B_STAGES;
+        mbar_expect_tx(full_base + stage * 8, bytes);
+        tma_load_1d(rec_base + stage * SGS_B_STAGE_BYTES, src + (size_t)lo * 48, bytes, full_base + stage * 8);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SGS_B_STAGES; s++) {
+            mbar_init(full_base + s * 8, 1);
+            s_done[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < min(nb, SGS_B_STAGES); j++) issue(j);
+    }
 
     BwdPix p0, p1;
     {
@@ -125,35 +193,27 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
     float* const acc_lane = acc + my_slot;
 
-    const float4* src = reinterpret_cast<const float4*>(packed + start);
-    uint32_t a0 = (uint32_t)__cvta_generic_to_shared(s_g0);
-    uint32_t a1 = (uint32_t)__cvta_generic_to_shared(s_g1);
-    uint32_t a2 = (uint32_t)__cvta_generic_to_shared(s_g2);
-    asm volatile("" : "+r"(a0), "+r"(a1), "+r"(a2));
+    __syncthreads();   // mbarrier initialisation visible to every warp (the only block-wide barrier)
 
-    for (int hi = count; hi > 0; hi -= SGS_R_BATCH) {
-        const int lo = max(0, hi - SGS_R_BATCH);
+    for (int j = 0; j < nb; j++) {
+        const int stage = j % SGS_B_STAGES;
+        const int hi = count - j * SGS_R_BATCH, lo = max(0, hi - SGS_R_BATCH);
         const int nrec = hi - lo;
-        __syncthreads();
-        if (tid < nrec) {
-            const float4* r = src + (size_t)(lo + tid) * 3;
-            const float4 ra = r[0];   // x, y, A, B
-            const float4 rb = r[1];   // C, opacity, thr, list_pos
-            const float4 rc = r[2];   // r, g, b, gid
-            s_g0[tid] = make_float4(ra.x, ra.y, ra.z, -ra.w);
-            s_g1[tid] = make_float4(rb.x, rb.z, rb.w, rb.y);
-            s_g2[tid] = rc;
-            s_mask[tid] = quadrant_mask(ra.x, ra.y, ra.z, ra.w, rb.x, rb.z, (float)tx0, (float)ty0);
-        }
-        __syncthreads();
+        const uint32_t sbase = rec_base + stage * SGS_B_STAGE_BYTES;
+        mbar_wait(full_base + stage * 8, (uint32_t)((j / SGS_B_STAGES) & 1));
 
-        // visit bitmap of this warp: quadrant bit set and list position below the warp's last contributor
+        // visit bitmap of this warp: quadrant bit (top 4 bits of the gid word) set and list position below the
+        // warp's last contributor
         uint32_t mywords = 0;
 #pragma unroll
         for (int k = 0; k < SGS_R_BATCH / 32; k++) {
             const int slot = k * 32 + lane;
             bool v = false;
-            if (slot < nrec) v = ((s_mask[slot] >> warp) & 1u) && (__float_as_uint(s_g1[slot].z) < warp_last);
+            if (slot < nrec) {
+                const uint32_t gw = lds32(sbase + slot * 48u + 44u);
+                const uint32_t pos = lds32(sbase + slot * 48u + 28u);
+                v = ((gw >> (28 + warp)) & 1u) && (pos < warp_last);
+            }
             const uint32_t b = __ballot_sync(0xFFFFFFFFu, v);
             if (lane == k) mywords = b;
         }
@@ -163,24 +223,24 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
             while (word) {
                 const uint32_t bit = 31u - __clz(word);
                 word ^= 1u << bit;
-                const uint32_t j = k * 32 + bit;
-                const float4 g0 = lds128(a0 + j * 16u);
-                const float4 g1 = lds128(a1 + j * 16u);
+                const uint32_t rec = sbase + (k * 32 + bit) * 48u;
+                const float4 ra = lds128(rec);          // x, y, A, B
+                const float4 rb = lds128(rec + 16u);    // C, opacity, thr, list_pos
                 float dx;
                 float2 dy;
-                const float2 pw = power2(g0, g1.x, pxf, npy, dx, dy);
-                const uint32_t pos = __float_as_uint(g1.z);
+                const float2 pw = power2(make_float4(ra.x, ra.y, ra.z, -ra.w), rb.x, pxf, npy, dx, dy);
+                const uint32_t pos = __float_as_uint(rb.w);
                 // same tests as forward: power > 0 -> skip; power < thr -> provably alpha < 1/255
                 // (a separate cheaper warp-level pre-test was measured slower: with the visit bitmaps
                 // nearly every visit blends something, so the exact tests are needed anyway)
-                const bool act0 = (pos < p0.lc) && !(pw.x > 0.0f) && !(pw.x < g1.y);
-                const bool act1 = (pos < p1.lc) && !(pw.y > 0.0f) && !(pw.y < g1.y);
+                const bool act0 = (pos < p0.lc) && !(pw.x > 0.0f) && !(pw.x < rb.z);
+                const bool act1 = (pos < p1.lc) && !(pw.y > 0.0f) && !(pw.y < rb.z);
                 if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;
 
-                const float4 c = lds128(a2 + j * 16u);   // r, g, b, gid
+                const float4 c = lds128(rec + 32u);   // r, g, b, gid | quadrant mask << 28
                 float g_0 = 0.f, w_0 = 0.f, g_1 = 0.f, w_1 = 0.f;
-                if (act0) grad_pixel(p0, pw.x, g1.w, c, g_0, w_0);
-                if (act1) grad_pixel(p1, pw.y, g1.w, c, g_1, w_1);
+                if (act0) grad_pixel(p0, pw.x, rb.y, c, g_0, w_0);
+                if (act1) grad_pixel(p1, pw.y, rb.y, c, g_1, w_1);
 
                 // moments of g over this thread's two pixels (dx shared)
                 const float gy0 = g_0 * dy.x, gy1 = g_1 * dy.y;
@@ -213,7 +273,18 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 // step 5 (xor 1)
                 r += __shfl_xor_sync(0xFFFFFFFFu, r, 1);
 
-                if (writer) atomicAdd(acc_lane + (size_t)__float_as_uint(c.w) * 12, r);
+                if (writer) atomicAdd(acc_lane + (size_t)(__float_as_uint(c.w) & 0x0FFFFFFFu) * 12, r);
+            }
+        }
+
+        // this warp is done with the stage; the LAST warp to finish refills it with batch j + STAGES
+        __syncwarp();
+        if (lane == 0 && j + SGS_B_STAGES < nb) {
+            const uint32_t old = atomicAdd(&s_done[stage], 1u);
+            if (old == SGS_R_THREADS / 32 - 1) {
+                s_done[stage] = 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(j + SGS_B_STAGES);
             }
         }
     }

@@ -50,7 +50,7 @@ __forceinline__ __device__ void blend_pixel(FwdPix& s, float power, float o, con
 }
 
 template <bool WRITE_PACKED, bool TILE_CULL>
-__global__ void __launch_bounds__(SGS_R_THREADS)
+__global__ void __launch_bounds__(SGS_R_THREADS, 10)
 render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
                   const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
                   const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
@@ -132,7 +132,7 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 float4* dst = reinterpret_cast<float4*>(packed + (size_t)range.x + packed_count + pos);
                 dst[0] = make_float4(r0.x, r0.y, r0.z, Bc);                      // x, y, A, B
                 dst[1] = make_float4(r1.x, r1.w, r1.y, r1.z);                    // C, opacity, thr, list_pos
-                dst[2] = make_float4(r2.x, r2.y, r2.z, __uint_as_float(gid));    // r, g, b, gid
+                dst[2] = make_float4(r2.x, r2.y, r2.z, __uint_as_float(gid | (mask << 28)));   // r, g, b, gid | mask
             }
         }
         packed_count += total;
