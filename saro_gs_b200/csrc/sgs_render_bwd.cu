@@ -51,21 +51,16 @@ struct BwdPix {
 
 // one pixel x one instance: returns g = G * dL/dalpha and w = alpha * T (0, 0 when the pair did not blend)
 __forceinline__ __device__ void grad_pixel(BwdPix& s, float power, float o, const float4 c, float& g, float& w) {
-    // exp(): forward uses the accurate expf() because its image must equal the reference's bit for bit.  Here
-    // only the DECISION  alpha >= 1/255  has to agree with forward; the value of G may carry a few ulp.
-    // ex2.approx(power * log2 e) is within ~1e-6 relative of expf(power) on [-6, 0]; when alpha lands within
-    // 1e-5 relative of the threshold the accurate expf() arbitrates (rare), so the decision is always forward's.
-    float G;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
-    float alpha = min(0.99f, o * G);
-    if (fabsf(alpha - 1.0f / 255.0f) < 4e-8f) {
-        G = expf(power);
-        alpha = min(0.99f, o * G);
-    }
+    // accurate expf() and a < 1 ulp reciprocal, like forward / the reference: alpha must equal forward's bit for
+    // bit and T is recovered by a long product of 1/(1-alpha) factors — a bare ex2.approx / rcp.approx (~1e-7
+    // each, but biased) drifts T by ~n * 1e-7 over n blended instances (measured: 2.5x the error on dL/dmeans3D).
+    const float G = expf(power);
+    const float alpha = min(0.99f, o * G);
     if (alpha < 1.0f / 255.0f) return;
-    const float om = 1.f - alpha;       // in [0.01, 1]: the approximate reciprocal is safe (<= 1 ulp)
-    float inv;
+    const float om = 1.f - alpha;       // in [0.01, 1]: no denormal / overflow cases, so MUFU.RCP + one Newton
+    float inv;                          // step is accurate to < 1 ulp without __frcp_rn's special-case path
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
+    inv = fmaf(inv, fmaf(-om, inv, 1.0f), inv);
     s.T *= inv;                          // $R/.../backward.cu:503
     s.a_rec = fmaf(s.last_alpha, s.last_cd, s.last_om * s.a_rec);   // :515-519, dotted with dL/dpix
     const float cd = fmaf(c.z, s.d2, fmaf(c.y, s.d1, c.x * s.d0));

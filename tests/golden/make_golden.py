@@ -134,6 +134,74 @@ def run_big(RefRast, dev, name, scene, cam, crop=64):
     print(name, "R =", R, "visible =", int(out["visible"]), flush=True)
 
 
+SEQ_TIMES = (0.0, 0.37, 0.74, 0.99)
+
+
+def run_seq(RefRast, dev, name):
+    """BASELINE.json configs[2] stand-in: frames of the config-2 cloud under per-Gaussian temporal survival
+    (P varies per frame) — colour pass + the test-time second pass with precomputed colours
+    (renderer/__init__.py:212-226 of the reference renders `lifespan.expand(-1, 3)` with shs=None)."""
+    base, cam = synthetic.config2_scene()
+    rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                       cam.viewmatrix.to(dev), cam.projmatrix.to(dev), base.sh_degree,
+                                       cam.campos.to(dev), False)
+    out = dict(times=np.array(SEQ_TIMES, np.float64))
+    refC = ref_loader.load_ref_C()
+    e = torch.Tensor([])
+    with torch.no_grad():
+        for k, t in enumerate(SEQ_TIMES):
+            sc = synthetic.temporal_frame(base, t)
+            P = sc.means3D.shape[0]
+            m3, op, scl, rot, sh = (x.to(dev) for x in (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.shs))
+            R, color, radii, gb, bb, ib, depth = refC.rasterize_gaussians(
+                rs.bg, m3, e, op, scl, rot, 1.0, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, cam.height,
+                cam.width, sh, sc.sh_degree, rs.campos, False)
+            life = op.expand(-1, 3).contiguous()
+            R2, color2, radii2, _, _, _, depth2 = refC.rasterize_gaussians(
+                rs.bg, m3, life, op, scl, rot, 1.0, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                cam.height, cam.width, e, 0, rs.campos, False)
+            out[f"P_{k}"] = np.int64(P)
+            out[f"R_{k}"] = np.int64(R)
+            out[f"sha_color_{k}"] = sha(color)
+            out[f"sha_depth_{k}"] = sha(depth)
+            out[f"sha_radii_{k}"] = sha(radii)
+            out[f"sha_color_life_{k}"] = sha(color2)
+            print(name, "t =", t, "P =", P, "R =", R, flush=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def run_big_grad(RefRast, dev, name, scene, cam, n_samples=4096):
+    """Full-size backward of the reference (configs[1], standard cotangent): per-tensor norms, max |.| and a
+    seeded sample of entries.  The reference sums with float atomics, so these are reproducible to ~1e-6 only."""
+    rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                       cam.viewmatrix.to(dev), cam.projmatrix.to(dev), scene.sh_degree,
+                                       cam.campos.to(dev), False)
+    leaves = {k: getattr(scene, k).to(dev).clone().requires_grad_(True)
+              for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    color, radii, depth = RefRast(rs)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                                      shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+    color.backward(synthetic.cotangent(cam.height, cam.width).to(dev))
+    torch.cuda.synchronize()
+    grads = {k: v.grad for k, v in leaves.items()}
+    grads["means2D"] = means2D.grad
+    out = {}
+    gen = torch.Generator().manual_seed(1234)
+    for k, g in grads.items():
+        flat = g.detach().reshape(-1).cpu()
+        idx = torch.randint(0, flat.numel(), (n_samples,), generator=gen)
+        # half of the sample among the largest entries, so the check is not dominated by zeros
+        top = torch.topk(flat.abs(), n_samples // 2).indices
+        idx[: n_samples // 2] = top
+        out[f"idx_{k}"] = idx.numpy()
+        out[f"val_{k}"] = flat[idx].numpy()
+        out[f"norm_{k}"] = np.float64(flat.double().norm().item())
+        out[f"maxabs_{k}"] = np.float64(flat.abs().max().item())
+        out[f"sum_{k}"] = np.float64(flat.double().sum().item())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: float(out[f"norm_{k}"]) for k in grads}, flush=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     dev = torch.device("cuda:0")
@@ -142,6 +210,8 @@ def main():
         run_case(RefRast, dev, name, spec)
     run_big(RefRast, dev, "config1_fwd", *synthetic.config1_scene())
     run_big(RefRast, dev, "config2_fwd", *synthetic.config2_scene())
+    run_big_grad(RefRast, dev, "config2_bwd", *synthetic.config2_scene())
+    run_seq(RefRast, dev, "config3_seq")
 
 
 if __name__ == "__main__":

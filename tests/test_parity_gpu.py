@@ -186,6 +186,65 @@ def test_full_size_bit_exact_tile_counts(sgs, dev, cfg):
             assert st["kept"] < R
 
 
+def test_full_size_backward_vs_reference_golden(sgs, dev):
+    """configs[1] backward at full size against the compiled reference's gradients (tests/golden/config2_bwd.npz:
+    per-tensor norms + a sample of entries, half of them the largest ones)."""
+    from saro_gs_b200 import synthetic
+    d = load("config2_bwd")
+    scene, cam = synthetic.config2_scene()
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), scene.sh_degree,
+                                           cam.campos.to(dev), False)
+    leaves = {k: getattr(scene, k).to(dev).requires_grad_(True)
+              for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    color, radii, depth = sgs.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d,
+                                                    opacities=leaves["opacities"], shs=leaves["shs"],
+                                                    scales=leaves["scales"], rotations=leaves["rotations"])
+    color.backward(synthetic.cotangent(cam.height, cam.width).to(dev))
+    grads = {k: v.grad for k, v in leaves.items()}
+    grads["means2D"] = m2d.grad
+    # At this size the reference does not reproduce ITSELF to 1e-4 on the cancellation-prone tensors: two runs of
+    # the compiled reference differ by 2.5e-4 (scales) and 1.1e-3 (rotations) of the largest entry, because its
+    # float atomics sum in a different order every run (measured on B200 with tools/grad_noise.py; the native
+    # kernels' own run-to-run spread is smaller: 2.3e-4 / 7e-4).  Those two tensors get a bar of a few times the
+    # reference's own noise; everything else meets the 1e-4 bar.
+    tol = {"scales": 1e-3, "rotations": 3e-3}
+    for k, g in grads.items():
+        flat = g.detach().reshape(-1).cpu().numpy().astype(np.float64)
+        ref_val = d[f"val_{k}"].astype(np.float64)
+        got_val = flat[d[f"idx_{k}"]]
+        scale = float(d[f"maxabs_{k}"])
+        err = np.abs(got_val - ref_val).max() / scale
+        assert err < tol.get(k, GRAD_TOL), (k, err)
+        assert normrel(got_val, ref_val) < 5e-4, (k, normrel(got_val, ref_val))
+        assert abs(np.linalg.norm(flat) - float(d[f"norm_{k}"])) / float(d[f"norm_{k}"]) < GRAD_TOL, k
+
+
+def test_config3_sequence_bit_exact(sgs, dev):
+    """BASELINE.json configs[2] stand-in: frames with a varying number of live Gaussians; colour, depth and
+    radii hash-equal to the reference, for the SH pass and for the precomputed-colour ('lifespan') pass."""
+    from saro_gs_b200 import synthetic
+    d = load("config3_seq")
+    base, cam = synthetic.config2_scene()
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), base.sh_degree,
+                                           cam.campos.to(dev), False)
+    rast = sgs.GaussianRasterizer(rs)
+    with torch.no_grad():
+        for k, t in enumerate(d["times"]):
+            sc = synthetic.temporal_frame(base, float(t))
+            assert sc.means3D.shape[0] == int(d[f"P_{k}"])
+            m3, op, scl, rot, sh = (x.to(dev) for x in (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.shs))
+            color, radii, depth = rast(means3D=m3, means2D=torch.zeros_like(m3), opacities=op, shs=sh, scales=scl,
+                                       rotations=rot)
+            assert _sha(color) == str(d[f"sha_color_{k}"]) and _sha(depth) == str(d[f"sha_depth_{k}"])
+            assert _sha(radii) == str(d[f"sha_radii_{k}"])
+            color2, _, _ = rast(means3D=m3, means2D=torch.zeros_like(m3), opacities=op, shs=None,
+                                colors_precomp=op.expand(-1, 3), scales=scl, rotations=rot)
+            assert _sha(color2) == str(d[f"sha_color_life_{k}"])
+
+
 def test_full_size_backward_properties(sgs, dev):
     """configs[1] backward at full size: linear in the cotangent, zero for culled Gaussians,
     deterministic forward."""
