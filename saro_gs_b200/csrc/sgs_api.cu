@@ -325,7 +325,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
         {
             StageScope sc(SGS_STAGE_TILE_RANGES, s, 1);
             const uint32_t hw[4] = {point_list == bc.b.gauss_vals[1] ? 1u : 0u, hdr[1], hdr[2], 0u};
-            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, sorted_tiles, img, bc.header, hw, s));
+            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, (int)tiles, sorted_tiles, img, bc.header, hw, s));
         }
     } else {
         SGS_CUDA_OK(cudaMemcpyAsync(bc.header, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));

@@ -49,11 +49,15 @@ void binning_geom_temp_bytes(int P, size_t* bytes) {
     *bytes = (a > b ? a : b) + 256;
 }
 
+// Tile ids are sorted as 16-bit keys whenever the grid has at most 65536 tiles (16.7 Mpixel): 6 instead of 8 bytes
+// per instance through the emit kernel, both onesweep passes and the range detection.
 void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes) {
-    size_t a = 0;
+    size_t a = 0, b = 0;
     cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int64_t)R, 0, tile_bits);
-    *bytes = a + 256;
+    cub::DoubleBuffer<uint16_t> k16(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b, k16, v, (int64_t)R, 0, tile_bits < 16 ? tile_bits : 16);
+    *bytes = (a > b ? a : b) + 256;
 }
 
 #define SGS_DUP_SMALL 8
@@ -80,9 +84,10 @@ cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s) {
 // visiting Gaussians in depth order.  Small rects are written by the owning thread; large rects are
 // written by the whole warp (coalesced), which removes the long divergent per-thread loops
 // of the reference's duplicateWithKeys.
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
 duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const uint64_t* __restrict__ sorted_offsets,
-                 const ushort4* __restrict__ rect_kept, uint32_t* __restrict__ tile_keys,
+                 const ushort4* __restrict__ rect_kept, KeyT* __restrict__ tile_keys,
                  uint32_t* __restrict__ gauss_vals) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -97,7 +102,7 @@ duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const u
     if (n > 0 && n <= SGS_DUP_SMALL) {
         for (uint32_t y = r.z; y < r.w; y++)
             for (uint32_t x = r.x; x < r.y; x++) {
-                tile_keys[off] = y * tiles_x + x;
+                tile_keys[off] = (KeyT)(y * tiles_x + x);
                 gauss_vals[off] = gid;
                 off++;
             }
@@ -114,15 +119,16 @@ duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const u
         const uint32_t sw = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.y, src) - sx0;
         for (uint32_t i = lane; i < sn; i += 32) {
             const uint32_t yy = i / sw, xx = i - yy * sw;
-            tile_keys[soff + i] = (sy0 + yy) * tiles_x + (sx0 + xx);
+            tile_keys[soff + i] = (KeyT)((sy0 + yy) * tiles_x + (sx0 + xx));
             gauss_vals[soff + i] = sgid;
         }
     }
 }
 
 // Step 4: per-tile [start,end) in the sorted instance list.
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t R, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges,
+tile_ranges_kernel(uint32_t R, const KeyT* __restrict__ sorted_tiles, uint2* __restrict__ ranges,
                    uint32_t* __restrict__ header, uint4 header_words) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *reinterpret_cast<uint4*>(header) = header_words;   // binning-buffer header rides along
@@ -146,9 +152,16 @@ static int bits_for_tiles(int n_tiles) {
 }
 
 // Step 2b launcher: emit the depth-ordered (tile, Gaussian) stream.
+static bool keys16(int n_tiles) { return n_tiles <= 65536; }
+
 cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s) {
-    duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, g.depth_vals[0], g.sorted_offsets, g.rect_kept,
-                                                    b.tile_keys[0], b.gauss_vals[0]);
+    if (keys16(vp.tiles_x * vp.tiles_y))
+        duplicate_kernel<uint16_t><<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, g.depth_vals[0], g.sorted_offsets,
+                                                                  g.rect_kept, reinterpret_cast<uint16_t*>(b.tile_keys[0]),
+                                                                  b.gauss_vals[0]);
+    else
+        duplicate_kernel<uint32_t><<<(P + 255) / 256, 256, 0, s>>>(P, vp.tiles_x, g.depth_vals[0], g.sorted_offsets,
+                                                                  g.rect_kept, b.tile_keys[0], b.gauss_vals[0]);
     return cudaGetLastError();
 }
 
@@ -156,20 +169,33 @@ cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningSt
 // holding the sorted Gaussian indices and tile ids.
 cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
                              const uint32_t** sorted_tiles, cudaStream_t s) {
-    cub::DoubleBuffer<uint32_t> keys(b.tile_keys[0], b.tile_keys[1]);
     cub::DoubleBuffer<uint32_t> vals(b.gauss_vals[0], b.gauss_vals[1]);
     size_t tb = b.temp_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
+    cudaError_t e;
+    if (keys16(n_tiles)) {
+        cub::DoubleBuffer<uint16_t> keys(reinterpret_cast<uint16_t*>(b.tile_keys[0]),
+                                         reinterpret_cast<uint16_t*>(b.tile_keys[1]));
+        e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
+        *sorted_tiles = reinterpret_cast<const uint32_t*>(keys.Current());
+    } else {
+        cub::DoubleBuffer<uint32_t> keys(b.tile_keys[0], b.tile_keys[1]);
+        e = cub::DeviceRadixSort::SortPairs(b.temp, tb, keys, vals, (int64_t)R, 0, bits_for_tiles(n_tiles), s);
+        *sorted_tiles = keys.Current();
+    }
     *point_list = vals.Current();
-    *sorted_tiles = keys.Current();
     return e;
 }
 
 // Step 4 launcher.
-cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
+cudaError_t launch_tile_ranges(size_t R, int n_tiles, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
                                const uint32_t header_words[4], cudaStream_t s) {
     const uint4 hw = make_uint4(header_words[0], header_words[1], header_words[2], header_words[3]);
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, sorted_tiles, img.ranges, header, hw);
+    const unsigned grid = (unsigned)((R + 255) / 256);
+    if (n_tiles <= 65536)
+        tile_ranges_kernel<uint16_t><<<grid, 256, 0, s>>>((uint32_t)R, reinterpret_cast<const uint16_t*>(sorted_tiles),
+                                                         img.ranges, header, hw);
+    else
+        tile_ranges_kernel<uint32_t><<<grid, 256, 0, s>>>((uint32_t)R, sorted_tiles, img.ranges, header, hw);
     return cudaGetLastError();
 }
 

@@ -112,7 +112,7 @@ static_assert(sizeof(PackedInst) == 48, "PackedInst must be 48 bytes");
 
 // Opaque "binning" state: per tile instance.  Replaces BinningState ($R/.../rasterizer_impl.h:59-69).
 struct BinningState {
-    uint32_t*   tile_keys[2];   // [R] tile id; CUB double buffer
+    uint32_t*   tile_keys[2];   // [R] tile id (stored as u16 when the grid has <= 65536 tiles); CUB double buffer
     uint32_t*   gauss_vals[2];  // [R] Gaussian index; CUB double buffer
     PackedInst* packed;         // [R] tile-ordered packed records (tile t uses [ranges[t].x, +tile_count[t]))
     char*       temp;
@@ -218,7 +218,7 @@ void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes);
 cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s);
 cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
                              const uint32_t** sorted_tiles, cudaStream_t s);
-cudaError_t launch_tile_ranges(size_t R, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
+cudaError_t launch_tile_ranges(size_t R, int n_tiles, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
                                const uint32_t header_words[4], cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,

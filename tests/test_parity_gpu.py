@@ -280,8 +280,10 @@ def test_full_size_backward_properties(sgs, dev):
         # property check, NOT the parity bar: three independent float-atomic sums + a float32 linear
         # combination; the scale/rotation gradients are differences of large cov3D terms (cancellation),
         # so a single worst entry can sit near 1e-3 of the max while the vector as a whole agrees to ~1e-5
-        assert normrel(gab[k].cpu().numpy(), want.cpu().numpy()) < 2e-4, k
-        assert maxrel(gab[k].cpu().numpy(), want.cpu().numpy()) < 3e-3, k
+        # (run-to-run spread of these two tensors at this size, tools/grad_noise.py: ~2e-4 norm-relative, ~1e-3 max)
+        noisy = k in ("scales", "rotations")
+        assert normrel(gab[k].cpu().numpy(), want.cpu().numpy()) < (2e-3 if noisy else 1e-4), k
+        assert maxrel(gab[k].cpu().numpy(), want.cpu().numpy()) < (1e-2 if noisy else 5e-4), k
         assert not gab[k][culled].any(), k                       # culled Gaussians get exact zeros
     assert not m2d.grad[:, 2].any()                              # dL/dmean2D.z is always 0
 
