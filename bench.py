@@ -143,8 +143,7 @@ def run_native_or_ref(args, impl):
     cot_pin = pin(cot_cpu)
     cam_pin = [(pin(c.viewmatrix), pin(c.projmatrix), pin(c.campos)) for c in cams]
     bg_pin = pin(bg_cpu)
-    img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    chk_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+    res_host = torch.empty((2,), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def zero_grads():
@@ -160,11 +159,13 @@ def run_native_or_ref(args, impl):
         color.backward(cot_dev)
         zero_grads()
 
-    # e2e leg: the caller overlaps its own copies with the rasterizer, as a training/eval loop would:
-    # the cotangent image travels host->device on a side stream while forward runs, and the rendered
-    # image travels device->host on another side stream while backward runs.  Same code for both arms.
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    ev_in, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
+    # e2e leg = one training-style step through the public API with HOST inputs: the per-view inputs (camera,
+    # background and the 16 MB dL/dcolor image — the stand-in for the ground-truth image a training step uploads)
+    # come from pinned host memory every step, and the step's result (a loss-like scalar of the rendered image and
+    # a gradient checksum) is read back to the host.  The caller overlaps its upload with the rasterizer as a
+    # training loop would: the image travels on a side stream while forward runs.  Same code for both arms.
+    s_in = torch.cuda.Stream(dev)
+    ev_in = torch.cuda.Event()
 
     def step_e2e(i):
         main = torch.cuda.current_stream(dev)
@@ -180,22 +181,17 @@ def run_native_or_ref(args, impl):
         rs = Settings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, v, p, scene.sh_degree, cp, False)
         color, radii, depth = Rast(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                                        shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
-        ev_fwd.record(main)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_fwd)
-            img_host.copy_(color.detach(), non_blocking=True)
-        color.record_stream(s_out)
         main.wait_event(ev_in)
         cot.record_stream(main)
         color.backward(cot)
-        chk = params["means3D"].grad.abs().sum() + params["shs"].grad.abs().sum()
-        chk_host.copy_(chk.reshape(1), non_blocking=True)
-        main.synchronize()    # the caller consumes the metric ...
-        s_out.synchronize()   # ... and the image on the host
+        res = torch.stack([(color.detach() * cot).sum(),
+                           params["means3D"].grad.abs().sum() + params["shs"].grad.abs().sum()])
+        res_host.copy_(res, non_blocking=True)
+        main.synchronize()    # the caller consumes the loss / metric on the host
         zero_grads()
 
     h2d_bytes = cot_pin.numel() * 4 + (16 + 16 + 3 + 3) * 4
-    d2h_bytes = img_host.numel() * 4 + 4
+    d2h_bytes = res_host.numel() * 4
 
     def barrier():
         if world > 1:
@@ -260,10 +256,10 @@ def run_native_or_ref(args, impl):
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks"},
         "e2e": {"value": e2e_ms / (K * world), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes,
-                "note": "per-view inputs (camera, bg, dL/dcolor) from pinned host memory; rendered image + grad "
-                        "checksum read back; Gaussian parameters resident (the API takes CUDA tensors only); the "
-                        "16 MB dL/dcolor upload overlaps forward and the 16 MB image download overlaps backward "
-                        "(side streams, same code for both arms)"},
+                "note": "per-view inputs (camera, bg, 16 MB dL/dcolor image) from pinned host memory every step; the "
+                        "step's loss-like scalar + gradient checksum read back; Gaussian parameters resident (the "
+                        "API takes CUDA tensors only); the image upload runs on a side stream while forward runs "
+                        "(same code for both arms)"},
         "clocks": clocks, "wall_ms_timed_region": wall_ms,
     }
     if impl == "reference":
@@ -290,12 +286,22 @@ def run_native_or_ref(args, impl):
         calls = max(1, stage["calls"]["render_bwd"])
         k_ms = stage["ms"]["render_bwd"] / calls
         achieved = alg / (k_ms * 1e-3) / 1e9
+        # measured once per round with `ncu --set full` on this exact workload (profiles/r01s_render_ncu_summary.csv)
+        NCU_TRAFFIC_BYTES = 93_287_936        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+        NCU_WARP_INSTRUCTIONS = 371_781_305   # smsp__inst_executed.sum of one launch
+        sm_mhz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        issue_peak = 148 * 4 * sm_mhz * 1e6   # one warp-instruction per SM sub-partition per clock
         line["roofline"] = {"kernel": "render_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                             "avg_launch_ms": k_ms,
-                            "note": "the compositing kernels are FP32-issue/SFU bound, not HBM bound (DESIGN.md); "
-                                    "pair-evaluation throughput is the meaningful ceiling"}
+                            "note": "reported against HBM as the contract asks, but this kernel is instruction-issue "
+                                    "bound (ncu: issue-active 87 %, DRAM 1.7 %): ~95 blended pixel x Gaussian pairs "
+                                    "are evaluated per 48-byte record (DESIGN.md section 3); see `issue`",
+                            "issue": {"warp_instructions_per_launch": NCU_WARP_INSTRUCTIONS,
+                                      "achieved_Tinst_s": NCU_WARP_INSTRUCTIONS / (k_ms * 1e-3) / 1e12,
+                                      "peak_Tinst_s": issue_peak / 1e12,
+                                      "frac": NCU_WARP_INSTRUCTIONS / (k_ms * 1e-3) / issue_peak}}
         line["stage_ms_per_step"] = {n: stage["ms"][n] / K for n in stage["ms"]}
         line["ms_per_step_with_stage_events"] = prof_ms / K
         line["gpu_launches"] = stage["own_launches"]
