@@ -38,35 +38,50 @@ __forceinline__ __device__ float xsplit(float lo, float hi, bool upper, int xorm
     return keep + __shfl_xor_sync(0xFFFFFFFFu, send, xorm);
 }
 
-struct BwdPix {
-    float T;           // transmittance in front of the instance being visited
-    float a_rec;       // sum_c accum_rec[c] * dL/dpix[c]
-    float last_alpha;  // alpha of the previously visited (= next deeper) blended instance
-    float last_cd;     // its colour . dL/dpix
-    float last_om;     // 1 - last_alpha
-    float d0, d1, d2;  // dL/dpix
-    float bgT;         // -T_final * (bg . dL/dpix)
-    uint32_t lc;       // n_contrib of the pixel
+// State of the two pixels of a thread, kept as f32x2 pairs so that the per-pair maths after exp() runs on the
+// packed FMUL2 / FFMA2 / FADD2 instructions (one issue slot for both pixels).
+struct BwdPix2 {
+    float2 T;           // transmittance in front of the instance being visited
+    float2 a_rec;       // sum_c accum_rec[c] * dL/dpix[c]
+    float2 last_alpha;  // alpha of the previously visited (= next deeper) blended instance
+    float2 last_cd;     // its colour . dL/dpix
+    float2 last_om;     // 1 - last_alpha
+    float2 d0, d1, d2;  // dL/dpix
+    float2 bgT;         // -T_final * (bg . dL/dpix)
+    uint32_t lc0, lc1;  // n_contrib of the two pixels
 };
 
-// one pixel x one instance: returns g = G * dL/dalpha and w = alpha * T (0, 0 when the pair did not blend)
-__forceinline__ __device__ void grad_pixel(BwdPix& s, float power, float o, const float4 c, float& g, float& w) {
+__forceinline__ __device__ float2 bcast2(float v) { return make_float2(v, v); }
+__forceinline__ __device__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+// two pixels x one instance: g = G * dL/dalpha and w = alpha * T per pixel (0 when the pair did not blend).
+// A pixel that does not blend runs through the same packed code with alpha = G = 0: then 1 - alpha = 1, its
+// reciprocal is exactly 1, T is unchanged, g = w = 0, and the pending accum_rec fold  a <- la*lcd + lom*a  is
+// merely applied one step early (afterwards la = 0, lom = 1, so the next fold returns a bit for bit).
+__forceinline__ __device__ void grad_pixels2(BwdPix2& s, float2 pw, bool act0, bool act1, float o, const float4 c,
+                                             float2& g, float2& w) {
     // accurate expf() and a < 1 ulp reciprocal, like forward / the reference: alpha must equal forward's bit for
     // bit and T is recovered by a long product of 1/(1-alpha) factors — a bare ex2.approx / rcp.approx (~1e-7
     // each, but biased) drifts T by ~n * 1e-7 over n blended instances (measured: 2.5x the error on dL/dmeans3D).
-    const float G = expf(power);
-    const float alpha = min(0.99f, o * G);
-    if (alpha < 1.0f / 255.0f) return;
-    const float om = 1.f - alpha;       // in [0.01, 1]: no denormal / overflow cases, so MUFU.RCP + one Newton
-    float inv;                          // step is accurate to < 1 ulp without __frcp_rn's special-case path
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
-    inv = fmaf(inv, fmaf(-om, inv, 1.0f), inv);
-    s.T *= inv;                          // $R/.../backward.cu:503
-    s.a_rec = fmaf(s.last_alpha, s.last_cd, s.last_om * s.a_rec);   // :515-519, dotted with dL/dpix
-    const float cd = fmaf(c.z, s.d2, fmaf(c.y, s.d1, c.x * s.d0));
-    const float dL_dalpha = fmaf(cd - s.a_rec, s.T, s.bgT * inv);   // :519-534
-    g = G * dL_dalpha;
-    w = alpha * s.T;
+    float2 G = {0.f, 0.f};
+    if (act0) G.x = expf(pw.x);
+    if (act1) G.y = expf(pw.y);
+    float2 alpha = __fmul2_rn(bcast2(o), G);
+    alpha.x = min(0.99f, alpha.x);
+    alpha.y = min(0.99f, alpha.y);
+    if (alpha.x < 1.0f / 255.0f) { alpha.x = 0.f; G.x = 0.f; }
+    if (alpha.y < 1.0f / 255.0f) { alpha.y = 0.f; G.y = 0.f; }
+    const float2 om = __fadd2_rn(bcast2(1.f), neg2(alpha));   // in [0.01, 1]
+    float2 inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(om.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(om.y));
+    inv = __ffma2_rn(inv, __ffma2_rn(neg2(om), inv, bcast2(1.f)), inv);   // one Newton step: < 1 ulp
+    s.T = __fmul2_rn(s.T, inv);                                            // $R/.../backward.cu:503
+    s.a_rec = __ffma2_rn(s.last_alpha, s.last_cd, __fmul2_rn(s.last_om, s.a_rec));   // :515-519, dotted with dL/dpix
+    const float2 cd = __ffma2_rn(bcast2(c.z), s.d2, __ffma2_rn(bcast2(c.y), s.d1, __fmul2_rn(bcast2(c.x), s.d0)));
+    const float2 dL_dalpha = __ffma2_rn(__fadd2_rn(cd, neg2(s.a_rec)), s.T, __fmul2_rn(s.bgT, inv));   // :519-534
+    g = __fmul2_rn(G, dL_dalpha);
+    w = __fmul2_rn(alpha, s.T);
     s.last_alpha = alpha;
     s.last_cd = cd;
     s.last_om = om;
@@ -155,31 +170,25 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
         for (int j = 0; j < min(nb, SGS_B_STAGES); j++) issue(j);
     }
 
-    BwdPix p0, p1;
+    BwdPix2 st;
     {
         const size_t HW = (size_t)H * W;
         const uint32_t id0 = (uint32_t)W * py0 + px, id1 = (uint32_t)W * py1 + px;
         const float Tf0 = in0 ? final_T[id0] : 0.f, Tf1 = in1 ? final_T[id1] : 0.f;
-        p0.T = Tf0;
-        p1.T = Tf1;
-        p0.lc = in0 ? n_contrib[id0] : 0u;
-        p1.lc = in1 ? n_contrib[id1] : 0u;
-        p0.d0 = in0 ? dL_dpix[id0] : 0.f;
-        p0.d1 = in0 ? dL_dpix[HW + id0] : 0.f;
-        p0.d2 = in0 ? dL_dpix[2 * HW + id0] : 0.f;
-        p1.d0 = in1 ? dL_dpix[id1] : 0.f;
-        p1.d1 = in1 ? dL_dpix[HW + id1] : 0.f;
-        p1.d2 = in1 ? dL_dpix[2 * HW + id1] : 0.f;
+        st.T = make_float2(Tf0, Tf1);
+        st.lc0 = in0 ? n_contrib[id0] : 0u;
+        st.lc1 = in1 ? n_contrib[id1] : 0u;
+        st.d0 = make_float2(in0 ? dL_dpix[id0] : 0.f, in1 ? dL_dpix[id1] : 0.f);
+        st.d1 = make_float2(in0 ? dL_dpix[HW + id0] : 0.f, in1 ? dL_dpix[HW + id1] : 0.f);
+        st.d2 = make_float2(in0 ? dL_dpix[2 * HW + id0] : 0.f, in1 ? dL_dpix[2 * HW + id1] : 0.f);
         const float b0 = vp.bg[0], b1 = vp.bg[1], b2 = vp.bg[2];
-        p0.bgT = -Tf0 * (b0 * p0.d0 + b1 * p0.d1 + b2 * p0.d2);   // :531-534
-        p1.bgT = -Tf1 * (b0 * p1.d0 + b1 * p1.d1 + b2 * p1.d2);
-        p0.a_rec = p1.a_rec = 0.f;
-        p0.last_alpha = p1.last_alpha = 0.f;
-        p0.last_cd = p1.last_cd = 0.f;
-        p0.last_om = p1.last_om = 1.f;
+        st.bgT = make_float2(-Tf0 * (b0 * st.d0.x + b1 * st.d1.x + b2 * st.d2.x),     // :531-534
+                             -Tf1 * (b0 * st.d0.y + b1 * st.d1.y + b2 * st.d2.y));
+        st.a_rec = st.last_alpha = st.last_cd = make_float2(0.f, 0.f);
+        st.last_om = make_float2(1.f, 1.f);
     }
     // warp-uniform bound: records at list positions >= this were blended by no pixel of the warp
-    const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(p0.lc, p1.lc));
+    const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(st.lc0, st.lc1));
 
     // which accumulator slot this lane owns after the butterfly (see the reduction below)
     //   bit1 set -> value 4 ; else value = (bit4 ? 5 : 0) + (bit2 ? 2 : 0) + (bit3 ? 1 : 0)
@@ -228,26 +237,25 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 // same tests as forward: power > 0 -> skip; power < thr -> provably alpha < 1/255
                 // (a separate cheaper warp-level pre-test was measured slower: with the visit bitmaps
                 // nearly every visit blends something, so the exact tests are needed anyway)
-                const bool act0 = (pos < p0.lc) && !(pw.x > 0.0f) && !(pw.x < rb.z);
-                const bool act1 = (pos < p1.lc) && !(pw.y > 0.0f) && !(pw.y < rb.z);
+                const bool act0 = (pos < st.lc0) && !(pw.x > 0.0f) && !(pw.x < rb.z);
+                const bool act1 = (pos < st.lc1) && !(pw.y > 0.0f) && !(pw.y < rb.z);
                 if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;
 
                 const float4 c = lds128(rec + 32u);   // r, g, b, gid | quadrant mask << 28
-                float g_0 = 0.f, w_0 = 0.f, g_1 = 0.f, w_1 = 0.f;
-                if (act0) grad_pixel(p0, pw.x, rb.y, c, g_0, w_0);
-                if (act1) grad_pixel(p1, pw.y, rb.y, c, g_1, w_1);
+                float2 g, w;
+                grad_pixels2(st, pw, act0, act1, rb.y, c, g, w);
 
                 // moments of g over this thread's two pixels (dx shared)
-                const float gy0 = g_0 * dy.x, gy1 = g_1 * dy.y;
-                float v5 = g_0 + g_1;                       // sum g            -> dL/dopacity
+                const float2 gy = __fmul2_rn(g, dy);
+                float v5 = g.x + g.y;                       // sum g            -> dL/dopacity
                 float v0 = v5 * dx;                         // sum g dx
-                float v1 = gy0 + gy1;                       // sum g dy
+                float v1 = gy.x + gy.y;                     // sum g dy
                 float v2 = v0 * dx;                         // sum g dx^2
                 float v3 = v1 * dx;                         // sum g dx dy
-                float v4 = fmaf(gy1, dy.y, gy0 * dy.x);     // sum g dy^2
-                float v6 = fmaf(w_1, p1.d0, w_0 * p0.d0);   // sum alpha T dL/dpix[c]  -> dL/dcolour
-                float v7 = fmaf(w_1, p1.d1, w_0 * p0.d1);
-                float v8 = fmaf(w_1, p1.d2, w_0 * p0.d2);
+                float v4 = fmaf(gy.y, dy.y, gy.x * dy.x);   // sum g dy^2
+                float v6 = fmaf(w.y, st.d0.y, w.x * st.d0.x);   // sum alpha T dL/dpix[c]  -> dL/dcolour
+                float v7 = fmaf(w.y, st.d1.y, w.x * st.d1.x);
+                float v8 = fmaf(w.y, st.d2.y, w.x * st.d2.x);
 
                 // transposing butterfly: 9 values x 32 lanes -> one value per writer lane
                 // step 1 (xor 16): pairs (v0,v5) (v1,v6) (v2,v7) (v3,v8); v4 reduced plainly
