@@ -306,6 +306,8 @@ def run_native_or_ref(args, impl):
         line["ms_per_step_with_stage_events"] = prof_ms / K
         line["gpu_launches"] = stage["own_launches"]
         line["gpu_launches_note"] = "hand-written kernels only (6/step); CUB sort/scan kernels launched by the library are extra"
+        if rank == 0:
+            line["loss_path"] = loss_path_timing(dev, H, W)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
     if rank == 0:
@@ -314,6 +316,39 @@ def run_native_or_ref(args, impl):
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+def loss_path_timing(dev, H, W, iters=20):
+    """SURVEY.md section 8(f) rank 3 (first row widened beyond the rasterizer): the L1 + D-SSIM loss that runs between
+    the rasterizer's forward and backward — fused CUDA kernels vs the same loss as PyTorch ops (what SaRO-GS runs),
+    forward + backward to dL/dimage, CUDA events, inputs resident."""
+    from saro_gs_b200 import loss_utils
+    from oracle.ssim_torch import torch_l1_dssim_loss
+    g = torch.Generator().manual_seed(11)
+    gt = torch.rand(3, H, W, generator=g).to(dev)
+    img = (gt + 0.05 * torch.randn(3, H, W, generator=g).to(dev)).clamp(0, 1)
+
+    def run(fn):
+        ms = []
+        for i in range(iters + 3):
+            x = img.clone().requires_grad_(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = fn(x, gt, 0.2)
+            loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        return sum(ms) / len(ms), float(loss.item())
+
+    fused_ms, fused_val = run(loss_utils.l1_dssim_loss)
+    torch_ms, torch_val = run(torch_l1_dssim_loss)
+    px = 3 * H * W
+    return {"what": "L1 + 0.2 D-SSIM loss forward + backward on one 3x%dx%d image" % (H, W),
+            "fused_ms": fused_ms, "pytorch_ops_ms": torch_ms, "speedup": torch_ms / fused_ms,
+            "fused_GBps": (8 + 12 + 20 + 4) * px / (fused_ms * 1e-3) / 1e9,
+            "loss_fused": fused_val, "loss_pytorch": torch_val}
 
 
 def cpu_baseline(precision="f32"):

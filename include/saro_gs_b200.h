@@ -128,6 +128,31 @@ void sgs_profile_enable(int on);
 int sgs_profile_read(float* stage_ms /*[SGS_PROFILE_STAGES]*/, int* stage_calls /*[SGS_PROFILE_STAGES]*/,
                      uint64_t* own_kernel_launches);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Photometric loss on the rasterizer's output — replaces, for CUDA float32 images,
+ * the PyTorch code of the reference's utils/loss_utils.py:18-19 (l1_loss) and :38-68 (ssim: 11x11 Gaussian window,
+ * sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2) as used by helper_train.py:50-53 / train.py:208-209.
+ * Images are [B][C][H][W] float32, contiguous, on the device.
+ *
+ * sgs_l1_dssim_forward:  sums[b] = ( sum |img - gt| , sum ssim_map ) over the C planes of image b (device, [B][2]).
+ *                        `dmaps` ([3][B*C][H][W] floats) receives what the backward pass needs, or NULL for
+ *                        evaluation only.  `workspace`: sgs_loss_workspace_floats() floats of scratch.
+ * sgs_l1_dssim_backward: dL_dimg = coef[b][0] * d(sum|.|)/dimg + coef[b][1] * d(sum ssim)/dimg, with coef ([B][2],
+ *                        device) the gradient of the caller's scalar loss with respect to `sums`.
+ * Both return 0 or a negative error code. */
+size_t sgs_loss_workspace_floats(int B, int C, int H, int W);
+int sgs_l1_dssim_forward(int B, int C, int H, int W, const float* img, const float* gt, float* dmaps, float* workspace,
+                         float* sums, void* stream);
+int sgs_l1_dssim_backward(int B, int C, int H, int W, const float* img, const float* gt, const float* dmaps,
+                          const float* coef, float* dL_dimg, void* stream);
+/* The training-step form in one call each way (helper_train.py:50-53 of the reference):
+ *   loss[0] = (1 - lambda) * mean|img - gt| + lambda * (1 - mean ssim_map)      (device scalar)
+ *   dL_dimg = grad_loss[0] * d loss / d img                                      (grad_loss: device scalar) */
+int sgs_l1_dssim_loss_forward(int B, int C, int H, int W, const float* img, const float* gt, float lambda_dssim,
+                              float* dmaps, float* workspace, float* loss, void* stream);
+int sgs_l1_dssim_loss_backward(int B, int C, int H, int W, const float* img, const float* gt, float lambda_dssim,
+                               const float* dmaps, const float* grad_loss, float* dL_dimg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

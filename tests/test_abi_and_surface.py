@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "saro_gs_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sgs_[a-z_]+)\s*\(", text)) - {"sgs_resize_fn"})
+    return sorted(set(re.findall(r"\b(sgs_[a-z0-9_]+)\s*\(", text)) - {"sgs_resize_fn"})
 
 
 def test_header_symbols_exported(native_lib):
