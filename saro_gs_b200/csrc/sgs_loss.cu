@@ -38,12 +38,23 @@ __device__ __forceinline__ float tile_load(const float* __restrict__ p, int H, i
     return (y >= 0 && y < H && x >= 0 && x < W) ? p[(size_t)y * W + x] : 0.f;   // zero padding (conv2d padding=5)
 }
 
+// sliding-window helper: out[j] = sum_k g[k] * v[j + k] for j = 0..3 from 14 consecutive samples
+__device__ __forceinline__ void window4(const float (&v)[14], float (&out)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) a = fmaf(c_g[k], v[j + k], a);
+        out[j] = a;
+    }
+}
+
 __global__ void __launch_bounds__(SL_THREADS)
 l1_dssim_fwd_kernel(int H, int W, const float* __restrict__ img, const float* __restrict__ gt,
                     float* __restrict__ dm /*[3][N][H][W] or null*/, size_t plane_stride_all,
                     float* __restrict__ partials /*[N][tiles][2]*/) {
     __shared__ float sx[SL_E][SL_E + 1], sy[SL_E][SL_E + 1];
-    __shared__ float sh[5][SL_E][SL_T];
+    __shared__ float sh[5][SL_E][SL_T + 1];
     __shared__ float s_red[2][SL_THREADS / 32];
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
@@ -57,57 +68,74 @@ l1_dssim_fwd_kernel(int H, int W, const float* __restrict__ img, const float* __
         sy[r][c] = tile_load(py, H, W, y0 + r - SL_R, x0 + c - SL_R);
     }
     __syncthreads();
-    // horizontal pass: 42 rows x 32 columns
-    for (int i = tid; i < SL_E * SL_T; i += SL_THREADS) {
-        const int r = i / SL_T, c = i - r * SL_T;
-        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+    // horizontal pass: 42 rows x 8 groups of 4 columns; every thread slides the 11-tap window over 14 samples held
+    // in registers (products formed once per sample instead of once per tap)
+    for (int i = tid; i < SL_E * (SL_T / 4); i += SL_THREADS) {
+        const int r = i / (SL_T / 4), c0 = (i - r * (SL_T / 4)) * 4;
+        float u[14], v[14], t[14], o[4];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float w = c_g[k], u = sx[r][c + k], v = sy[r][c + k];
-            a = fmaf(w, u, a);
-            b = fmaf(w, v, b);
-            aa = fmaf(w, u * u, aa);
-            bb = fmaf(w, v * v, bb);
-            ab = fmaf(w, u * v, ab);
-        }
-        sh[0][r][c] = a; sh[1][r][c] = b; sh[2][r][c] = aa; sh[3][r][c] = bb; sh[4][r][c] = ab;
+        for (int k = 0; k < 14; k++) { u[k] = sx[r][c0 + k]; v[k] = sy[r][c0 + k]; }
+        window4(u, o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sh[0][r][c0 + j] = o[j];
+        window4(v, o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sh[1][r][c0 + j] = o[j];
+#pragma unroll
+        for (int k = 0; k < 14; k++) t[k] = u[k] * u[k];
+        window4(t, o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sh[2][r][c0 + j] = o[j];
+#pragma unroll
+        for (int k = 0; k < 14; k++) t[k] = v[k] * v[k];
+        window4(t, o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sh[3][r][c0 + j] = o[j];
+#pragma unroll
+        for (int k = 0; k < 14; k++) t[k] = u[k] * v[k];
+        window4(t, o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sh[4][r][c0 + j] = o[j];
     }
     __syncthreads();
-    // vertical pass + SSIM + derivative maps
+    // vertical pass: 32 columns x 8 groups of 4 rows = one item per thread; then SSIM + derivative maps
     float sum_abs = 0.f, sum_ssim = 0.f;
     const size_t HW = (size_t)H * W;
-    for (int i = tid; i < SL_T * SL_T; i += SL_THREADS) {
-        const int r = i / SL_T, c = i - r * SL_T;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy >= H || gx >= W) continue;
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    {
+        const int c = tid & (SL_T - 1), r0 = (tid / SL_T) * 4;
+        float m[5][4];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float w = c_g[k];
-            mu1 = fmaf(w, sh[0][r + k][c], mu1);
-            mu2 = fmaf(w, sh[1][r + k][c], mu2);
-            e11 = fmaf(w, sh[2][r + k][c], e11);
-            e22 = fmaf(w, sh[3][r + k][c], e22);
-            e12 = fmaf(w, sh[4][r + k][c], e12);
+        for (int p = 0; p < 5; p++) {
+            float v[14];
+#pragma unroll
+            for (int k = 0; k < 14; k++) v[k] = sh[p][r0 + k][c];
+            window4(v, m[p]);
         }
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-        const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
-        const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
-        const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
-        const float inv = 1.f / (B1 * B2);
-        const float S = A1 * A2 * inv;
-        sum_ssim += S;
-        sum_abs += fabsf(sx[r + SL_R][c + SL_R] - sy[r + SL_R][c + SL_R]);
-        if (dm != nullptr) {
-            // total derivative of S through mu1 (also inside sigma1^2 = Exx - mu1^2 and sigma12 = Exy - mu1 mu2)
-            const float dS_dmu1 = 2.f * inv * (mu2 * (A2 - A1) - mu1 * S * (B2 - B1));
-            const float dS_de11 = -S / B2;
-            const float dS_de12 = 2.f * A1 * inv;
-            const size_t o = (size_t)n * HW + (size_t)gy * W + gx;
-            dm[o] = dS_dmu1;
-            dm[plane_stride_all + o] = dS_de11;
-            dm[2 * plane_stride_all + o] = dS_de12;
+        const int gx = x0 + c;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gy = y0 + r0 + j;
+            if (gy >= H || gx >= W) continue;
+            const float mu1 = m[0][j], mu2 = m[1][j], e11 = m[2][j], e22 = m[3][j], e12 = m[4][j];
+            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+            const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
+            const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+            const float inv = 1.f / (B1 * B2);
+            const float S = A1 * A2 * inv;
+            sum_ssim += S;
+            sum_abs += fabsf(sx[r0 + j + SL_R][c + SL_R] - sy[r0 + j + SL_R][c + SL_R]);
+            if (dm != nullptr) {
+                // total derivative of S through mu1 (also inside sigma1^2 = Exx - mu1^2 and sigma12 = Exy - mu1 mu2)
+                const float dS_dmu1 = 2.f * inv * (mu2 * (A2 - A1) - mu1 * S * (B2 - B1));
+                const float dS_de11 = -S / B2;
+                const float dS_de12 = 2.f * A1 * inv;
+                const size_t o = (size_t)n * HW + (size_t)gy * W + gx;
+                dm[o] = dS_dmu1;
+                dm[plane_stride_all + o] = dS_de11;
+                dm[2 * plane_stride_all + o] = dS_de12;
+            }
         }
     }
     // deterministic block reduction
@@ -119,11 +147,11 @@ l1_dssim_fwd_kernel(int H, int W, const float* __restrict__ img, const float* __
     if ((tid & 31) == 0) { s_red[0][tid >> 5] = sum_abs; s_red[1][tid >> 5] = sum_ssim; }
     __syncthreads();
     if (tid == 0) {
-        float a = 0.f, b = 0.f;
-        for (int w = 0; w < SL_THREADS / 32; w++) { a += s_red[0][w]; b += s_red[1][w]; }
+        float a = 0.f, b2 = 0.f;
+        for (int w = 0; w < SL_THREADS / 32; w++) { a += s_red[0][w]; b2 += s_red[1][w]; }
         const size_t blk = ((size_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         partials[2 * blk] = a;
-        partials[2 * blk + 1] = b;
+        partials[2 * blk + 1] = b2;
     }
 }
 
@@ -169,7 +197,7 @@ l1_dssim_bwd_kernel(int C, int H, int W, const float* __restrict__ img, const fl
                     const float* __restrict__ dm, size_t plane_stride_all, const float* __restrict__ coef,
                     int coef_stride, float scale_l1, float scale_ssim, float* __restrict__ dL_dimg) {
     __shared__ float sd[3][SL_E][SL_E + 1];
-    __shared__ float sh[3][SL_E][SL_T];
+    __shared__ float sh[3][SL_E][SL_T + 1];
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * SL_T, y0 = blockIdx.y * SL_T;
@@ -183,36 +211,40 @@ l1_dssim_bwd_kernel(int C, int H, int W, const float* __restrict__ img, const fl
             sd[m][r][c] = tile_load(dm + m * plane_stride_all + (size_t)n * HW, H, W, y0 + r - SL_R, x0 + c - SL_R);
     }
     __syncthreads();
-    for (int i = tid; i < SL_E * SL_T; i += SL_THREADS) {
-        const int r = i / SL_T, c = i - r * SL_T;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = tid; i < SL_E * (SL_T / 4); i += SL_THREADS) {
+        const int r = i / (SL_T / 4), c0 = (i - r * (SL_T / 4)) * 4;
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float w = c_g[k];
-            a0 = fmaf(w, sd[0][r][c + k], a0);
-            a1 = fmaf(w, sd[1][r][c + k], a1);
-            a2 = fmaf(w, sd[2][r][c + k], a2);
+        for (int m = 0; m < 3; m++) {
+            float v[14], o[4];
+#pragma unroll
+            for (int k = 0; k < 14; k++) v[k] = sd[m][r][c0 + k];
+            window4(v, o);
+#pragma unroll
+            for (int j = 0; j < 4; j++) sh[m][r][c0 + j] = o[j];
         }
-        sh[0][r][c] = a0; sh[1][r][c] = a1; sh[2][r][c] = a2;
     }
     __syncthreads();
-    for (int i = tid; i < SL_T * SL_T; i += SL_THREADS) {
-        const int r = i / SL_T, c = i - r * SL_T;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy >= H || gx >= W) continue;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    {
+        const int c = tid & (SL_T - 1), r0 = (tid / SL_T) * 4;
+        float w[3][4];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float w = c_g[k];
-            v0 = fmaf(w, sh[0][r + k][c], v0);
-            v1 = fmaf(w, sh[1][r + k][c], v1);
-            v2 = fmaf(w, sh[2][r + k][c], v2);
+        for (int m = 0; m < 3; m++) {
+            float v[14];
+#pragma unroll
+            for (int k = 0; k < 14; k++) v[k] = sh[m][r0 + k][c];
+            window4(v, w[m]);
         }
-        const size_t o = (size_t)n * HW + (size_t)gy * W + gx;
-        const float x = img[o], y = gt[o];
-        const float d = x - y;
-        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);   // torch.abs: zero gradient at 0
-        dL_dimg[o] = cL1 * sgn + cS * (v0 + 2.f * x * v1 + y * v2);
+        const int gx = x0 + c;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int gy = y0 + r0 + j;
+            if (gy >= H || gx >= W) continue;
+            const size_t o = (size_t)n * HW + (size_t)gy * W + gx;
+            const float x = img[o], y = gt[o];
+            const float d = x - y;
+            const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);   // torch.abs: zero gradient at 0
+            dL_dimg[o] = cL1 * sgn + cS * (w[0][j] + 2.f * x * w[1][j] + y * w[2][j]);
+        }
     }
 }
 
