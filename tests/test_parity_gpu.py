@@ -346,3 +346,100 @@ def test_unmodified_reference_style_caller(sgs, dev):
                             colors_precomp=lifespan.expand(-1, 3), opacities=scene.opacities.to(dev),
                             scales=scene.scales.to(dev), rotations=scene.rotations.to(dev), cov3D_precomp=None)
     assert img2.shape == rendered_image.shape and torch.isfinite(img2).all()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_culling_fuzz_extreme_shapes(sgs, dev, seed):
+    """The three conservative culls (alpha-box rect clip, quadrant masks, power threshold) against the unculled
+    path on deliberately nasty inputs: needle-like and pancake Gaussians, opacities straddling 1/255, huge splats,
+    centres far off screen.  Image, depth, radii and final_T must be bit-identical."""
+    gen = torch.Generator().manual_seed(1000 + seed)
+    P, W, H, fx = 600, 112, 96, 100.0
+    z = torch.rand(P, generator=gen) * 8.0 + 0.25
+    spread = 3.0 if seed % 2 else 1.2                      # odd seeds: many centres off screen
+    x = (torch.rand(P, generator=gen) * 2 - 1) * spread * (W / (2 * fx)) * z
+    y = (torch.rand(P, generator=gen) * 2 - 1) * spread * (H / (2 * fx)) * z
+    means = torch.stack([x, y, z], 1)
+    scales = torch.exp(torch.randn(P, 3, generator=gen) * 2.0 - 2.5)       # 3 decades of anisotropy
+    q = torch.randn(P, 4, generator=gen)
+    rots = q / q.norm(dim=1, keepdim=True)
+    op = torch.sigmoid(torch.randn(P, 1, generator=gen) * 3.0)
+    op[: P // 6] = (1.0 / 255.0) * (1.0 + (torch.rand(P // 6, 1, generator=gen) - 0.5) * 0.02)   # at the threshold
+    op[P // 6: P // 5] = 1.0
+    cols = torch.rand(P, 3, generator=gen)
+    from saro_gs_b200 import synthetic
+    cam = synthetic.make_camera(W, H, fx)
+    args = lambda: (torch.tensor([0.1, 0.2, 0.3], device=dev), means.to(dev), cols.to(dev), op.to(dev), scales.to(dev),
+                    rots.to(dev), 1.0, torch.Tensor([]), cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.tanfovx,
+                    cam.tanfovy, H, W, torch.Tensor([]), 0, cam.campos.to(dev), False)
+    R0, c0, r0, g0, b0, i0, d0 = sgs._C.rasterize_gaussians(*args())
+    R1, c1, r1, g1, b1, i1, d1 = sgs._C.rasterize_gaussians(*args(), _no_tile_cull=True)
+    s0 = sgs._C.debug_export(P, W, H, R0, g0, b0, i0)
+    s1 = sgs._C.debug_export(P, W, H, R1, g1, b1, i1)
+    assert R0 == R1 and torch.equal(r0, r1)
+    assert torch.equal(c0, c1) and torch.equal(d0, d1)
+    assert torch.equal(s0["final_T"], s1["final_T"]) and torch.equal(s0["tiles_touched"], s1["tiles_touched"])
+    assert s0["kept"] <= s1["kept"] == R1
+
+
+def test_more_than_65536_tiles_uses_32_bit_keys(sgs, dev, oracle_mod):
+    """4112 x 4112 = 257 x 257 = 66049 tiles: the binning falls back from 16-bit to 32-bit tile keys."""
+    from saro_gs_b200 import synthetic
+    W = H = 4112
+    gen = torch.Generator().manual_seed(77)
+    P = 48
+    cam = synthetic.make_camera(W, H, 3000.0)
+    z = torch.rand(P, generator=gen) * 3 + 2
+    x = (torch.rand(P, generator=gen) * 2 - 1) * (W / 6000.0) * z
+    y = (torch.rand(P, generator=gen) * 2 - 1) * (H / 6000.0) * z
+    means = torch.stack([x, y, z], 1)
+    scales = torch.exp(torch.randn(P, 3, generator=gen) * 0.5 - 3.0)
+    q = torch.randn(P, 4, generator=gen)
+    rots = q / q.norm(dim=1, keepdim=True)
+    op = torch.rand(P, 1, generator=gen) * 0.9 + 0.05
+    cols = torch.rand(P, 3, generator=gen)
+    bg = torch.tensor([0.0, 0.0, 0.0])
+    rs = sgs.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg.to(dev), 1.0, cam.viewmatrix.to(dev),
+                                           cam.projmatrix.to(dev), 0, cam.campos.to(dev), False)
+    color, radii, depth = sgs.GaussianRasterizer(rs)(means3D=means.to(dev), means2D=torch.zeros(P, 3, device=dev),
+                                                    opacities=op.to(dev), colors_precomp=cols.to(dev),
+                                                    scales=scales.to(dev), rotations=rots.to(dev))
+    ref = oracle_mod.forward(means, op, cam.viewmatrix, cam.projmatrix, cam.campos, bg, W, H, cam.tanfovx, cam.tanfovy,
+                             sh_degree=0, colors_precomp=cols, scales=scales, rotations=rots, precision="f32")
+    assert np.array_equal(radii.cpu().numpy(), ref.radii)
+    # the float32 C oracle is not bit-compatible with the GPU (no FMA contraction) and pixel coordinates reach 4111,
+    # so single pixels can flip the alpha >= 1/255 test (measured: 3.5e-3 = one threshold flip, identical for the
+    # compiled reference): a loose value check here, bit-exactness against the live reference below
+    err = np.abs(color.cpu().numpy() - ref.color).max()
+    assert err < 5e-3, err
+    assert np.abs(color.cpu().numpy() - ref.color).mean() < 1e-6
+    assert int((radii > 0).sum()) > 10 and float(color.max()) > 0.05
+    from oracle import ref_loader
+    if ref_loader.available():
+        RefRast = ref_loader.ref_api()[1]
+        c2, r2, d2 = RefRast(rs)(means3D=means.to(dev), means2D=torch.zeros(P, 3, device=dev), opacities=op.to(dev),
+                                 colors_precomp=cols.to(dev), scales=scales.to(dev), rotations=rots.to(dev))
+        assert torch.equal(color, c2) and torch.equal(depth, d2) and torch.equal(radii, r2)
+
+
+def test_non_finite_inputs_do_not_hang_or_crash(sgs, dev):
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.small_scene(P=128, seed=21)
+    means = scene.means3D.clone()
+    scales = scene.scales.clone()
+    op = scene.opacities.clone()
+    means[3] = float("nan")
+    means[7, 0] = float("inf")
+    scales[11] = float("inf")
+    scales[13] = 0.0
+    op[17] = float("nan")
+    op[19] = -1.0
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    m = means.to(dev).requires_grad_(True)
+    color, radii, depth = sgs.GaussianRasterizer(rs)(means3D=m, means2D=torch.zeros_like(m), opacities=op.to(dev),
+                                                    shs=scene.shs.to(dev), scales=scales.to(dev),
+                                                    rotations=scene.rotations.to(dev))
+    color.nan_to_num().sum().backward()
+    torch.cuda.synchronize()
+    assert color.shape == (3, cam.height, cam.width) and m.grad is not None
