@@ -62,10 +62,23 @@ l1_dssim_fwd_kernel(int H, int W, const float* __restrict__ img, const float* __
     const float* px = img + (size_t)n * H * W;
     const float* py = gt + (size_t)n * H * W;
 
-    for (int i = tid; i < SL_E * SL_E; i += SL_THREADS) {
-        const int r = i / SL_E, c = i - r * SL_E;
-        sx[r][c] = tile_load(px, H, W, y0 + r - SL_R, x0 + c - SL_R);
-        sy[r][c] = tile_load(py, H, W, y0 + r - SL_R, x0 + c - SL_R);
+    {   // all global loads of the thread are issued before the first shared-memory store (latency paid once)
+        constexpr int kIt = (SL_E * SL_E + SL_THREADS - 1) / SL_THREADS;
+        float rx[kIt], ry[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; it++) {
+            const int i = tid + it * SL_THREADS;
+            const int r = i / SL_E, c = i - r * SL_E;
+            const bool ok = i < SL_E * SL_E;
+            rx[it] = ok ? tile_load(px, H, W, y0 + r - SL_R, x0 + c - SL_R) : 0.f;
+            ry[it] = ok ? tile_load(py, H, W, y0 + r - SL_R, x0 + c - SL_R) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; it++) {
+            const int i = tid + it * SL_THREADS;
+            const int r = i / SL_E, c = i - r * SL_E;
+            if (i < SL_E * SL_E) { sx[r][c] = rx[it]; sy[r][c] = ry[it]; }
+        }
     }
     __syncthreads();
     // horizontal pass: 42 rows x 8 groups of 4 columns; every thread slides the 11-tap window over 14 samples held
@@ -204,11 +217,28 @@ l1_dssim_bwd_kernel(int C, int H, int W, const float* __restrict__ img, const fl
     const size_t HW = (size_t)H * W;
     const float cL1 = coef[coef_stride * (n / C)] * scale_l1;
     const float cS = coef[coef_stride * (n / C) + (coef_stride ? 1 : 0)] * scale_ssim;
-    for (int i = tid; i < SL_E * SL_E; i += SL_THREADS) {
-        const int r = i / SL_E, c = i - r * SL_E;
+    {   // all global loads of the thread are issued before the first shared-memory store
+        constexpr int kIt = (SL_E * SL_E + SL_THREADS - 1) / SL_THREADS;
+        float rv[3][kIt];
 #pragma unroll
-        for (int m = 0; m < 3; m++)
-            sd[m][r][c] = tile_load(dm + m * plane_stride_all + (size_t)n * HW, H, W, y0 + r - SL_R, x0 + c - SL_R);
+        for (int it = 0; it < kIt; it++) {
+            const int i = tid + it * SL_THREADS;
+            const int r = i / SL_E, c = i - r * SL_E;
+            const bool ok = i < SL_E * SL_E;
+#pragma unroll
+            for (int m = 0; m < 3; m++)
+                rv[m][it] = ok ? tile_load(dm + m * plane_stride_all + (size_t)n * HW, H, W, y0 + r - SL_R, x0 + c - SL_R)
+                               : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; it++) {
+            const int i = tid + it * SL_THREADS;
+            const int r = i / SL_E, c = i - r * SL_E;
+            if (i < SL_E * SL_E) {
+#pragma unroll
+                for (int m = 0; m < 3; m++) sd[m][r][c] = rv[m][it];
+            }
+        }
     }
     __syncthreads();
     for (int i = tid; i < SL_E * (SL_T / 4); i += SL_THREADS) {
