@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Developer tool (GPU box): one small forward + backward (+ fused loss) — run under compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_small.py
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+    compute-sanitizer --tool synccheck python tools/sanitize_small.py
+"""
+import sys
+import torch
+sys.path.insert(0, '.')
+import saro_gs_b200 as sgs
+from saro_gs_b200 import synthetic, loss_utils
+
+dev = torch.device('cuda:0')
+for (P, seed, kw) in [(3000, 0, dict(width=160, height=112, fx=120.0, log_scale_mean=-1.6)), (64, 1, {})]:
+    scene, cam = synthetic.small_scene(P=P, seed=seed, **kw)
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    leaves = {k: getattr(scene, k).to(dev).requires_grad_(True)
+              for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    image, radii, depth = sgs.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=torch.zeros_like(leaves["means3D"]),
+                                                    opacities=leaves["opacities"], shs=leaves["shs"],
+                                                    scales=leaves["scales"], rotations=leaves["rotations"])
+    gt = torch.rand_like(image)
+    loss = loss_utils.l1_dssim_loss(image, gt, 0.2)
+    loss.backward()
+    torch.cuda.synchronize()
+    print("ok", P, float(loss), int((radii > 0).sum()), float(leaves["means3D"].grad.abs().sum()))
