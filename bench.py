@@ -234,6 +234,15 @@ def run_native_or_ref(args, impl):
             dev_ms = float(t.item())
         return dev_ms, wall, stage
 
+    def step_forward_only(i):
+        # test-time rendering (test.py:121,158 of the reference): no autograd, no state kept for backward
+        c = cams[i % len(cams)]
+        v, p, cp = cams_dev[i % len(cams)]
+        rs = Settings(H, W, c.tanfovx, c.tanfovy, bg_dev, 1.0, v, p, scene.sh_degree, cp, False)
+        with torch.no_grad():
+            Rast(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"], shs=params["shs"],
+                     scales=params["scales"], rotations=params["rotations"])
+
     K, W_ = args.steps, max(3, args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
@@ -243,6 +252,7 @@ def run_native_or_ref(args, impl):
         # behind `roofline` (kept out of the headline pass: ~20 extra event records per step cost host time)
         prof_ms, _, stage = timed(step_resident, K, 3, profile=True)
     e2e_ms, _, _ = timed(step_e2e, K, W_)
+    fwd_ms, _, _ = timed(step_forward_only, K, 3)
     clocks = sampler.stop()
 
     ms_per_step = dev_ms / K
@@ -261,6 +271,9 @@ def run_native_or_ref(args, impl):
                         "API takes CUDA tensors only); the image upload runs on a side stream while forward runs "
                         "(same code for both arms)"},
         "clocks": clocks, "wall_ms_timed_region": wall_ms,
+        "forward_only": {"ms_per_frame": fwd_ms / (K * world), "frames_per_s": 1e3 * K * world / fwd_ms,
+                         "note": "inference render of the same views (no_grad), inputs resident; BASELINE.json "
+                                 "configs[2] reports FPS with this protocol"},
     }
     if impl == "reference":
         line["impl"] = "reference"

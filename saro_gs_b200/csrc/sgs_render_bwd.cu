@@ -117,7 +117,7 @@ __forceinline__ __device__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-#define SGS_B_STAGES 4
+#define SGS_B_STAGES 3
 #define SGS_B_STAGE_BYTES (SGS_R_BATCH * 48)
 
 __global__ void __launch_bounds__(SGS_R_THREADS)
