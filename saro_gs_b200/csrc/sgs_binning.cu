@@ -126,23 +126,37 @@ duplicate_kernel(int P, int tiles_x, const uint32_t* __restrict__ order, const u
 }
 
 // Step 4: per-tile [start,end) in the sorted instance list.
+// Each thread scans 16 bytes of sorted keys (8 x u16 or 4 x u32, one vector load) plus the key before them.
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(uint32_t R, const KeyT* __restrict__ sorted_tiles, uint2* __restrict__ ranges,
                    uint32_t* __restrict__ header, uint4 header_words) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *reinterpret_cast<uint4*>(header) = header_words;   // binning-buffer header rides along
-    if (i >= R) return;
-    const uint32_t cur = sorted_tiles[i];
-    if (i == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = sorted_tiles[i - 1];
-        if (cur != prev) {
-            ranges[prev].y = i;
-            ranges[cur].x = i;
+    constexpr uint32_t kPer = 16 / sizeof(KeyT);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *reinterpret_cast<uint4*>(header) = header_words;   // binning-buffer header rides along
+    const uint32_t i0 = t * kPer;
+    if (i0 >= R) return;
+    KeyT k[kPer];
+    if (i0 + kPer <= R) {
+        *reinterpret_cast<uint4*>(k) = *reinterpret_cast<const uint4*>(sorted_tiles + i0);
+    } else {
+#pragma unroll
+        for (uint32_t j = 0; j < kPer; j++) k[j] = (i0 + j < R) ? sorted_tiles[i0 + j] : (KeyT)0;
+    }
+    uint32_t prev = (i0 == 0) ? 0xFFFFFFFFu : (uint32_t)sorted_tiles[i0 - 1];
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; j++) {
+        const uint32_t i = i0 + j;
+        if (i < R) {
+            const uint32_t cur = (uint32_t)k[j];
+            if (cur != prev) {
+                if (i != 0) ranges[prev].y = i;
+                ranges[cur].x = i;
+            }
+            if (i == R - 1) ranges[cur].y = R;
+            prev = cur;
         }
     }
-    if (i == R - 1) ranges[cur].y = R;
 }
 
 static int bits_for_tiles(int n_tiles) {
@@ -190,7 +204,8 @@ cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32
 cudaError_t launch_tile_ranges(size_t R, int n_tiles, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
                                const uint32_t header_words[4], cudaStream_t s) {
     const uint4 hw = make_uint4(header_words[0], header_words[1], header_words[2], header_words[3]);
-    const unsigned grid = (unsigned)((R + 255) / 256);
+    const size_t per = (n_tiles <= 65536) ? 8 : 4;
+    const unsigned grid = (unsigned)(((R + per - 1) / per + 255) / 256);
     if (n_tiles <= 65536)
         tile_ranges_kernel<uint16_t><<<grid, 256, 0, s>>>((uint32_t)R, reinterpret_cast<const uint16_t*>(sorted_tiles),
                                                          img.ranges, header, hw);
