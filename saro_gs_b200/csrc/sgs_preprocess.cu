@@ -177,9 +177,29 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       int* __restrict__ radii, GeomState g, int cull) {
     __shared__ ViewSmem cam;
     __shared__ float4 s_sh[VEC_SH ? (SGS_PRE_THREADS / 32) * 32 * SGS_SH_PAD4 : 1];
-    stage_view(cam, vp);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < P;
+
+    // The kernel is latency-bound (ncu: 44 % of the samples wait on global loads at 38 % occupancy), so every load a
+    // Gaussian may need is issued up front — its own parameters and the warp's 32 SH rows (coalesced, through shared
+    // memory) — before the camera staging barrier and before the first dependent instruction.
+    float3 pre_p = {0.f, 0.f, 0.f}, pre_sc = {0.f, 0.f, 0.f};
+    float4 pre_q = {1.f, 0.f, 0.f, 0.f};
+    float pre_o = 0.f;
+    if (valid) {
+        pre_p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        pre_o = opacities[idx];
+        if (cov3D_precomp == nullptr) {
+            pre_sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+            pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+        }
+    }
+    if (VEC_SH && colors_precomp == nullptr) {
+        const int warp = threadIdx.x >> 5;
+        const int first_row = blockIdx.x * blockDim.x + warp * 32;
+        if (first_row < P) load_sh_rows(s_sh + warp * 32 * SGS_SH_PAD4, shs, first_row, min(32, P - first_row));
+    }
+    stage_view(cam, vp);
 
     // defaults for a Gaussian that takes no further part
     int out_radius = 0;
@@ -191,7 +211,7 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     float depth = 0.f;
 
     if (valid) {
-        p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        p_orig = pre_p;
         const float3 p_view = xform_point_4x3(p_orig, cam.view);
         depth = p_view.z;
 
@@ -211,9 +231,7 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
 #pragma unroll
                 for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
             } else {
-                const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-                const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
-                cov3d_from_scale_rot(sc, vp.scale_modifier, q, cov3D);
+                cov3d_from_scale_rot(pre_sc, vp.scale_modifier, pre_q, cov3D);
 #pragma unroll
                 for (int i = 0; i < 6; i++) g.cov3D[6 * idx + i] = cov3D[i];
             }
@@ -235,7 +253,7 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                 uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
                 if (ntiles != 0) {
                     visible = true;
-                    const float o = opacities[idx];
+                    const float o = pre_o;
                     g.depths[idx] = p_view.z;
                     g.means2D[idx] = point_image;
                     g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, o);
@@ -256,9 +274,7 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         if (VEC_SH) {
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             float4* rows = s_sh + warp * 32 * SGS_SH_PAD4;
-            const int first_row = blockIdx.x * blockDim.x + warp * 32;
-            if (__any_sync(0xFFFFFFFFu, visible)) {
-                load_sh_rows(rows, shs, first_row, min(32, P - first_row));
+            {
                 if (visible) {
                     float f[48];
 #pragma unroll

@@ -58,12 +58,33 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < P;
     const int M = vp.sh_coeffs;
-    const bool visible = valid && radii[idx] > 0;
+    // latency-bound kernel (ncu: 51 % of the samples wait on global loads at 23 % occupancy): every load of this
+    // Gaussian is issued up front, unconditionally, so that all of them are in flight together
+    int pre_radius = 0;
+    float4 pre_a0 = {0.f, 0.f, 0.f, 0.f}, pre_a1 = pre_a0, pre_a2 = pre_a0, pre_co = pre_a0, pre_q = pre_a0;
+    float3 pre_mean = {0.f, 0.f, 0.f}, pre_sc = {0.f, 0.f, 0.f};
+    float pre_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint8_t pre_cm = 0;
+    if (valid) {
+        pre_radius = radii[idx];
+        const float4* arow = reinterpret_cast<const float4*>(acc + (size_t)idx * 12);
+        pre_a0 = arow[0]; pre_a1 = arow[1]; pre_a2 = arow[2];
+        pre_co = conic_opacity[idx];
+        pre_mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+#pragma unroll
+        for (int i = 0; i < 6; i++) pre_cov[i] = cov3Ds[6 * (size_t)idx + i];
+        pre_cm = clamped[idx];
+        if (scales != nullptr) {
+            pre_sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+            pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+        }
+    }
+    const bool visible = valid && pre_radius > 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* rows = s_sh + (VEC_SH ? warp * 32 * SGS_SH_PAD4 : 0);
     const int first_row = blockIdx.x * blockDim.x + warp * 32;
     const int nrows = min(32, P - first_row);
-    if (VEC_SH && shs != nullptr && __any_sync(0xFFFFFFFFu, visible)) {
+    if (VEC_SH && shs != nullptr && nrows > 0) {
         const float4* src = reinterpret_cast<const float4*>(shs + (size_t)first_row * 48);
         const int total = nrows * SGS_SH_ROW4;
 #pragma unroll
@@ -89,9 +110,8 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     for (int k = 0; k < 16; k++) o_sh[k] = {0.f, 0.f, 0.f};
 
     if (visible) {
-        const float4* arow = reinterpret_cast<const float4*>(acc + (size_t)idx * 12);
-        const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2];
-        const float4 co = conic_opacity[idx];   // A, B, C, opacity
+        const float4 a0 = pre_a0, a1 = pre_a1, a2 = pre_a2;
+        const float4 co = pre_co;   // A, B, C, opacity
         // $R/cuda_rasterizer/backward.cu:460-461 (double product rounded to float once)
         const float ddelx_dx = (float)(0.5 * vp.W), ddely_dy = (float)(0.5 * vp.H);
         const float Sx = a0.x, Sy = a0.y, Sxx = a0.z, Sxy = a0.w, Syy = a1.x;
@@ -104,8 +124,8 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         o_color[1] = a1.w;
         o_color[2] = a2.x;
 
-        const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-        const float* cov3D = cov3Ds + 6 * (size_t)idx;
+        const float3 mean = pre_mean;
+        const float* cov3D = pre_cov;
         const float* view = cam.view;
         const float h_x = vp.focal_x, h_y = vp.focal_y;
 
@@ -214,7 +234,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                     else sh[k] = {0.f, 0.f, 0.f};
                 }
             }
-            const uint8_t cm = clamped[idx];
+            const uint8_t cm = pre_cm;
             F3 dL_dRGB = {o_color[0], o_color[1], o_color[2]};
             dL_dRGB.x *= (cm & 1) ? 0 : 1;
             dL_dRGB.y *= (cm & 2) ? 0 : 1;
@@ -276,8 +296,8 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
 
         // ---- cov3D -> scale / rotation --------------------------------------------------------
         if (scales != nullptr) {
-            const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+            const float3 sc = pre_sc;
+            const float4 q = pre_q;
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
                                2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
