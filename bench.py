@@ -299,9 +299,9 @@ def run_native_or_ref(args, impl):
         calls = max(1, stage["calls"]["render_bwd"])
         k_ms = stage["ms"]["render_bwd"] / calls
         achieved = alg / (k_ms * 1e-3) / 1e9
-        # measured once per round with `ncu --set full` on this exact workload (profiles/r01s_render_ncu_summary.csv)
-        NCU_TRAFFIC_BYTES = 93_287_936        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
-        NCU_WARP_INSTRUCTIONS = 371_781_305   # smsp__inst_executed.sum of one launch
+        # measured once per round with `ncu --set full` on this exact workload (profiles/r02b_render_ncu_summary.csv)
+        NCU_TRAFFIC_BYTES = 94_591_488        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+        NCU_WARP_INSTRUCTIONS = 349_131_307   # smsp__inst_executed.sum of one launch
         sm_mhz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
         issue_peak = 148 * 4 * sm_mhz * 1e6   # one warp-instruction per SM sub-partition per clock
         line["roofline"] = {"kernel": "render_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -309,7 +309,7 @@ def run_native_or_ref(args, impl):
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                             "avg_launch_ms": k_ms,
                             "note": "reported against HBM as the contract asks, but this kernel is instruction-issue "
-                                    "bound (ncu: issue-active 87 %, DRAM 1.7 %): ~95 blended pixel x Gaussian pairs "
+                                    "bound (ncu: issue-active 85 %, DRAM 1.7 %): ~95 blended pixel x Gaussian pairs "
                                     "are evaluated per 48-byte record (DESIGN.md section 3); see `issue`",
                             "issue": {"warp_instructions_per_launch": NCU_WARP_INSTRUCTIONS,
                                       "achieved_Tinst_s": NCU_WARP_INSTRUCTIONS / (k_ms * 1e-3) / 1e12,
