@@ -6,6 +6,8 @@
 #include "../../include/saro_gs_b200.h"
 #include "sgs_common.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx when a tool is attached
+
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -190,10 +192,28 @@ struct Profiler {
 Profiler g_prof;
 std::mutex g_prof_mu;
 
+// SGS_NVTX=1: one NVTX range per stage (the reference has coarse timers only)
+bool nvtx_on() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SGS_NVTX");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+const char* const kStageNames[kStages] = {"sgs/preprocess_fwd", "sgs/depth_sort_scan", "sgs/duplicate", "sgs/tile_sort",
+                                          "sgs/tile_ranges",    "sgs/render_fwd",      "sgs/bwd_zero",  "sgs/render_bwd",
+                                          "sgs/preprocess_bwd"};
+
 struct StageScope {
     int slot = -1;
+    bool range = false;
     cudaStream_t s;
     StageScope(int stage, cudaStream_t stream, int own_kernel_launches) : s(stream) {
+        if (nvtx_on()) {
+            nvtxRangePushA(kStageNames[stage]);
+            range = true;
+        }
         std::lock_guard<std::mutex> lk(g_prof_mu);
         g_prof.own_launches += (uint64_t)own_kernel_launches;
         if (!g_prof.enabled || g_prof.used >= kPool) return;
@@ -208,6 +228,7 @@ struct StageScope {
     }
     ~StageScope() {
         if (slot >= 0) cudaEventRecord(g_prof.ev[slot][1], s);
+        if (range) nvtxRangePop();
     }
 };
 
