@@ -151,6 +151,9 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
 
         // ---- composite -------------------------------------------------------------------
         for (int k = 0; k < SGS_R_BATCH / 32; k++) {
+            // saturation of the whole quadrant is tested once per 32 staged slots, not once per visit
+            both_done = p0.done && p1.done;
+            if (__all_sync(0xFFFFFFFFu, both_done)) break;
             uint32_t word = __shfl_sync(0xFFFFFFFFu, mywords, k);
             while (word) {
                 const uint32_t j = k * 32 + (__ffs(word) - 1);
@@ -168,13 +171,9 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 const uint32_t pos = __float_as_uint(g1.z);
                 if (act0) blend_pixel(p0, pw.x, g1.w, c, pos);
                 if (act1) blend_pixel(p1, pw.y, g1.w, c, pos);
-                both_done = p0.done && p1.done;
-                if (__all_sync(0xFFFFFFFFu, both_done)) {
-                    k = SGS_R_BATCH;   // leave both loops
-                    break;
-                }
             }
         }
+        both_done = p0.done && p1.done;
     }
 
     if (WRITE_PACKED && tid == 0) tile_count[tile] = packed_count;
