@@ -299,8 +299,8 @@ def run_native_or_ref(args, impl):
         calls = max(1, stage["calls"]["render_bwd"])
         k_ms = stage["ms"]["render_bwd"] / calls
         achieved = alg / (k_ms * 1e-3) / 1e9
-        # measured once per round with `ncu --set full` on this exact workload (profiles/r02b_render_ncu_summary.csv)
-        NCU_TRAFFIC_BYTES = 94_591_488        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+        # measured once per round with `ncu --set full` on this exact workload (profiles/r02f_render_ncu_summary.csv)
+        NCU_TRAFFIC_BYTES = 93_804_544        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
         NCU_WARP_INSTRUCTIONS = 349_131_307   # smsp__inst_executed.sum of one launch
         sm_mhz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
         issue_peak = 148 * 4 * sm_mhz * 1e6   # one warp-instruction per SM sub-partition per clock
