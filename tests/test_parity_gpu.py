@@ -483,3 +483,65 @@ def test_runs_on_a_non_default_stream(sgs, dev):
     assert np.array_equal(c0, c1) and np.array_equal(r0, r1) and np.array_equal(d0, d1)
     for k in g0:
         assert maxrel(g1[k], g0[k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_vs_live_reference(sgs, dev, seed):
+    """Random scenes, image sizes, ROTATED cameras, SH degrees, scale modifiers and backgrounds through both the
+    native library and the compiled unmodified reference: forward bit-exact, gradients within tolerance."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not present")
+    from saro_gs_b200 import synthetic
+    import math
+    RefRast = ref_loader.ref_api()[1]
+    gen = torch.Generator().manual_seed(7000 + seed)
+    r = lambda lo, hi: lo + (hi - lo) * float(torch.rand(1, generator=gen))
+    W, H = int(r(40, 300)), int(r(40, 220))
+    P = int(r(50, 4000))
+    fx = r(0.6, 1.6) * W
+    yaw, pitch = r(-0.5, 0.5), r(-0.3, 0.3)
+    cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+    Ry = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]], dtype=torch.float64)
+    Rx = torch.tensor([[1, 0, 0], [0, cp, -sp], [0, sp, cp]], dtype=torch.float64)
+    cam = synthetic.make_camera(W, H, fx, fy=fx * r(0.8, 1.25), R=(Rx @ Ry), t=(r(-0.5, 0.5), r(-0.5, 0.5), r(0.0, 2.0)))
+    means = (torch.rand(P, 3, generator=gen) * 2 - 1) * torch.tensor([3.0, 3.0, 3.0]) + torch.tensor([0.0, 0.0, 3.0])
+    scales = torch.exp(torch.randn(P, 3, generator=gen) * r(0.3, 1.2) + r(-3.5, -1.5))
+    q = torch.randn(P, 4, generator=gen)
+    rots = q / q.norm(dim=1, keepdim=True)
+    op = torch.sigmoid(torch.randn(P, 1, generator=gen) * 2.0)
+    deg = int(r(0, 3.999))
+    shs = torch.randn(P, 16, 3, generator=gen) * 0.3
+    bg = torch.rand(3, generator=gen)
+    mod = r(0.5, 1.5)
+    rs = sgs.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg.to(dev), mod, cam.viewmatrix.to(dev),
+                                           cam.projmatrix.to(dev), deg, cam.campos.to(dev), False)
+    cot = torch.randn(3, H, W, generator=gen).to(dev)
+    outs = []
+    for Rast in (sgs.GaussianRasterizer, RefRast, RefRast):
+        leaves = {k: v.to(dev).clone().requires_grad_(True)
+                  for k, v in dict(means3D=means, scales=scales, rotations=rots, opacities=op, shs=shs).items()}
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii, depth = Rast(rs)(means2D=m2d, **leaves)
+        color.backward(cot)
+        g = {k: v.grad for k, v in leaves.items()}
+        g["means2D"] = m2d.grad
+        outs.append((color.detach(), radii, depth.detach(), g))
+    (c0, r0, d0, g0), (c1, r1, d1, g1), (_, _, _, g2) = outs
+    assert torch.equal(r0, r1) and torch.equal(c0, c1) and torch.equal(d0, d1)
+    for k in g0:
+        scale = float(g1[k].abs().max())
+        if scale == 0.0:
+            assert not g0[k].any(), k
+            continue
+        # The reference sums with float atomics in a different order every run; for ill-conditioned Gaussians
+        # (needle / pancake shapes: the cov3D -> scale, rotation, mean chain cancels by 1e4 and more) two runs of the
+        # REFERENCE differ by percents of the largest entry (seed 8: 5e-2 on means3D; the native kernels' own spread
+        # is 3e-5 there and they sit closer to the float64 oracle than the reference does).  Rows on which the
+        # reference does not reproduce itself to 1e-5 cannot arbitrate and are left out; every other row must agree
+        # to 2e-4 of the largest entry, and such rows must be the overwhelming majority.
+        a, b1, b2 = (t.reshape(t.shape[0], -1) for t in (g0[k], g1[k], g2[k]))
+        stable = (b1 - b2).abs().amax(dim=1) <= 1e-5 * scale
+        assert float(stable.float().mean()) > 0.97, (k, float(stable.float().mean()))
+        err = float((a - b1).abs().amax(dim=1)[stable].max()) / scale
+        assert err < 2e-4, (k, err)
