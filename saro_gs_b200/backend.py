@@ -129,6 +129,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             _ptr(out_color), _ptr(out_depth), _ptr(radii), flags, ctypes.c_void_p(stream))
     _tls.bufs = None
     _check(rendered, "sgs_forward")
+    # remembered on the (opaque) binning buffer so that a backward call on inference-only state fails loudly
+    bufs[_BINNING]._sgs_kept_for_backward = bool(keep_for_backward)
     return int(rendered), out_color, radii, bufs[_GEOM], bufs[_BINNING], bufs[_IMAGE], out_depth
 
 
@@ -148,6 +150,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     if P == 0:
         z = lambda *s: torch.zeros(s, **opts)
         return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, M, 3), z(0, 3), z(0, 4)
+    if getattr(binningBuffer, "_sgs_kept_for_backward", True) is False:
+        raise RuntimeError("rasterize_gaussians_backward: the forward call ran with keep_for_backward=False "
+                           "(inference mode) — its state buffers do not hold the per-tile lists backward needs")
 
     means3D = _f32c(means3D, dev)
     colors = _f32c(colors, dev)

@@ -124,6 +124,21 @@ def test_tile_culling_is_exact(sgs, dev, name):
     assert s0["kept"] <= s1["kept"] and s0["tile_count"].sum() <= s1["tile_count"].sum()
 
 
+def test_backward_on_inference_state_fails_loudly(sgs, dev):
+    d = load("small_sh3")
+    ins = {k: v.to(dev) for k, v in inputs_of(d).items()}
+    rs = settings_from(sgs, d, dev)
+    e = torch.Tensor([])
+    R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(
+        rs.bg, ins["means3D"], e, ins["opacities"], ins["scales"], ins["rotations"], 1.0, e, rs.viewmatrix, rs.projmatrix,
+        rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, ins["shs"], rs.sh_degree, rs.campos, False,
+        keep_for_backward=False)
+    with pytest.raises(RuntimeError, match="keep_for_backward=False"):
+        sgs._C.rasterize_gaussians_backward(rs.bg, ins["means3D"], radii, e, ins["scales"], ins["rotations"], 1.0, e,
+                                            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, torch.zeros_like(color),
+                                            ins["shs"], rs.sh_degree, rs.campos, gb, R, bb, ib)
+
+
 def test_inference_forward_equals_training_forward(sgs, dev):
     d = load("small_sh3")
     _, c0, _, d0, _ = native_state(sgs, d, dev, keep_for_backward=True)
