@@ -153,6 +153,33 @@ int sgs_l1_dssim_loss_forward(int B, int C, int H, int W, const float* img, cons
 int sgs_l1_dssim_loss_backward(int B, int C, int H, int W, const float* img, const float* gt, float lambda_dssim,
                                const float* dmaps, const float* grad_loss, float* dL_dimg, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Per-frame deformation -> rasterizer hand-off — replaces, for the configuration every
+ * shipped config uses (dx, drot, dopacity, dsh on; hidden width 128; time encoding 4; plane feature width <= 39),
+ * GaussianModel.get_deformation_eval of the reference (scene/saro_gaussian.py:871-921): survival-state selection
+ * (state = exp(-4 ((t - temporal_pos) / lifespan)^2) > 0.001, :757-759,:872-881), the three 3-layer MLPs
+ * (:104,:108,:110) on [plane feature | time embedding], and the residual / activation epilogues that produce the
+ * rasterizer's means3D, rotations, scales, opacities and shs for the selected Gaussians, in source order.
+ *
+ * sgs_deform_pack_mlp: converts one MLP's float32 nn.Linear parameters (W [out][in] row-major, device pointers) into
+ *   the resident tensor-core image; call once per MLP (mlp = 0 motion [3 outputs], 1 rot+scale [7], 2 shs [48]) whenever
+ *   the weights change.  `packed`: sgs_deform_packed_bytes() bytes on the device.  in_dim = feature width + 9.
+ * sgs_deform_eval: all inputs are device float32, contiguous: xyz [N][3], rotation [N][4], scaling [N][3], opacity [N],
+ *   features_dc [N][3], features_rest [N][45], temporal_pos [N], lifespan [N], hexplane_feature [N][feat_dim].
+ *   Outputs have room for N rows; the first `return value` rows are written: out_means3D [.][3], out_rotations [.][4],
+ *   out_scales [.][3], out_opacity [.], out_shs [.][48].  `workspace`: sgs_deform_workspace_bytes(N) bytes of device
+ *   scratch.  Returns the number of selected Gaussians (the host waits only for the selection pass; the MLP kernel is
+ *   still running on `stream` when the call returns) or a negative error code. */
+size_t sgs_deform_packed_bytes(void);
+size_t sgs_deform_workspace_bytes(int N);
+int sgs_deform_pack_mlp(int mlp, int in_dim, const float* W1, const float* b1, const float* W2, const float* b2,
+                        const float* W3, const float* b3, void* packed, void* stream);
+int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, const float* rotation, const float* scaling,
+                        const float* opacity, const float* features_dc, const float* features_rest,
+                        const float* temporal_pos, const float* lifespan, const float* hexplane_feature,
+                        const void* packed, void* workspace, size_t workspace_bytes, float* out_means3D,
+                        float* out_rotations, float* out_scales, float* out_opacity, float* out_shs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

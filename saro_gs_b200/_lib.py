@@ -41,6 +41,10 @@ ABI = {
     "sgs_l1_dssim_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_l1_dssim_loss_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "sgs_l1_dssim_loss_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "sgs_deform_packed_bytes": (ctypes.c_size_t, []),
+    "sgs_deform_workspace_bytes": (ctypes.c_size_t, [_i]),
+    "sgs_deform_pack_mlp": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_deform_eval": (_i64, [_i, _i, _f] + [_vp] * 10 + [_vp, ctypes.c_size_t] + [_vp] * 5 + [_vp]),
     "sgs_profile_enable": (None, [_i]),
     "sgs_profile_read": (_i, [_vp, _vp, _vp]),
 }

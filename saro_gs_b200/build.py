@@ -22,6 +22,7 @@ SOURCES = [
     "sgs_render_bwd.cu",
     "sgs_preprocess_bwd.cu",
     "sgs_loss.cu",
+    "sgs_deform.cu",
 ]
 HEADERS = ["sgs_common.cuh", os.path.join("..", "..", "include", "saro_gs_b200.h")]
 

@@ -1,0 +1,137 @@
+// Developer probe (GPU box): one 128 x N x K tcgen05.mma (kind::f16, bf16 inputs, f32 accumulate in TMEM) from operands
+// laid out by plain st.shared in the no-swizzle K-major canonical layout, checked against a CPU product. Used once to pin
+// the shared-memory descriptor fields (LBO / SBO meaning) and the instruction descriptor before the fused deformation
+// kernel was written on top of the same primitives.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe umma_probe.cu
+//   ./umma_probe N K variant        variant 0: LBO = K-chunk stride, SBO = 8-row-group stride; 1: swapped
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (sm_100)
+    return d;                        // base offset 0, lbo mode 0, layout type 0 (no swizzle)
+}
+
+__global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                  float* __restrict__ D, int N, int K, int variant, int reps)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 128 * K * 2;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // A: row r = tid, K/8 chunks of 16 B; physical offset = chunk * (128 * 16) + r * 16
+    for (int kc = 0; kc < K / 8; ++kc)
+        *reinterpret_cast<uint4*>(sA + kc * 128 * 16 + tid * 16) = *reinterpret_cast<const uint4*>(A + (size_t)tid * K + kc * 8);
+    for (int i = tid; i < N * (K / 8); i += 128) {
+        int n = i % N, kc = i / N;
+        *reinterpret_cast<uint4*>(sB + kc * N * 16 + n * 16) = *reinterpret_cast<const uint4*>(B + (size_t)n * K + kc * 8);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t strideA = 128 * 16, strideB = (uint32_t)N * 16;   // K-chunk stride in bytes
+    uint32_t phase = 0;
+    long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+        if (tid == 0) {
+            for (int ks = 0; ks < K / 16; ++ks) {
+                uint64_t da = variant == 0 ? make_desc(smem_u32(sA) + ks * 2 * strideA, strideA, 128)
+                                           : make_desc(smem_u32(sA) + ks * 2 * strideA, 128, strideA);
+                uint64_t db = variant == 0 ? make_desc(smem_u32(sB) + ks * 2 * strideB, strideB, 128)
+                                           : make_desc(smem_u32(sB) + ks * 2 * strideB, 128, strideB);
+                uint32_t acc = ks > 0;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+        }
+        uint32_t done = 0;
+        for (long long spin = 0; !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+            if (spin > (1ll << 22)) { if (tid == 0) printf("mbarrier wait timed out\n"); __trap(); }
+        }
+        phase ^= 1;
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int i = 0; i < 8; ++i) D[(size_t)tid * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    if (tid == 0 && reps > 1) printf("clocks per %d-step MMA chain + commit + wait: %.1f\n", K / 16, double(t1 - t0) / reps);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u));
+}
+
+int main(int argc, char** argv)
+{
+    int N = argc > 1 ? atoi(argv[1]) : 128, K = argc > 2 ? atoi(argv[2]) : 128, variant = argc > 3 ? atoi(argv[3]) : 0;
+    int reps = argc > 4 ? atoi(argv[4]) : 1;
+    std::vector<__nv_bfloat16> hA(128 * K), hB(N * K);
+    std::vector<float> fA(128 * K), fB(N * K);
+    srand(7);
+    for (int i = 0; i < 128 * K; ++i) { float v = float((rand() % 17) - 8); fA[i] = v; hA[i] = __float2bfloat16(v); }
+    for (int i = 0; i < N * K; ++i) { float v = float((rand() % 13) - 6) * 0.5f; fB[i] = v; hB[i] = __float2bfloat16(v); }
+    __nv_bfloat16 *dA, *dB; float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xFF, 128 * N * 4));
+    size_t smem = (128 + N) * K * 2 + 1024;
+    CK(cudaFuncSetAttribute(umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_probe<<<1, 128, smem>>>(dA, dB, dD, N, K, variant, reps);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hD(128 * N);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0; double maxerr = 0;
+    for (int r = 0; r < 128; ++r)
+        for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)fA[r * K + k] * fB[n * K + k];
+            double e = fabs(s - hD[r * N + n]);
+            if (!(e <= 1e-3)) { if (bad < 4) printf("  mismatch r=%d n=%d got %g want %g\n", r, n, hD[r * N + n], s); ++bad; }
+            if (e > maxerr) maxerr = e;
+        }
+    printf("N=%d K=%d variant=%d: %s (%d / %d mismatches, max err %g)\n", N, K, variant, bad ? "FAIL" : "OK", bad, 128 * N, maxerr);
+    return bad ? 1 : 0;
+}
