@@ -321,6 +321,7 @@ def run_native_or_ref(args, impl):
         line["gpu_launches_note"] = "hand-written kernels only (6/step); CUB sort/scan kernels launched by the library are extra"
         if rank == 0:
             line["loss_path"] = loss_path_timing(dev, H, W)
+            line["deform_path"] = deform_path_timing(dev)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
     if rank == 0:
@@ -362,6 +363,56 @@ def loss_path_timing(dev, H, W, iters=20):
             "fused_ms": fused_ms, "pytorch_ops_ms": torch_ms, "speedup": torch_ms / fused_ms,
             "fused_GBps": (8 + 12 + 20 + 4) * px / (fused_ms * 1e-3) / 1e9,
             "loss_fused": fused_val, "loss_pytorch": torch_val}
+
+
+def deform_path_timing(dev, iters=15):
+    """the per-frame deformation -> rasterizer hand-off of the test-time render loop
+    (renderer/__init__.py:188-203 times get_deformation_eval + the rasterizer).  Fused tcgen05 kernel vs the same
+    function as the PyTorch ops SaRO-GS runs, on the headline cloud (300 k Gaussians, 32 plane features), and the
+    whole test-time frame (hand-off + forward render) on both sides.  CUDA events, inputs resident, no_grad."""
+    import saro_gs_b200 as sgs
+    from saro_gs_b200 import synthetic, deformation
+    from oracle.deform_torch import torch_get_deformation_eval
+    from oracle import ref_loader
+    scene, cam = synthetic.config2_scene()
+    pc = synthetic.model_to(synthetic.dynamic_model(scene), dev)
+    rs_args = (cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0, cam.viewmatrix.to(dev),
+               cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    native_rast = sgs.GaussianRasterizer(sgs.GaussianRasterizationSettings(*rs_args))
+    ref_rast = None
+    if ref_loader.available():
+        ref_rast = ref_loader.ref_api()[1](sgs.GaussianRasterizationSettings(*rs_args))
+    stamps = [0.1 + 0.8 * i / (iters + 2) for i in range(iters + 3)]
+
+    def run(deform, rast):
+        ms, sel = [], 0
+        with torch.no_grad():
+            for i, t in enumerate(stamps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m3, rot, sc, op, shs = deform(pc, t)
+                if rast is not None:
+                    rast(means3D=m3, means2D=torch.zeros_like(m3), opacities=op, shs=shs, scales=sc, rotations=rot)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms.append(e0.elapsed_time(e1))
+                    sel += m3.shape[0]
+        return sum(ms) / len(ms), sel / len(ms)
+
+    fused_ms, sel = run(deformation.get_deformation_eval, None)
+    torch_ms, _ = run(torch_get_deformation_eval, None)
+    frame_native, _ = run(deformation.get_deformation_eval, native_rast)
+    out = {"what": "get_deformation_eval on 300k Gaussians (32 plane features, 3 MLPs 41-128-128-{3,7,48}), "
+                   "timestamps swept over [0.1, 0.9]",
+           "selected_mean": sel, "fused_ms": fused_ms, "pytorch_ops_ms": torch_ms, "speedup": torch_ms / fused_ms,
+           "fused_TFLOPs_fp32_equivalent": sel * 2 * (3 * 41 * 128 + 3 * 128 * 128 + 128 * 58) / (fused_ms * 1e-3) / 1e12,
+           "test_time_frame_ms": {"native": frame_native}}
+    if ref_rast is not None:
+        frame_ref, _ = run(torch_get_deformation_eval, ref_rast)
+        out["test_time_frame_ms"]["reference_ops_and_rasterizer"] = frame_ref
+        out["test_time_frame_ms"]["speedup"] = frame_ref / frame_native
+    return out
 
 
 def cpu_baseline(precision="f32"):

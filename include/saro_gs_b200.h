@@ -155,7 +155,7 @@ int sgs_l1_dssim_loss_backward(int B, int C, int H, int W, const float* img, con
 
 /* ---------------------------------------------------------------------------------------------------
  * Per-frame deformation -> rasterizer hand-off — replaces, for the configuration every
- * shipped config uses (dx, drot, dopacity, dsh on; hidden width 128; time encoding 4; plane feature width <= 39),
+ * shipped config uses (dx, drot, dopacity, dsh on; hidden width 128; time encoding 4; plane feature width 8/16/24/32),
  * GaussianModel.get_deformation_eval of the reference (scene/saro_gaussian.py:871-921): survival-state selection
  * (state = exp(-4 ((t - temporal_pos) / lifespan)^2) > 0.001, :757-759,:872-881), the three 3-layer MLPs
  * (:104,:108,:110) on [plane feature | time embedding], and the residual / activation epilogues that produce the

@@ -53,9 +53,7 @@ constexpr int OFF_B2 = OFF_B1 + HID * 4;
 constexpr int OFF_B3 = OFF_B2 + HID * 4;
 constexpr int IMG_BYTES = OFF_B3 + N3_MAX * 4;                 // 115 904
 constexpr int IMG_PAD = (IMG_BYTES + 1023) / 1024 * 1024;      // 116 736
-constexpr int A_PLANE = ROWS * HID * 2;                        // 32 768: one bf16 plane of the A operand
-constexpr int SMEM_BYTES = IMG_PAD + 2 * A_PLANE + 64;
-constexpr int A_CHUNK = ROWS * 16;                             // byte stride between 8-wide K chunks of A
+constexpr int SMEM_BYTES = IMG_PAD + 64;                       // weights + two mbarriers + the TMEM base slot
 
 __host__ __device__ constexpr int n3_real(int mlp) { return mlp == 0 ? 3 : mlp == 1 ? 7 : 48; }
 __host__ __device__ constexpr int n3_pad(int mlp) { return mlp == 2 ? 48 : 16; }
@@ -124,9 +122,10 @@ __global__ void pack_mlp_kernel(int mlp, int in_dim, const float* __restrict__ W
 // ------------------------------------------------------------------------------------------------ tcgen05 helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// shared-memory matrix descriptor, no swizzle, K-major: LBO = byte stride between the two 8-wide K chunks of one
-// instruction, SBO = byte stride between 8-row groups (128: rows are packed 16 B apart).  Pinned on hardware by
-// tools/microbench/umma_probe.cu.
+// B operand: shared-memory matrix descriptor, no swizzle, K-major: LBO = byte stride between the two 8-wide K chunks
+// of one instruction, SBO = byte stride between 8-row groups (128: rows are packed 16 B apart).
+// A operand: TMEM, lane = row, 32-bit column c = K elements (2c | 2c+1 << 16).
+// Both pinned on hardware by tools/microbench/umma_probe.cu (variants 0 and 2).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
@@ -135,29 +134,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t umma_idesc(int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
 
-// One layer: D[128 x N] = A[128 x 16*ksteps] * B[N x 16*ksteps]^T as hi*hi + hi*lo + lo*hi; one thread calls this.
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            int ksteps, int N, uint32_t mbar) {
+// One layer: D[128 x N] = A[128 x 16*KSTEPS] * B[N x 16*KSTEPS]^T as hi*hi + hi*lo + lo*hi.  Called by ALL lanes of
+// the issuing warp with warp-uniform arguments (descriptor arithmetic stays off the critical path; the probe measured
+// 64 clocks per N = 128 instruction this way against 160 when a single divergent thread builds the operands);
+// `elected` is one lane's predicate.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_layer(uint32_t elected, uint32_t acc_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                            uint32_t b_lo, int N, uint32_t mbar) {
     const uint32_t idesc = umma_idesc(N);
     const uint32_t b_chunk = (uint32_t)N * 16;
-    uint32_t acc = 0;
-#pragma unroll 1
+    const uint64_t b_step = (uint64_t)((2 * b_chunk) >> 4);
+#pragma unroll
     for (int prod = 0; prod < 3; ++prod) {
         const uint32_t a = prod == 2 ? a_lo : a_hi;
-        const uint32_t b = prod == 1 ? b_lo : b_hi;
-#pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
-            umma_bf16(tmem, umma_desc(a + ks * 2 * A_CHUNK, A_CHUNK), umma_desc(b + ks * 2 * b_chunk, b_chunk), idesc, acc);
-            acc = 1;
+        uint64_t db = umma_desc(prod == 1 ? b_lo : b_hi, b_chunk);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            if (elected)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)((prod | ks) != 0)) : "memory");
+            db += b_step;
         }
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+    if (elected)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+    __syncwarp();
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
@@ -179,9 +182,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
 
-// 8 consecutive K values of this thread's row -> hi / lo bf16 planes of the A operand
-__device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, int kc, int row, const float (&v)[8]) {
+// 8 consecutive K values of this thread's row -> 4 + 4 packed words of the hi / lo bf16 planes of the TMEM A operand
+__device__ __forceinline__ void store_chunk(uint32_t t_hi, uint32_t t_lo, int kc, const float (&v)[8]) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -191,8 +198,16 @@ __device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, int kc
         h[i] = *reinterpret_cast<const uint32_t*>(&hh);
         l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    *reinterpret_cast<uint4*>(a_hi + kc * A_CHUNK + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(a_lo + kc * A_CHUNK + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    tmem_st4(t_hi + kc * 4, h);
+    tmem_st4(t_lo + kc * 4, l);
+}
+
+// order this thread's TMEM stores before the MMA another thread is about to issue, then meet the group
+__device__ __forceinline__ void publish_operand(int group) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + group), "r"(ROWS) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
 struct EvalParams {
@@ -205,191 +220,217 @@ struct EvalParams {
     float *o_means3D, *o_rot, *o_scale, *o_opacity, *o_shs;
 };
 
-// hidden layer epilogue: accumulator row -> + bias, ReLU -> next layer's A operand (in place of the previous one)
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* a_hi,
-                                                uint8_t* a_lo, int row) {
+// hidden layer epilogue: accumulator row -> + bias, ReLU -> next layer's A operand (TMEM, bf16 hi / lo planes)
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias) {
 #pragma unroll 1
     for (int c0 = 0; c0 < HID; c0 += 16) {
         float v[16];
-        tmem_ld16(tmem_row + c0, v);
+        tmem_ld16(t_acc + c0, v);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float x[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = fmaxf(v[h * 8 + i] + bias[c0 + h * 8 + i], 0.f);
-            store_chunk(a_hi, a_lo, c0 / 8 + h, row, x);
+            store_chunk(t_hi, t_lo, c0 / 8 + h, x);
         }
     }
 }
 
-__global__ void __launch_bounds__(ROWS, 1) deform_mlp_kernel(const EvalParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* img = smem;
-    uint8_t* a_hi = smem + IMG_PAD;
-    uint8_t* a_lo = a_hi + A_PLANE;
-    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(a_lo + A_PLANE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 1);
+struct RowInputs {        // what one thread needs to build its row of the layer-1 operand
+    int src;
+    float d;              // timestamp - temporal_pos
+    float4 f[8];          // up to 32 plane features
+};
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int mlp = 2 - (int)(blockIdx.x % 3);                   // block 0 -> shs (the most expensive of the three)
-    const int worker = blockIdx.x / 3;
-    const int workers = ((int)gridDim.x - (int)(blockIdx.x % 3) + 2) / 3;
-    const int count = *p.count;
-    const int tiles = (count + ROWS - 1) / ROWS;
+__device__ __forceinline__ void load_row_inputs(const EvalParams& p, int j, int count, int nf, RowInputs& r) {
+    r.src = __ldg(p.index + (j < count ? j : count - 1));
+    r.d = p.timestamp - __ldg(p.tpos + r.src);
+    const float4* frow = reinterpret_cast<const float4*>(p.feat + (size_t)r.src * p.feat_dim);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < 2 * nf) r.f[q] = __ldg(frow + q);
+}
 
-    {   // resident weights: linear copy of this MLP's packed image
-        const uint4* src = reinterpret_cast<const uint4*>(p.packed + (size_t)mlp * IMG_BYTES);
-        uint4* dst = reinterpret_cast<uint4*>(img);
-        for (int i = tid; i < IMG_BYTES / 16; i += ROWS) dst[i] = __ldg(src + i);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p)), "r"(1u));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t mbar = smem_u32(mbar_p);
-    const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), simg = smem_u32(img);
+template <int MLP>
+__device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img, int group, int worker, int workers,
+                                        uint32_t tmem_group, uint32_t mbar) {
+    const int tid = threadIdx.x & (ROWS - 1), warp_in_group = tid >> 5;
+    const bool issuer = warp_in_group == 0;
+    uint32_t elected = 0;
+    if (issuer) asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+    const uint32_t lane_base = (uint32_t)(warp_in_group * 32) << 16;
+    const uint32_t acc_u = tmem_group, hi_u = tmem_group + 128, lo_u = tmem_group + 192;     // lane-0 addresses (MMA)
+    const uint32_t t_acc = acc_u + lane_base, t_hi = hi_u + lane_base, t_lo = lo_u + lane_base;
+    const uint32_t simg = smem_u32(img);
     const float* b1 = reinterpret_cast<const float*>(img + OFF_B1);
     const float* b2 = reinterpret_cast<const float*>(img + OFF_B2);
     const float* b3 = reinterpret_cast<const float*>(img + OFF_B3);
-    const Alive alive{p.tpos, p.life, p.timestamp};
-    const int F = p.feat_dim, n3 = n3_pad(mlp);
+    const int count = *p.count;
+    const int tiles = (count + ROWS - 1) / ROWS;
+    const int nf = p.feat_dim >> 3;                    // feature chunks of 8 (feat_dim is a multiple of 8, <= 32)
+    constexpr int N3 = n3_pad(MLP);
     uint32_t phase = 0;
+
+    RowInputs cur;
+    if (worker < tiles) load_row_inputs(p, worker * ROWS + tid, count, nf, cur);
 
 #pragma unroll 1
     for (int tile = worker; tile < tiles; tile += workers) {
         const int j = tile * ROWS + tid;
         const bool valid = j < count;
-        const int src = p.index[valid ? j : count - 1];
+        const int src = cur.src;
 
-        // ---- layer-1 operand: [hexplane feature | time embedding | 0 padding]
+        // ---- layer-1 operand: [plane feature | time embedding | 0 padding]  (saro_gaussian.py:875-876, :939-969)
         {
-            const float d = p.timestamp - p.tpos[src];
             float emb[TIME_DIMS];
-            emb[0] = d;
+            emb[0] = cur.d;
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                const float x = d * (float)(1 << f);
+                const float x = cur.d * (float)(1 << f);
                 emb[1 + 2 * f] = sinf(x);
                 emb[2 + 2 * f] = cosf(x);
             }
-            const float* frow = p.feat + (size_t)src * F;
 #pragma unroll
             for (int kc = 0; kc < K1 / 8; ++kc) {
                 float x[8];
-                if ((F & 3) == 0 && kc * 8 + 8 <= F) {
-                    const float4 u = __ldg(reinterpret_cast<const float4*>(frow + kc * 8));
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(frow + kc * 8 + 4));
+                if (kc < 4 && kc < nf) {
+                    const float4 u = cur.f[2 * (kc < 4 ? kc : 0)], w = cur.f[2 * (kc < 4 ? kc : 0) + 1];
                     x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
+                } else if (kc == nf) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = emb[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = kc * 8 + i;
-                        float val = 0.f;
-                        if (k < F) val = __ldg(frow + k);
-                        else if (k - F < TIME_DIMS) {
-                            const int e = k - F;
-                            val = emb[0];
-#pragma unroll
-                            for (int q = 1; q < TIME_DIMS; ++q) val = e == q ? emb[q] : val;
-                        }
-                        x[i] = val;
-                    }
+                    for (int i = 0; i < 8; ++i) x[i] = 0.f;
+                    if (kc == nf + 1) x[0] = emb[8];
                 }
-                store_chunk(a_hi, a_lo, kc, tid, x);
+                store_chunk(t_hi, t_lo, kc, x);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(tmem, sa_hi, sa_lo, simg + OFF_W1HI, simg + OFF_W1LO, K1 / 16, HID, mbar);
+        publish_operand(group);
+        if (issuer) issue_layer<K1 / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W1HI, simg + OFF_W1LO, HID, mbar);
+
+        // ---- while the tensor core works: next tile's inputs and this tile's residual bases (consumed much later)
+        RowInputs nxt = cur;
+        if (tile + workers < tiles) load_row_inputs(p, (tile + workers) * ROWS + tid, count, nf, nxt);
+        float base[MLP == 2 ? 48 : 8];
+        if (MLP == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) base[c] = __ldg(p.xyz + (size_t)src * 3 + c);
+        } else if (MLP == 1) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.rotation) + src);
+            base[0] = q0.x; base[1] = q0.y; base[2] = q0.z; base[3] = q0.w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) base[4 + c] = __ldg(p.scaling + (size_t)src * 3 + c);
+            base[7] = __ldg(p.opacity + src);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) base[c] = __ldg(p.features_dc + (size_t)src * 3 + c);
+#pragma unroll
+            for (int c = 0; c < 45; ++c) base[3 + c] = __ldg(p.features_rest + (size_t)src * 45 + c);
         }
+        float state = 0.f;
+        if (MLP == 1) {                                  // saro_gaussian.py:872-873 (selection re-evaluated, same arithmetic)
+            const float q = cur.d / __ldg(p.life + src);
+            state = expf(-4.f * (q * q));
+        }
+
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue(tmem_row, b1, a_hi, a_lo, tid);
-
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(tmem, sa_hi, sa_lo, simg + OFF_W2HI, simg + OFF_W2LO, HID / 16, HID, mbar);
-        }
+        hidden_epilogue(t_acc, t_hi, t_lo, b1);
+        publish_operand(group);
+        if (issuer) issue_layer<HID / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W2HI, simg + OFF_W2LO, HID, mbar);
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue(tmem_row, b2, a_hi, a_lo, tid);
-
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_layer(tmem, sa_hi, sa_lo, simg + OFF_W3HI, simg + OFF_W3LO, HID / 16, n3, mbar);
-        }
+        hidden_epilogue(t_acc, t_hi, t_lo, b2);
+        publish_operand(group);
+        if (issuer) issue_layer<HID / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W3HI, simg + OFF_W3LO, N3, mbar);
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- output epilogue: residual + activation, written in the rasterizer's input layout
-        if (mlp == 0) {                                  // means3D = xyz + motion            (:883-885)
+        if (MLP == 0) {                                  // means3D = xyz + motion            (:883-885)
             float r[16];
-            tmem_ld16(tmem_row, r);
+            tmem_ld16(t_acc, r);
             if (valid) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) p.o_means3D[(size_t)j * 3 + c] = p.xyz[(size_t)src * 3 + c] + (r[c] + b3[c]);
+                for (int c = 0; c < 3; ++c) p.o_means3D[(size_t)j * 3 + c] = base[c] + (r[c] + b3[c]);
             }
-        } else if (mlp == 1) {                           // rotation, scale, opacity         (:889-897, :903-905)
+        } else if (MLP == 1) {                           // rotation, scale, opacity         (:889-897, :903-905)
             float r[16];
-            tmem_ld16(tmem_row, r);
+            tmem_ld16(t_acc, r);
             if (valid) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.rotation) + src);
-                const float qx = q0.x + (r[0] + b3[0]), qy = q0.y + (r[1] + b3[1]);
-                const float qz = q0.z + (r[2] + b3[2]), qw = q0.w + (r[3] + b3[3]);
+                const float qx = base[0] + (r[0] + b3[0]), qy = base[1] + (r[1] + b3[1]);
+                const float qz = base[2] + (r[2] + b3[2]), qw = base[3] + (r[3] + b3[3]);
                 const float nrm = fmaxf(sqrtf(qx * qx + qy * qy + qz * qz + qw * qw), 1e-12f);   // F.normalize eps
                 reinterpret_cast<float4*>(p.o_rot)[j] = make_float4(qx / nrm, qy / nrm, qz / nrm, qw / nrm);
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    p.o_scale[(size_t)j * 3 + c] = expf(p.scaling[(size_t)src * 3 + c] + (r[4 + c] + b3[4 + c]));
-                const float o = 1.f / (1.f + expf(-p.opacity[src]));
-                p.o_opacity[j] = o * alive.state(src);
+                for (int c = 0; c < 3; ++c) p.o_scale[(size_t)j * 3 + c] = expf(base[4 + c] + (r[4 + c] + b3[4 + c]));
+                p.o_opacity[j] = (1.f / (1.f + expf(-base[7]))) * state;
             }
         } else {                                         // shs = cat(dc, rest) + residual   (:911-915)
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < 48; c0 += 16) {
                 float r[16];
-                tmem_ld16(tmem_row + c0, r);
+                tmem_ld16(t_acc + c0, r);
                 if (valid) {
-                    float base[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = c0 + i;
-                        base[i] = c < 3 ? __ldg(p.features_dc + (size_t)src * 3 + c) : __ldg(p.features_rest + (size_t)src * 45 + (c - 3));
-                    }
                     float4* out = reinterpret_cast<float4*>(p.o_shs + (size_t)j * 48 + c0);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        out[i] = make_float4(base[4 * i] + (r[4 * i] + b3[c0 + 4 * i]), base[4 * i + 1] + (r[4 * i + 1] + b3[c0 + 4 * i + 1]),
-                                             base[4 * i + 2] + (r[4 * i + 2] + b3[c0 + 4 * i + 2]), base[4 * i + 3] + (r[4 * i + 3] + b3[c0 + 4 * i + 3]));
+                        out[i] = make_float4(base[c0 + 4 * i] + (r[4 * i] + b3[c0 + 4 * i]),
+                                             base[c0 + 4 * i + 1] + (r[4 * i + 1] + b3[c0 + 4 * i + 1]),
+                                             base[c0 + 4 * i + 2] + (r[4 * i + 2] + b3[c0 + 4 * i + 2]),
+                                             base[c0 + 4 * i + 3] + (r[4 * i + 3] + b3[c0 + 4 * i + 3]));
                 }
             }
         }
-        // the next tile's layer-1 MMA overwrites the accumulator columns read above
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        cur = nxt;
     }
+}
+
+// 256 threads = two independent row groups of 128 that share one MLP's resident weights: while one group's layer is
+// in the tensor core the other group runs its epilogue, so the chain latency of one tile hides behind the other's.
+__global__ void __launch_bounds__(2 * ROWS, 1) deform_mlp_kernel(const EvalParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* img = smem;
+    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + IMG_PAD);          // one per group
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, group = tid >> 7;
+    const int mlp = 2 - (int)(blockIdx.x % 3);                   // block 0 -> shs (the most expensive of the three)
+    const int ctas = ((int)gridDim.x - (int)(blockIdx.x % 3) + 2) / 3;       // CTAs working on this MLP
+    const int worker = (int)(blockIdx.x / 3) * 2 + group;
+    const int workers = ctas * 2;
+
+    {   // resident weights: linear copy of this MLP's packed image
+        const uint4* src = reinterpret_cast<const uint4*>(p.packed + (size_t)mlp * IMG_BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(img);
+        for (int i = tid; i < IMG_BYTES / 16; i += 2 * ROWS) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + 1)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t tmem_group = tmem + (uint32_t)group * 256;    // acc [0,128) | operand hi [128,192) | operand lo [192,256)
+    const uint32_t mbar = smem_u32(mbar_p + group);
+
+    if (mlp == 0) run_mlp<0>(p, img, group, worker, workers, tmem_group, mbar);
+    else if (mlp == 1) run_mlp<1>(p, img, group, worker, workers, tmem_group, mbar);
+    else run_mlp<2>(p, img, group, worker, workers, tmem_group, mbar);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
 
 std::mutex g_mu;
@@ -440,7 +481,7 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
                         const void* packed, void* workspace, size_t workspace_bytes, float* out_means3D,
                         float* out_rotations, float* out_scales, float* out_opacity, float* out_shs, void* stream) {
     using namespace sgs_deform;
-    if (N < 0 || feat_dim <= 0 || feat_dim + TIME_DIMS > K1) return SGS_ERR_INVALID_ARGUMENT;
+    if (N < 0 || feat_dim <= 0 || (feat_dim & 7) || feat_dim > 32) return SGS_ERR_INVALID_ARGUMENT;
     if (N == 0) return 0;
     if (!xyz || !rotation || !scaling || !opacity || !features_dc || !features_rest || !temporal_pos || !lifespan ||
         !hexplane_feature || !packed || !workspace || !out_means3D || !out_rotations || !out_scales || !out_opacity || !out_shs)
@@ -479,8 +520,8 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
     p.o_means3D = out_means3D; p.o_rot = out_rotations; p.o_scale = out_scales; p.o_opacity = out_opacity; p.o_shs = out_shs;
     const int tiles_max = (N + ROWS - 1) / ROWS;
     int grid = g_sm_count > 0 ? g_sm_count : 148;
-    if (grid > 3 * tiles_max) grid = 3 * tiles_max;
-    deform_mlp_kernel<<<grid, ROWS, SMEM_BYTES, s>>>(p);
+    if (grid > 3 * ((tiles_max + 1) / 2)) grid = 3 * ((tiles_max + 1) / 2);
+    deform_mlp_kernel<<<grid, 2 * ROWS, SMEM_BYTES, s>>>(p);
     if (cudaGetLastError() != cudaSuccess) return SGS_ERR_CUDA;
     // the host needs the number of selected Gaussians to shape the rasterizer call; it is ready as soon as the
     // selection pass is, while the MLP kernel keeps running

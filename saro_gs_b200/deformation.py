@@ -17,7 +17,6 @@ from . import _lib
 
 TIME_DIMS = 9          # get_embedder(4): x, sin/cos of 1x, 2x, 4x, 8x  (saro_gaussian.py:94, :922-969)
 HIDDEN = 128           # args.deform_hidden_dim                       (arguments/__init__.py:65)
-MAX_IN_DIM = 48
 _OUT_DIMS = (3, 7, 48)
 
 
@@ -68,9 +67,10 @@ class PackedMLPs:
             got = [tuple(t.shape) for t in ps]
             if got != want:
                 raise UnsupportedDeformationConfig(f"MLP {m}: parameter shapes {got}, supported {want}")
-        if not (TIME_DIMS < in_dim <= MAX_IN_DIM):
+        if in_dim - TIME_DIMS not in (8, 16, 24, 32):
             raise UnsupportedDeformationConfig(
-                f"MLP input width {in_dim} (plane feature + {TIME_DIMS}) is outside ({TIME_DIMS}, {MAX_IN_DIM}]")
+                f"MLP input width {in_dim} = plane feature width {in_dim - TIME_DIMS} + {TIME_DIMS}: the kernel supports "
+                "plane feature widths 8, 16, 24 and 32 (every shipped config uses 16 or 32)")
         self.in_dim = in_dim
         self.feat_dim = in_dim - TIME_DIMS
         self.buffer = torch.empty(lib.sgs_deform_packed_bytes(), dtype=torch.uint8, device=dev)

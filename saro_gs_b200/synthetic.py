@@ -153,3 +153,47 @@ def temporal_frame(scene, t, seed=7):
     return Scene(means[keep].contiguous(), scene.scales[keep].contiguous(), scene.rotations[keep].contiguous(),
                  (scene.opacities * survival[:, None])[keep].contiguous(), scene.shs[keep].contiguous(),
                  scene.sh_degree)
+
+
+def dynamic_model(scene, feat_dim=32, seed=0, lifespan=(0.15, 1.2), residual_gain=0.05):
+    """A stand-in for the reference's dynamic GaussianModel after get_deformfeature() (scene/saro_gaussian.py:863-869):
+    the attributes get_deformation_eval reads (:871-921) — raw (pre-activation) parameters derived from `scene`, a
+    temporal centre and lifespan per Gaussian, cached plane features and the three 3-layer MLPs (:104,:108,:110).
+    CPU tensors / modules; move with `.to(device)` per attribute (see tests and bench.py)."""
+    import types
+    gen = torch.Generator().manual_seed(seed + 1234)
+    P = scene.means3D.shape[0]
+
+    def mlp(out_dim):
+        m = torch.nn.Sequential(torch.nn.Linear(feat_dim + 9, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128),
+                                torch.nn.ReLU(), torch.nn.Linear(128, out_dim))
+        with torch.no_grad():
+            for i, layer in enumerate(l for l in m if isinstance(l, torch.nn.Linear)):
+                torch.nn.init.xavier_uniform_(layer.weight, generator=gen)
+                layer.bias.uniform_(-0.05, 0.05, generator=gen)
+                if i == 2:
+                    layer.weight.mul_(residual_gain)
+                    layer.bias.mul_(residual_gain)
+        return m
+
+    op = scene.opacities.clamp(1e-4, 1 - 1e-4)
+    pc = types.SimpleNamespace(
+        args=types.SimpleNamespace(dx=True, drot=True, dopacity=True, dsh=True, sigmoid_tcenter=False),
+        _xyz=scene.means3D.clone(), _rotation=scene.rotations.clone(), _scaling=torch.log(scene.scales),
+        _opacity=torch.log(op / (1 - op)).reshape(P, 1),
+        _features_dc=scene.shs[:, :1, :].contiguous(), _features_rest=scene.shs[:, 1:, :].contiguous(),
+        get_temporalpos=torch.rand(P, 1, generator=gen),
+        _lifespan=torch.rand(P, 1, generator=gen) * (lifespan[1] - lifespan[0]) + lifespan[0],
+        hexplane_feature=torch.randn(P, feat_dim, generator=gen) * 0.3,
+        motion_mlp=mlp(3), rot_mlp=mlp(7), shs_mlp=mlp(48))
+    return pc
+
+
+def model_to(pc, device):
+    """Move every tensor / module of a dynamic_model() to `device` (returns a new namespace)."""
+    import types
+    out = types.SimpleNamespace(args=pc.args)
+    for k, v in vars(pc).items():
+        if k != "args":
+            setattr(out, k, v.to(device))
+    return out

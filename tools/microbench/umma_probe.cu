@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
@@ -58,11 +58,51 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
+    // variants 2/3: the A operand lives in TMEM (lane = row, 32-bit column c = K elements 2c | 2c+1), written by tcgen05.st
+    const uint32_t tmem_a = tmem + 256;
+    if (variant >= 2) {
+        for (int c0 = 0; c0 < K / 2; c0 += 8) {
+            uint32_t v[8];
+            for (int i = 0; i < 8; ++i) {
+                uint32_t e0 = reinterpret_cast<const uint16_t*>(A)[(size_t)tid * K + 2 * (c0 + i)];
+                uint32_t e1 = reinterpret_cast<const uint16_t*>(A)[(size_t)tid * K + 2 * (c0 + i) + 1];
+                v[i] = variant == 2 ? (e0 | (e1 << 16)) : (e1 | (e0 << 16));
+            }
+            uint32_t taddr = tmem_a + ((uint32_t)(warp * 32) << 16) + c0;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t strideA = 128 * 16, strideB = (uint32_t)N * 16;   // K-chunk stride in bytes
     uint32_t phase = 0;
     long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep) {
+        if (variant == 4) {
+            // warp-uniform issue: all 32 lanes of warp 0 run the loop, one elected lane executes the MMA
+            if (warp == 0) {
+                uint32_t elected;
+                asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+                uint64_t da = make_desc(smem_u32(sA), strideA, 128), db = make_desc(smem_u32(sB), strideB, 128);
+                const uint64_t ia = (2 * strideA) >> 4, ib = (2 * strideB) >> 4;
+                const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    if (elected)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     :: "r"(tm), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+                    da += ia; db += ib;
+                }
+                if (elected)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+                __syncwarp();
+            }
+        } else
         if (tid == 0) {
             for (int ks = 0; ks < K / 16; ++ks) {
                 uint64_t da = variant == 0 ? make_desc(smem_u32(sA) + ks * 2 * strideA, strideA, 128)
@@ -70,6 +110,13 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
                 uint64_t db = variant == 0 ? make_desc(smem_u32(sB) + ks * 2 * strideB, strideB, 128)
                                            : make_desc(smem_u32(sB) + ks * 2 * strideB, 128, strideB);
                 uint32_t acc = ks > 0;
+                if (variant >= 2) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                 :: "r"(tmem), "r"(tmem_a + ks * 8), "l"(make_desc(smem_u32(sB) + ks * 2 * strideB, strideB, 128)),
+                                    "r"(idesc), "r"(acc) : "memory");
+                    continue;
+                }
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                              :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
@@ -99,7 +146,7 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
 
 int main(int argc, char** argv)
