@@ -32,11 +32,14 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace sgs_deform {
 
 constexpr int ROWS = 128;            // Gaussians per tile = UMMA M = TMEM lanes
+constexpr int GROUP_THREADS = 256;   // two threads per row
 constexpr int HID = 128;             // hidden width (args.deform_hidden_dim)
 constexpr int K1 = 48;               // padded input width (feature dim + 9 <= 48)
 constexpr int TIME_DIMS = 9;         // get_embedder(4): x + 4 x (sin, cos)
@@ -53,7 +56,11 @@ constexpr int OFF_B2 = OFF_B1 + HID * 4;
 constexpr int OFF_B3 = OFF_B2 + HID * 4;
 constexpr int IMG_BYTES = OFF_B3 + N3_MAX * 4;                 // 115 904
 constexpr int IMG_PAD = (IMG_BYTES + 1023) / 1024 * 1024;      // 116 736
-constexpr int SMEM_BYTES = IMG_PAD + 64;                       // weights + two mbarriers + the TMEM base slot
+constexpr int STAGE_STRIDE = 49;                               // floats per staged SH row (48 + 1: conflict-free by row and by column)
+constexpr int STAGE_BYTES = ROWS * STAGE_STRIDE * 4;           // 25 088 per row group
+constexpr int SMEM_BYTES = IMG_PAD + 2 * STAGE_BYTES + 64;     // weights + SH staging + two mbarriers + the TMEM base slot
+
+constexpr float COST_MOTION = 10.8f, COST_ROT = 13.1f, COST_SHS = 16.3f;   // re-measured below after each kernel change
 
 __host__ __device__ constexpr int n3_real(int mlp) { return mlp == 0 ? 3 : mlp == 1 ? 7 : 48; }
 __host__ __device__ constexpr int n3_pad(int mlp) { return mlp == 2 ? 48 : 16; }
@@ -138,10 +145,10 @@ __device__ __forceinline__ uint32_t umma_idesc(int N) {
 // One layer: D[128 x N] = A[128 x 16*KSTEPS] * B[N x 16*KSTEPS]^T as hi*hi + hi*lo + lo*hi.  Called by ALL lanes of
 // the issuing warp with warp-uniform arguments (descriptor arithmetic stays off the critical path; the probe measured
 // 64 clocks per N = 128 instruction this way against 160 when a single divergent thread builds the operands);
-// `elected` is one lane's predicate.
+// one lane is elected per instruction.
 template <int KSTEPS>
-__device__ __forceinline__ void issue_layer(uint32_t elected, uint32_t acc_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                            uint32_t b_lo, int N, uint32_t mbar) {
+__device__ __forceinline__ void issue_layer(uint32_t acc_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            int N, uint32_t mbar) {
     const uint32_t idesc = umma_idesc(N);
     const uint32_t b_chunk = (uint32_t)N * 16;
     const uint64_t b_step = (uint64_t)((2 * b_chunk) >> 4);
@@ -151,15 +158,21 @@ __device__ __forceinline__ void issue_layer(uint32_t elected, uint32_t acc_tmem,
         uint64_t db = umma_desc(prod == 1 ? b_lo : b_hi, b_chunk);
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-            if (elected)
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)((prod | ks) != 0)) : "memory");
+            // elect.sync and the predicated MMA in one block: ptxas then emits a single predicated UTCHMMA instead of a
+            // per-active-thread serialisation loop around it
+            if ((prod | ks) != 0)
+                asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                             "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;\n\t}"
+                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc) : "memory");
+            else
+                asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                             "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 0;\n\t}"
+                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc) : "memory");
             db += b_step;
         }
     }
-    if (elected)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(mbar) : "memory");
     __syncwarp();
 }
 
@@ -172,15 +185,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
     }
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {    // caller issues tcgen05.wait::ld
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
@@ -188,13 +205,13 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4])
 }
 
 // 8 consecutive K values of this thread's row -> 4 + 4 packed words of the hi / lo bf16 planes of the TMEM A operand
-__device__ __forceinline__ void store_chunk(uint32_t t_hi, uint32_t t_lo, int kc, const float (&v)[8]) {
+__device__ __forceinline__ void store_chunk(uint32_t t_hi, uint32_t t_lo, int kc, const float2 (&v)[4]) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        const float2 hf = __bfloat1622float2(hh);
-        const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        const __nv_bfloat162 hh = __float22bfloat162_rn(v[i]);
+        const float2 lo = __ffma2_rn(__bfloat1622float2(hh), make_float2(-1.f, -1.f), v[i]);     // v - hi, exact
+        const __nv_bfloat162 ll = __float22bfloat162_rn(lo);
         h[i] = *reinterpret_cast<const uint32_t*>(&hh);
         l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
@@ -206,7 +223,7 @@ __device__ __forceinline__ void store_chunk(uint32_t t_hi, uint32_t t_lo, int kc
 __device__ __forceinline__ void publish_operand(int group) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync %0, %1;" :: "r"(1 + group), "r"(ROWS) : "memory");
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + group), "r"(GROUP_THREADS) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
@@ -218,47 +235,75 @@ struct EvalParams {
     const int* index;            // [count] source rows, ascending
     const int* count;
     float *o_means3D, *o_rot, *o_scale, *o_opacity, *o_shs;
+    int ctas_shs, ctas_motion;   // CTA split between the MLPs (the rest work on rot)
+    long long* phase_clocks;     // developer profiling (SGS_DEFORM_PROFILE=1): [3 MLPs][16 phases] clocks of one thread, or NULL
 };
 
-// hidden layer epilogue: accumulator row -> + bias, ReLU -> next layer's A operand (TMEM, bf16 hi / lo planes)
-__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias) {
-#pragma unroll 1
-    for (int c0 = 0; c0 < HID; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_acc + c0, v);
+// hidden layer epilogue for this thread's half of the columns: accumulator row -> + bias, ReLU -> next layer's A
+// operand (TMEM, bf16 hi / lo planes).  The next 16 columns are in flight while the current 16 are converted.
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias,
+                                                int half) {
+    const int cbase = half * (HID / 2);
+    uint32_t r[2][16];
+    tmem_ld16_async(t_acc + cbase, r[0]);
+#pragma unroll
+    for (int it = 0; it < HID / 32; ++it) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (it + 1 < HID / 32) tmem_ld16_async(t_acc + cbase + (it + 1) * 16, r[(it + 1) & 1]);
+        const int c0 = cbase + it * 16;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float x[8];
+            float2 x[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fmaxf(v[h * 8 + i] + bias[c0 + h * 8 + i], 0.f);
+            for (int i = 0; i < 4; ++i) {
+                const float2 b = *reinterpret_cast<const float2*>(bias + c0 + h * 8 + 2 * i);
+                const float2 y = __fadd2_rn(make_float2(__uint_as_float(r[it & 1][h * 8 + 2 * i]),
+                                                        __uint_as_float(r[it & 1][h * 8 + 2 * i + 1])), b);
+                x[i] = make_float2(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f));
+            }
             store_chunk(t_hi, t_lo, c0 / 8 + h, x);
         }
     }
 }
 
-struct RowInputs {        // what one thread needs to build its row of the layer-1 operand
-    int src;
-    float d;              // timestamp - temporal_pos
-    float4 f[8];          // up to 32 plane features
+// Two threads share a row: `half` 0 owns K chunks 0, 2, 4 of the layer-1 operand and the low half of every column
+// range, `half` 1 the others.
+struct RowInputs {
+    float tpos;           // raw load; timestamp - tpos is formed at the point of use so the load never stalls the prefetch
+    float4 f[4];          // this thread's (up to two) 8-wide plane-feature chunks
 };
 
-__device__ __forceinline__ void load_row_inputs(const EvalParams& p, int j, int count, int nf, RowInputs& r) {
-    r.src = __ldg(p.index + (j < count ? j : count - 1));
-    r.d = p.timestamp - __ldg(p.tpos + r.src);
-    const float4* frow = reinterpret_cast<const float4*>(p.feat + (size_t)r.src * p.feat_dim);
+__device__ __forceinline__ void load_row_inputs(const EvalParams& p, int src, int nf, int half, RowInputs& r) {
+    r.tpos = __ldg(p.tpos + src);
+    const float4* frow = reinterpret_cast<const float4*>(p.feat + (size_t)src * p.feat_dim);
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        if (q < 2 * nf) r.f[q] = __ldg(frow + q);
+    for (int c = 0; c < 2; ++c)
+        if (2 * c + half < nf) {
+            r.f[2 * c] = __ldg(frow + 2 * (2 * c + half));
+            r.f[2 * c + 1] = __ldg(frow + 2 * (2 * c + half) + 1);
+        }
 }
 
+__device__ __forceinline__ int load_src(const EvalParams& p, int tile, int tiles, int row, int count) {
+    if (tile >= tiles) return 0;
+    const int j = tile * ROWS + row;
+    return __ldg(p.index + (j < count ? j : count - 1));
+}
+
+#define DF_TICK(i)                                                              \
+    if (prof) {                                                                 \
+        const long long t_ = clock64();                                         \
+        prof[i] += t_ - t_prev;                                                 \
+        t_prev = t_;                                                            \
+    }
+
 template <int MLP>
-__device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img, int group, int worker, int workers,
+__device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img, float* stage, int group, int worker, int workers,
                                         uint32_t tmem_group, uint32_t mbar) {
-    const int tid = threadIdx.x & (ROWS - 1), warp_in_group = tid >> 5;
+    const int gt = threadIdx.x & (GROUP_THREADS - 1);
+    const int row = gt & (ROWS - 1), half = gt >> 7, warp_in_group = gt >> 5;
     const bool issuer = warp_in_group == 0;
-    uint32_t elected = 0;
-    if (issuer) asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
-    const uint32_t lane_base = (uint32_t)(warp_in_group * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp_in_group & 3) * 32) << 16;
     const uint32_t acc_u = tmem_group, hi_u = tmem_group + 128, lo_u = tmem_group + 192;     // lane-0 addresses (MMA)
     const uint32_t t_acc = acc_u + lane_base, t_hi = hi_u + lane_base, t_lo = lo_u + lane_base;
     const uint32_t simg = smem_u32(img);
@@ -270,142 +315,199 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
     const int nf = p.feat_dim >> 3;                    // feature chunks of 8 (feat_dim is a multiple of 8, <= 32)
     constexpr int N3 = n3_pad(MLP);
     uint32_t phase = 0;
+    long long* prof = (p.phase_clocks && worker == 0 && threadIdx.x == 0) ? p.phase_clocks + MLP * 16 : nullptr;
+    long long t_prev = clock64();
 
+    // software pipeline over tiles: source index two tiles ahead, row inputs one tile ahead
     RowInputs cur;
-    if (worker < tiles) load_row_inputs(p, worker * ROWS + tid, count, nf, cur);
+    int src = load_src(p, worker, tiles, row, count);
+    int src_next = load_src(p, worker + workers, tiles, row, count);
+    if (worker < tiles) load_row_inputs(p, src, nf, half, cur);
 
 #pragma unroll 1
     for (int tile = worker; tile < tiles; tile += workers) {
-        const int j = tile * ROWS + tid;
+        const int j = tile * ROWS + row;
         const bool valid = j < count;
-        const int src = cur.src;
+        const float d = p.timestamp - cur.tpos;
 
         // ---- layer-1 operand: [plane feature | time embedding | 0 padding]  (saro_gaussian.py:875-876, :939-969)
         {
+            // [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d]: one accurate sincos, then three
+            // double-angle steps (error <= 1e-6, far below the bf16 hi/lo split of the operand)
             float emb[TIME_DIMS];
-            emb[0] = cur.d;
+            emb[0] = d;
+            sincosf(d, &emb[1], &emb[2]);
 #pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const float x = cur.d * (float)(1 << f);
-                emb[1 + 2 * f] = sinf(x);
-                emb[2 + 2 * f] = cosf(x);
+            for (int f = 1; f < 4; ++f) {
+                emb[1 + 2 * f] = 2.f * emb[2 * f - 1] * emb[2 * f];
+                emb[2 + 2 * f] = 1.f - 2.f * emb[2 * f - 1] * emb[2 * f - 1];
             }
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) {
-                float x[8];
-                if (kc < 4 && kc < nf) {
-                    const float4 u = cur.f[2 * (kc < 4 ? kc : 0)], w = cur.f[2 * (kc < 4 ? kc : 0) + 1];
-                    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
+            for (int c = 0; c < 3; ++c) {
+                const int kc = 2 * c + half;
+                float2 x[4];
+                if (c < 2 && kc < nf) {
+                    const float4 u = cur.f[2 * (c < 2 ? c : 0)], w = cur.f[2 * (c < 2 ? c : 0) + 1];
+                    x[0] = make_float2(u.x, u.y); x[1] = make_float2(u.z, u.w);
+                    x[2] = make_float2(w.x, w.y); x[3] = make_float2(w.z, w.w);
                 } else if (kc == nf) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = emb[i];
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(emb[2 * i], emb[2 * i + 1]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = 0.f;
-                    if (kc == nf + 1) x[0] = emb[8];
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(0.f, 0.f);
+                    if (kc == nf + 1) x[0].x = emb[8];
                 }
                 store_chunk(t_hi, t_lo, kc, x);
             }
         }
+        DF_TICK(0)
         publish_operand(group);
-        if (issuer) issue_layer<K1 / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W1HI, simg + OFF_W1LO, HID, mbar);
+        DF_TICK(1)
+        if (issuer) issue_layer<K1 / 16>(acc_u, hi_u, lo_u, simg + OFF_W1HI, simg + OFF_W1LO, HID, mbar);
+        DF_TICK(2)
 
         // ---- while the tensor core works: next tile's inputs and this tile's residual bases (consumed much later)
         RowInputs nxt = cur;
-        if (tile + workers < tiles) load_row_inputs(p, (tile + workers) * ROWS + tid, count, nf, nxt);
-        float base[MLP == 2 ? 48 : 8];
+        if (tile + workers < tiles) load_row_inputs(p, src_next, nf, half, nxt);
+        const int src_next2 = load_src(p, tile + 2 * workers, tiles, row, count);
+        float base[4];
+        float life = 1.f;
         if (MLP == 0) {
+            if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) base[c] = __ldg(p.xyz + (size_t)src * 3 + c);
+                for (int c = 0; c < 3; ++c) base[c] = __ldg(p.xyz + (size_t)src * 3 + c);
+            }
         } else if (MLP == 1) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.rotation) + src);
-            base[0] = q0.x; base[1] = q0.y; base[2] = q0.z; base[3] = q0.w;
+            if (half == 0) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.rotation) + src);
+                base[0] = q0.x; base[1] = q0.y; base[2] = q0.z; base[3] = q0.w;
+            } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) base[4 + c] = __ldg(p.scaling + (size_t)src * 3 + c);
-            base[7] = __ldg(p.opacity + src);
+                for (int c = 0; c < 3; ++c) base[c] = __ldg(p.scaling + (size_t)src * 3 + c);
+                base[3] = __ldg(p.opacity + src);
+                life = __ldg(p.life + src);
+            }
         } else {
+            // the [16][3] SH block of 16 rows per warp, one row per pass: lanes walk the row's 48 contiguous floats
+            // (3 dc + 45 rest), so the gather is coalesced; staged in shared memory until the output epilogue
+            const int sub = warp_in_group >> 2, lane = gt & 31;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) base[c] = __ldg(p.features_dc + (size_t)src * 3 + c);
+            for (int batch = 0; batch < 2; ++batch) {
+                float v0[8], v1[8];
 #pragma unroll
-            for (int c = 0; c < 45; ++c) base[3 + c] = __ldg(p.features_rest + (size_t)src * 45 + c);
-        }
-        float state = 0.f;
-        if (MLP == 1) {                                  // saro_gaussian.py:872-873 (selection re-evaluated, same arithmetic)
-            const float q = cur.d / __ldg(p.life + src);
-            state = expf(-4.f * (q * q));
+                for (int i = 0; i < 8; ++i) {
+                    const int r_src = __shfl_sync(0xffffffffu, src, sub * 16 + batch * 8 + i);
+                    const float* rest = p.features_rest + (size_t)r_src * 45;
+                    v0[i] = __ldg(lane < 3 ? p.features_dc + (size_t)r_src * 3 + lane : rest + (lane - 3));
+                    v1[i] = lane < 16 ? __ldg(rest + 29 + lane) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float* srow = stage + ((warp_in_group & 3) * 32 + sub * 16 + batch * 8 + i) * STAGE_STRIDE;
+                    srow[lane] = v0[i];
+                    if (lane < 16) srow[32 + lane] = v1[i];
+                }
+            }
         }
 
+        DF_TICK(3)
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue(t_acc, t_hi, t_lo, b1);
+        DF_TICK(4)
+        hidden_epilogue(t_acc, t_hi, t_lo, b1, half);
+        DF_TICK(5)
         publish_operand(group);
-        if (issuer) issue_layer<HID / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W2HI, simg + OFF_W2LO, HID, mbar);
+        DF_TICK(6)
+        if (issuer) issue_layer<HID / 16>(acc_u, hi_u, lo_u, simg + OFF_W2HI, simg + OFF_W2LO, HID, mbar);
+        DF_TICK(7)
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue(t_acc, t_hi, t_lo, b2);
+        DF_TICK(8)
+        hidden_epilogue(t_acc, t_hi, t_lo, b2, half);
+        DF_TICK(9)
         publish_operand(group);
-        if (issuer) issue_layer<HID / 16>(elected, acc_u, hi_u, lo_u, simg + OFF_W3HI, simg + OFF_W3LO, N3, mbar);
+        DF_TICK(10)
+        if (issuer) issue_layer<HID / 16>(acc_u, hi_u, lo_u, simg + OFF_W3HI, simg + OFF_W3LO, N3, mbar);
+        DF_TICK(11)
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        DF_TICK(12)
 
         // ---- output epilogue: residual + activation, written in the rasterizer's input layout
         if (MLP == 0) {                                  // means3D = xyz + motion            (:883-885)
-            float r[16];
-            tmem_ld16(t_acc, r);
-            if (valid) {
+            float r[8];
+            tmem_ld8(t_acc, r);
+            if (valid && half == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) p.o_means3D[(size_t)j * 3 + c] = base[c] + (r[c] + b3[c]);
             }
         } else if (MLP == 1) {                           // rotation, scale, opacity         (:889-897, :903-905)
-            float r[16];
-            tmem_ld16(t_acc, r);
-            if (valid) {
+            float r[8];
+            tmem_ld8(t_acc, r);
+            if (valid && half == 0) {
                 const float qx = base[0] + (r[0] + b3[0]), qy = base[1] + (r[1] + b3[1]);
                 const float qz = base[2] + (r[2] + b3[2]), qw = base[3] + (r[3] + b3[3]);
                 const float nrm = fmaxf(sqrtf(qx * qx + qy * qy + qz * qz + qw * qw), 1e-12f);   // F.normalize eps
                 reinterpret_cast<float4*>(p.o_rot)[j] = make_float4(qx / nrm, qy / nrm, qz / nrm, qw / nrm);
+            } else if (valid) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) p.o_scale[(size_t)j * 3 + c] = expf(base[4 + c] + (r[4 + c] + b3[4 + c]));
-                p.o_opacity[j] = (1.f / (1.f + expf(-base[7]))) * state;
+                for (int c = 0; c < 3; ++c) p.o_scale[(size_t)j * 3 + c] = expf(base[c] + (r[4 + c] + b3[4 + c]));
+                const float q = d / life;                                    // :872-873, same arithmetic as the selection
+                p.o_opacity[j] = (1.f / (1.f + expf(-base[3]))) * expf(-4.f * (q * q));
             }
         } else {                                         // shs = cat(dc, rest) + residual   (:911-915)
+            float* mine = stage + row * STAGE_STRIDE + half * 24;
 #pragma unroll
-            for (int c0 = 0; c0 < 48; c0 += 16) {
-                float r[16];
-                tmem_ld16(t_acc + c0, r);
-                if (valid) {
-                    float4* out = reinterpret_cast<float4*>(p.o_shs + (size_t)j * 48 + c0);
+            for (int c0 = 0; c0 < 24; c0 += 8) {
+                float r[8];
+                tmem_ld8(t_acc + half * 24 + c0, r);
+                const float* bb = b3 + half * 24 + c0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        out[i] = make_float4(base[c0 + 4 * i] + (r[4 * i] + b3[c0 + 4 * i]),
-                                             base[c0 + 4 * i + 1] + (r[4 * i + 1] + b3[c0 + 4 * i + 1]),
-                                             base[c0 + 4 * i + 2] + (r[4 * i + 2] + b3[c0 + 4 * i + 2]),
-                                             base[c0 + 4 * i + 3] + (r[4 * i + 3] + b3[c0 + 4 * i + 3]));
-                }
+                for (int i = 0; i < 8; ++i) mine[c0 + i] += r[i] + bb[i];
+            }
+            asm volatile("bar.sync %0, %1;" :: "r"(1 + group), "r"(GROUP_THREADS) : "memory");
+            // the tile's 128 x 48 outputs are one contiguous block: coalesced float4 stores
+            float4* out = reinterpret_cast<float4*>(p.o_shs + (size_t)tile * ROWS * 48);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int e4 = gt + k * GROUP_THREADS;
+                const int o_row = (e4 * 4) / 48, c = (e4 * 4) % 48;
+                const float* sp = stage + o_row * STAGE_STRIDE + c;
+                if (tile * ROWS + o_row < count) out[e4] = make_float4(sp[0], sp[1], sp[2], sp[3]);
             }
         }
         cur = nxt;
+        src = src_next;
+        src_next = src_next2;
+        DF_TICK(13)
+        if (prof) prof[15] += 1;
     }
 }
 
-// 256 threads = two independent row groups of 128 that share one MLP's resident weights: while one group's layer is
-// in the tensor core the other group runs its epilogue, so the chain latency of one tile hides behind the other's.
-__global__ void __launch_bounds__(2 * ROWS, 1) deform_mlp_kernel(const EvalParams p) {
+// 512 threads = two independent row groups (128 rows each, two threads per row) that share one MLP's resident
+// weights: while one group's layer is in the tensor core the other group runs its epilogue, so the chain latency of
+// one tile hides behind the other's.
+__global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_mlp_kernel(const EvalParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* img = smem;
-    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + IMG_PAD);          // one per group
+    float* stage_all = reinterpret_cast<float*>(smem + IMG_PAD);
+    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + IMG_PAD + 2 * STAGE_BYTES);          // one per group
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5, group = tid >> 7;
-    const int mlp = 2 - (int)(blockIdx.x % 3);                   // block 0 -> shs (the most expensive of the three)
-    const int ctas = ((int)gridDim.x - (int)(blockIdx.x % 3) + 2) / 3;       // CTAs working on this MLP
-    const int worker = (int)(blockIdx.x / 3) * 2 + group;
+    const int tid = threadIdx.x, warp = tid >> 5, group = tid / GROUP_THREADS;
+    // CTAs are split between the three MLPs in proportion to their cost per tile (shs first: it is the longest)
+    int mlp = 2, first = 0, ctas = p.ctas_shs;
+    if ((int)blockIdx.x >= p.ctas_shs + p.ctas_motion) { mlp = 1; first = p.ctas_shs + p.ctas_motion; ctas = (int)gridDim.x - first; }
+    else if ((int)blockIdx.x >= p.ctas_shs) { mlp = 0; first = p.ctas_shs; ctas = p.ctas_motion; }
+    const int worker = ((int)blockIdx.x - first) * 2 + group;
     const int workers = ctas * 2;
+    float* stage = stage_all + group * (STAGE_BYTES / 4);
 
     {   // resident weights: linear copy of this MLP's packed image
         const uint4* src = reinterpret_cast<const uint4*>(p.packed + (size_t)mlp * IMG_BYTES);
         uint4* dst = reinterpret_cast<uint4*>(img);
-        for (int i = tid; i < IMG_BYTES / 16; i += 2 * ROWS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < IMG_BYTES / 16; i += 2 * GROUP_THREADS) dst[i] = __ldg(src + i);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
@@ -424,9 +526,9 @@ __global__ void __launch_bounds__(2 * ROWS, 1) deform_mlp_kernel(const EvalParam
     const uint32_t tmem_group = tmem + (uint32_t)group * 256;    // acc [0,128) | operand hi [128,192) | operand lo [192,256)
     const uint32_t mbar = smem_u32(mbar_p + group);
 
-    if (mlp == 0) run_mlp<0>(p, img, group, worker, workers, tmem_group, mbar);
-    else if (mlp == 1) run_mlp<1>(p, img, group, worker, workers, tmem_group, mbar);
-    else run_mlp<2>(p, img, group, worker, workers, tmem_group, mbar);
+    if (mlp == 0) run_mlp<0>(p, img, stage, group, worker, workers, tmem_group, mbar);
+    else if (mlp == 1) run_mlp<1>(p, img, stage, group, worker, workers, tmem_group, mbar);
+    else run_mlp<2>(p, img, stage, group, worker, workers, tmem_group, mbar);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -521,8 +623,36 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
     const int tiles_max = (N + ROWS - 1) / ROWS;
     int grid = g_sm_count > 0 ? g_sm_count : 148;
     if (grid > 3 * ((tiles_max + 1) / 2)) grid = 3 * ((tiles_max + 1) / 2);
-    deform_mlp_kernel<<<grid, 2 * ROWS, SMEM_BYTES, s>>>(p);
+    // measured clocks per tile (SGS_DEFORM_PROFILE=1): motion : rot : shs = COST_MOTION : COST_ROT : COST_SHS
+    p.ctas_shs = (int)(grid * (COST_SHS / (COST_SHS + COST_MOTION + COST_ROT)) + 0.5f);
+    p.ctas_motion = (int)(grid * (COST_MOTION / (COST_SHS + COST_MOTION + COST_ROT)) + 0.5f);
+    if (p.ctas_shs < 1) p.ctas_shs = 1;
+    if (p.ctas_motion < 1) p.ctas_motion = 1;
+    while (p.ctas_shs + p.ctas_motion >= grid) { if (p.ctas_shs > 1) --p.ctas_shs; else --p.ctas_motion; }
+    static const bool profile = getenv("SGS_DEFORM_PROFILE") != nullptr;
+    static long long* d_prof = nullptr;
+    p.phase_clocks = nullptr;
+    if (profile) {
+        if (!d_prof && cudaMalloc(&d_prof, 48 * sizeof(long long)) != cudaSuccess) return SGS_ERR_ALLOC;
+        cudaMemsetAsync(d_prof, 0, 48 * sizeof(long long), s);
+        p.phase_clocks = d_prof;
+    }
+    deform_mlp_kernel<<<grid, 2 * GROUP_THREADS, SMEM_BYTES, s>>>(p);
     if (cudaGetLastError() != cudaSuccess) return SGS_ERR_CUDA;
+    if (profile) {
+        long long h[48];
+        cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        static const char* names[14] = {"build", "publish1", "issue1", "prefetch", "wait1", "epi1", "publish2", "issue2", "wait2",
+                                        "epi2", "publish3", "issue3", "wait3", "final"};
+        for (int m = 0; m < 3; ++m) {
+            const double tiles = (double)(h[m * 16 + 15] > 0 ? h[m * 16 + 15] : 1);
+            fprintf(stderr, "[sgs_deform profile] mlp %d, %lld tiles, clocks/tile:", m, h[m * 16 + 15]);
+            double tot = 0;
+            for (int i = 0; i < 14; ++i) { fprintf(stderr, " %s %.0f", names[i], h[m * 16 + i] / tiles); tot += h[m * 16 + i] / tiles; }
+            fprintf(stderr, " | total %.0f\n", tot);
+        }
+    }
     // the host needs the number of selected Gaussians to shape the rasterizer call; it is ready as soon as the
     // selection pass is, while the MLP kernel keeps running
     if (cudaEventSynchronize(g_count_ready) != cudaSuccess) return SGS_ERR_CUDA;

@@ -60,13 +60,13 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
 
     // variants 2/3: the A operand lives in TMEM (lane = row, 32-bit column c = K elements 2c | 2c+1), written by tcgen05.st
     const uint32_t tmem_a = tmem + 256;
-    if (variant >= 2) {
+    if (variant == 2 || variant == 3 || variant == 5) {
         for (int c0 = 0; c0 < K / 2; c0 += 8) {
             uint32_t v[8];
             for (int i = 0; i < 8; ++i) {
                 uint32_t e0 = reinterpret_cast<const uint16_t*>(A)[(size_t)tid * K + 2 * (c0 + i)];
                 uint32_t e1 = reinterpret_cast<const uint16_t*>(A)[(size_t)tid * K + 2 * (c0 + i) + 1];
-                v[i] = variant == 2 ? (e0 | (e1 << 16)) : (e1 | (e0 << 16));
+                v[i] = variant != 3 ? (e0 | (e1 << 16)) : (e1 | (e0 << 16));
             }
             uint32_t taddr = tmem_a + ((uint32_t)(warp * 32) << 16) + c0;
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
     uint32_t phase = 0;
     long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep) {
-        if (variant == 4) {
+        if (variant == 4 || variant == 5) {
             // warp-uniform issue: all 32 lanes of warp 0 run the loop, one elected lane executes the MMA
             if (warp == 0) {
                 uint32_t elected;
@@ -92,7 +92,11 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
                 const uint64_t ia = (2 * strideA) >> 4, ib = (2 * strideB) >> 4;
                 const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
                 for (int ks = 0; ks < K / 16; ++ks) {
-                    if (elected)
+                    if (elected && variant == 5)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                     :: "r"(tm), "r"(tm + 256 + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+                    else if (elected)
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                                      :: "r"(tm), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(128) umma_probe(const __nv_bfloat16* __restric
                 uint64_t db = variant == 0 ? make_desc(smem_u32(sB) + ks * 2 * strideB, strideB, 128)
                                            : make_desc(smem_u32(sB) + ks * 2 * strideB, 128, strideB);
                 uint32_t acc = ks > 0;
-                if (variant >= 2) {
+                if (variant == 2 || variant == 3) {
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                                  :: "r"(tmem), "r"(tmem_a + ks * 8), "l"(make_desc(smem_u32(sB) + ks * 2 * strideB, strideB, 128)),
