@@ -180,6 +180,22 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
                         const void* packed, void* workspace, size_t workspace_bytes, float* out_means3D,
                         float* out_rotations, float* out_scales, float* out_opacity, float* out_shs, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Densification statistics of one training iteration — replaces the per-view lists and
+ * the batch reduction of the reference's train.py:192-218 and :281-292 (with scene/saro_gaussian.py:745-747).
+ *
+ * sgs_densify_add_view: after one view's backward pass: grad_sum[i] += |dL_dmeans2D[i][0:2]|, vis_count[i] += radii[i] > 0,
+ *   radii_max[i] = max(radii_max[i], radii[i]).  dL_dmeans2D is the rasterizer's [P][3] means2D gradient, radii its
+ *   int32 [P] output; the three running buffers ([P] float / int32 / int32, device) start at zero each iteration.
+ * sgs_densify_commit: where vis_count > 0: max_radii2D = max(max_radii2D, radii_max); xyz_gradient_accum += grad_sum /
+ *   vis_count; denom += 1   (all three are the model's float32 [P] statistics, updated in place).
+ * Data-parallel training runs sgs_densify_add_view on each rank's view, all-reduces grad_sum (SUM), vis_count (SUM) and
+ * radii_max (MAX), then commits on every rank.  Both return 0 or a negative error code. */
+int sgs_densify_add_view(int P, const float* dL_dmeans2D, const int* radii, float* grad_sum, int* vis_count, int* radii_max,
+                         void* stream);
+int sgs_densify_commit(int P, const float* grad_sum, const int* vis_count, const int* radii_max, float* max_radii2D,
+                       float* xyz_gradient_accum, float* denom, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ SOURCES = [
     "sgs_preprocess_bwd.cu",
     "sgs_loss.cu",
     "sgs_deform.cu",
+    "sgs_densify.cu",
 ]
 HEADERS = ["sgs_common.cuh", os.path.join("..", "..", "include", "saro_gs_b200.h")]
 
