@@ -322,6 +322,7 @@ def run_native_or_ref(args, impl):
         if rank == 0:
             line["loss_path"] = loss_path_timing(dev, H, W)
             line["deform_path"] = deform_path_timing(dev)
+            line["densify_path"] = densify_path_timing(dev)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
     if rank == 0:
@@ -413,6 +414,63 @@ def deform_path_timing(dev, iters=15):
         out["test_time_frame_ms"]["reference_ops_and_rasterizer"] = frame_ref
         out["test_time_frame_ms"]["speedup"] = frame_ref / frame_native
     return out
+
+
+def densify_path_timing(dev, P=300_000, V=4, iters=20):
+    """SURVEY.md section 8(f) rank 4 (the part that consumes the rasterizer's outputs): densification statistics of a
+    V-view batch, fused kernels vs the reference's list / stack / boolean-index PyTorch ops (train.py:211-215,
+    :281-291).  CUDA events, inputs resident."""
+    import types
+    from saro_gs_b200.densify import BatchDensifyStats
+    g = torch.Generator().manual_seed(0)
+    grads = [(torch.randn(P, 3, generator=g) * 1e-4).to(dev) for _ in range(V)]
+    radii = [torch.where(torch.rand(P, generator=g) < 0.3, 0, torch.randint(1, 60, (P,), generator=g)).to(torch.int32).to(dev)
+             for _ in range(V)]
+
+    def model():
+        return types.SimpleNamespace(max_radii2D=torch.zeros(P, device=dev), xyz_gradient_accum=torch.zeros(P, 1, device=dev),
+                                     denom=torch.zeros(P, 1, device=dev))
+
+    def fused(m, stats):
+        stats.reset()
+        for a, b in zip(grads, radii):
+            stats.add_view(a, b)
+        stats.commit(m)
+
+    def torch_ops(m, _):
+        batch_point_grad, batch_radii, batch_vis = [], [], []
+        for a, b in zip(grads, radii):
+            batch_point_grad.append(torch.norm(a[:, :2], dim=-1))
+            batch_radii.append(b)
+            batch_vis.append(b > 0)
+        visibility_count = torch.stack(batch_vis, 1).sum(1)
+        visibility_filter = visibility_count > 0
+        r = torch.stack(batch_radii, 1).max(1)[0]
+        gr = torch.stack(batch_point_grad, 1).sum(1)
+        gr[visibility_filter] = gr[visibility_filter] / visibility_count[visibility_filter]
+        gr = gr.unsqueeze(1)
+        m.max_radii2D[visibility_filter] = torch.max(m.max_radii2D[visibility_filter], r[visibility_filter])
+        m.xyz_gradient_accum[visibility_filter] += gr[visibility_filter]
+        m.denom[visibility_filter] += 1
+
+    def run(fn):
+        m, stats, ms = model(), BatchDensifyStats(P, dev), []
+        for i in range(iters + 3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(m, stats)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        return sum(ms) / len(ms), m
+
+    a, ma = run(fused)
+    b, mb = run(torch_ops)
+    agree = torch.equal(ma.max_radii2D, mb.max_radii2D) and torch.equal(ma.denom, mb.denom) and \
+        torch.allclose(ma.xyz_gradient_accum, mb.xyz_gradient_accum, rtol=1e-5)
+    return {"what": "densification statistics, %d views x %d Gaussians (8 launches: launch-latency bound)" % (V, P),
+            "fused_ms": a, "pytorch_ops_ms": b, "speedup": b / a, "agree": bool(agree)}
 
 
 def cpu_baseline(precision="f32"):

@@ -25,3 +25,22 @@ for (P, seed, kw) in [(3000, 0, dict(width=160, height=112, fx=120.0, log_scale_
     loss.backward()
     torch.cuda.synchronize()
     print("ok", P, float(loss), int((radii > 0).sum()), float(leaves["means3D"].grad.abs().sum()))
+
+# deformation hand-off (tcgen05 / TMEM kernel) and densification statistics on small clouds
+from saro_gs_b200 import deformation
+from saro_gs_b200.densify import BatchDensifyStats
+import types
+for P in (700, 129):
+    scene, _ = synthetic.small_scene(P=P, seed=3)
+    pc = synthetic.model_to(synthetic.dynamic_model(scene, feat_dim=32 if P == 700 else 16), dev)
+    with torch.no_grad():
+        out = deformation.get_deformation_eval(pc, 0.4)
+    torch.cuda.synchronize()
+    print("deform ok", P, out[0].shape[0], float(out[4].abs().sum()))
+    stats = BatchDensifyStats(P, dev)
+    stats.add_view(torch.randn(P, 3, device=dev), torch.randint(0, 9, (P,), device=dev, dtype=torch.int32))
+    m = types.SimpleNamespace(max_radii2D=torch.zeros(P, device=dev), xyz_gradient_accum=torch.zeros(P, 1, device=dev),
+                              denom=torch.zeros(P, 1, device=dev))
+    stats.commit(m)
+    torch.cuda.synchronize()
+    print("densify ok", P, float(m.denom.sum()))
