@@ -49,9 +49,8 @@ constexpr int OFF_W1HI = 0;
 constexpr int OFF_W1LO = OFF_W1HI + K1 * HID * 2;
 constexpr int OFF_W2HI = OFF_W1LO + K1 * HID * 2;
 constexpr int OFF_W2LO = OFF_W2HI + HID * HID * 2;
-constexpr int OFF_W3HI = OFF_W2LO + HID * HID * 2;
-constexpr int OFF_W3LO = OFF_W3HI + HID * N3_MAX * 2;
-constexpr int OFF_B1 = OFF_W3LO + HID * N3_MAX * 2;
+constexpr int OFF_W3 = OFF_W2LO + HID * HID * 2;               // [hi rows ; lo rows] stacked along N
+constexpr int OFF_B1 = OFF_W3 + 2 * HID * N3_MAX * 2;
 constexpr int OFF_B2 = OFF_B1 + HID * 4;
 constexpr int OFF_B3 = OFF_B2 + HID * 4;
 constexpr int IMG_BYTES = OFF_B3 + N3_MAX * 4;                 // 115 904
@@ -60,7 +59,7 @@ constexpr int STAGE_STRIDE = 49;                               // floats per sta
 constexpr int STAGE_BYTES = ROWS * STAGE_STRIDE * 4;           // 25 088 per row group
 constexpr int SMEM_BYTES = IMG_PAD + 2 * STAGE_BYTES + 64;     // weights + SH staging + two mbarriers + the TMEM base slot
 
-constexpr float COST_MOTION = 10.8f, COST_ROT = 13.1f, COST_SHS = 16.3f;   // re-measured below after each kernel change
+constexpr float COST_MOTION = 10.7f, COST_ROT = 11.9f, COST_SHS = 15.4f;   // re-measured below after each kernel change
 
 __host__ __device__ constexpr int n3_real(int mlp) { return mlp == 0 ? 3 : mlp == 1 ? 7 : 48; }
 __host__ __device__ constexpr int n3_pad(int mlp) { return mlp == 2 ? 48 : 16; }
@@ -85,7 +84,7 @@ __global__ void pack_mlp_kernel(int mlp, int in_dim, const float* __restrict__ W
                                 const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
                                 const float* __restrict__ b3, uint8_t* __restrict__ img) {
     const int n3r = n3_real(mlp), n3p = n3_pad(mlp);
-    const int total = HID * K1 + HID * HID + n3p * HID + 2 * HID + N3_MAX;
+    const int total = HID * K1 + HID * HID + 2 * n3p * HID + 2 * HID + N3_MAX;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         int i = e;
         if (i < HID * K1) {                         // W1 [128][in_dim] -> [128][K1]
@@ -108,16 +107,15 @@ __global__ void pack_mlp_kernel(int mlp, int in_dim, const float* __restrict__ W
             continue;
         }
         i -= HID * HID;
-        if (i < n3p * HID) {
-            const int n = i / HID, k = i % HID;
+        if (i < 2 * n3p * HID) {                    // W3: hi and lo planes stacked along N -> one [2 n3][128] operand
+            const int ns = i / HID, k = i % HID, n = ns % n3p;
             __nv_bfloat16 hi, lo;
             split_bf16(n < n3r ? W3[n * HID + k] : 0.f, hi, lo);
-            const int off = (k / 8) * (n3p * 16) + n * 16 + (k % 8) * 2;
-            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3HI + off) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3LO + off) = lo;
+            const int off = (k / 8) * (2 * n3p * 16) + ns * 16 + (k % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3 + off) = ns < n3p ? hi : lo;
             continue;
         }
-        i -= n3p * HID;
+        i -= 2 * n3p * HID;
         if (i < HID) { reinterpret_cast<float*>(img + OFF_B1)[i] = b1[i]; continue; }
         i -= HID;
         if (i < HID) { reinterpret_cast<float*>(img + OFF_B2)[i] = b2[i]; continue; }
@@ -160,6 +158,37 @@ __device__ __forceinline__ void issue_layer(uint32_t acc_tmem, uint32_t a_hi, ui
         for (int ks = 0; ks < KSTEPS; ++ks) {
             // elect.sync and the predicated MMA in one block: ptxas then emits a single predicated UTCHMMA instead of a
             // per-active-thread serialisation loop around it
+            if ((prod | ks) != 0)
+                asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                             "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;\n\t}"
+                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc) : "memory");
+            else
+                asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                             "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 0;\n\t}"
+                             :: "r"(acc_tmem), "r"(a + ks * 8), "l"(db), "r"(idesc) : "memory");
+            db += b_step;
+        }
+    }
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(mbar) : "memory");
+    __syncwarp();
+}
+
+// Last layer (N3 = 16 or 48 outputs: far below the tensor pipe's appetite, so the instruction count is what costs).
+// W3's hi and lo planes are stacked along N: A_hi x [W_hi ; W_lo] leaves hi*hi in accumulator columns [0, N3) and
+// hi*lo in [N3, 2 N3) with ONE instruction per K step, A_lo x W_hi accumulates into [0, N3): 16 instructions
+// instead of 24; the output epilogue adds the two column blocks.
+__device__ __forceinline__ void issue_last_layer(uint32_t acc_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b, int N3,
+                                                 uint32_t mbar) {
+    const uint32_t chunk = (uint32_t)(2 * N3) * 16;
+    const uint64_t b_step = (uint64_t)((2 * chunk) >> 4);
+#pragma unroll
+    for (int prod = 0; prod < 2; ++prod) {
+        const uint32_t a = prod ? a_lo : a_hi;
+        const uint32_t idesc = umma_idesc(prod ? N3 : 2 * N3);
+        uint64_t db = umma_desc(b, chunk);
+#pragma unroll
+        for (int ks = 0; ks < HID / 16; ++ks) {
             if ((prod | ks) != 0)
                 asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
                              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;\n\t}"
@@ -368,6 +397,19 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
         DF_TICK(2)
 
         // ---- while the tensor core works: next tile's inputs and this tile's residual bases (consumed much later)
+        float sh0[16], sh1[16];                           // shs class: this warp's 16 rows of the SH block, in flight
+        if (MLP == 2) {
+            // the [16][3] SH block of 16 rows per warp, one row per pass: lanes walk the row's 48 contiguous floats
+            // (3 dc + 45 rest), so the gather is coalesced; all 32 loads are issued before anything waits on them
+            const int sub = warp_in_group >> 2, lane = gt & 31;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r_src = __shfl_sync(0xffffffffu, src, sub * 16 + i);
+                const float* rest = p.features_rest + (size_t)r_src * 45;
+                sh0[i] = __ldg(lane < 3 ? p.features_dc + (size_t)r_src * 3 + lane : rest + (lane - 3));
+                sh1[i] = lane < 16 ? __ldg(rest + 29 + lane) : 0.f;
+            }
+        }
         RowInputs nxt = cur;
         if (tile + workers < tiles) load_row_inputs(p, src_next, nf, half, nxt);
         const int src_next2 = load_src(p, tile + 2 * workers, tiles, row, count);
@@ -389,25 +431,13 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
                 life = __ldg(p.life + src);
             }
         } else {
-            // the [16][3] SH block of 16 rows per warp, one row per pass: lanes walk the row's 48 contiguous floats
-            // (3 dc + 45 rest), so the gather is coalesced; staged in shared memory until the output epilogue
+            // staged in shared memory (49-float row stride) until the output epilogue
             const int sub = warp_in_group >> 2, lane = gt & 31;
 #pragma unroll
-            for (int batch = 0; batch < 2; ++batch) {
-                float v0[8], v1[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r_src = __shfl_sync(0xffffffffu, src, sub * 16 + batch * 8 + i);
-                    const float* rest = p.features_rest + (size_t)r_src * 45;
-                    v0[i] = __ldg(lane < 3 ? p.features_dc + (size_t)r_src * 3 + lane : rest + (lane - 3));
-                    v1[i] = lane < 16 ? __ldg(rest + 29 + lane) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float* srow = stage + ((warp_in_group & 3) * 32 + sub * 16 + batch * 8 + i) * STAGE_STRIDE;
-                    srow[lane] = v0[i];
-                    if (lane < 16) srow[32 + lane] = v1[i];
-                }
+            for (int i = 0; i < 16; ++i) {
+                float* srow = stage + ((warp_in_group & 3) * 32 + sub * 16 + i) * STAGE_STRIDE;
+                srow[lane] = sh0[i];
+                if (lane < 16) srow[32 + lane] = sh1[i];
             }
         }
 
@@ -428,7 +458,7 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
         DF_TICK(9)
         publish_operand(group);
         DF_TICK(10)
-        if (issuer) issue_layer<HID / 16>(acc_u, hi_u, lo_u, simg + OFF_W3HI, simg + OFF_W3LO, N3, mbar);
+        if (issuer) issue_last_layer(acc_u, hi_u, lo_u, simg + OFF_W3, N3, mbar);
         DF_TICK(11)
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -436,15 +466,19 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
 
         // ---- output epilogue: residual + activation, written in the rasterizer's input layout
         if (MLP == 0) {                                  // means3D = xyz + motion            (:883-885)
-            float r[8];
+            float r[8], r2[8];
             tmem_ld8(t_acc, r);
+            tmem_ld8(t_acc + N3, r2);
             if (valid && half == 0) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) p.o_means3D[(size_t)j * 3 + c] = base[c] + (r[c] + b3[c]);
+                for (int c = 0; c < 3; ++c) p.o_means3D[(size_t)j * 3 + c] = base[c] + ((r[c] + r2[c]) + b3[c]);
             }
         } else if (MLP == 1) {                           // rotation, scale, opacity         (:889-897, :903-905)
-            float r[8];
+            float r[8], r2[8];
             tmem_ld8(t_acc, r);
+            tmem_ld8(t_acc + N3, r2);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) r[c] += r2[c];
             if (valid && half == 0) {
                 const float qx = base[0] + (r[0] + b3[0]), qy = base[1] + (r[1] + b3[1]);
                 const float qz = base[2] + (r[2] + b3[2]), qw = base[3] + (r[3] + b3[3]);
@@ -460,11 +494,12 @@ __device__ __forceinline__ void run_mlp(const EvalParams& p, const uint8_t* img,
             float* mine = stage + row * STAGE_STRIDE + half * 24;
 #pragma unroll
             for (int c0 = 0; c0 < 24; c0 += 8) {
-                float r[8];
+                float r[8], r2[8];
                 tmem_ld8(t_acc + half * 24 + c0, r);
+                tmem_ld8(t_acc + N3 + half * 24 + c0, r2);
                 const float* bb = b3 + half * 24 + c0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mine[c0 + i] += r[i] + bb[i];
+                for (int i = 0; i < 8; ++i) mine[c0 + i] += (r[i] + r2[i]) + bb[i];
             }
             asm volatile("bar.sync %0, %1;" :: "r"(1 + group), "r"(GROUP_THREADS) : "memory");
             // the tile's 128 x 48 outputs are one contiguous block: coalesced float4 stores
