@@ -16,16 +16,25 @@
 // (renderer/__init__.py:188-203).
 //
 // B200 design.  The three MLPs are GEMM-shaped (145 kFLOP per Gaussian), so they run on the 5th-generation tensor
-// cores:  a CTA owns ONE of the three MLPs for its whole life, keeps that MLP's weights resident in shared memory in
-// the UMMA no-swizzle K-major canonical layout, and walks 128-Gaussian tiles.  Per tile each thread owns one row
-// (= one TMEM lane): it gathers the row's features, writes them to the A-operand buffer, one elected thread issues
-// tcgen05.mma (M = 128, N = 128 | 16 | 48, K = 16 per instruction) with the accumulator in TMEM, and after the
-// tcgen05.commit -> mbarrier hand-shake every thread reads its own accumulator row back with tcgen05.ld, applies
-// bias + ReLU and writes the next layer's A operand in place.  Hidden activations never leave the SM.
-// fp32 fidelity on bf16 tensor cores: every operand x is split as x = hi + lo (two bf16 values, 16 significand bits)
-// and each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation — measured 7e-6 of the output range
-// against float64, 13x inside the 1e-4 parity bar, at 3 MMAs per product instead of the 8x slower fp32 SIMT path.
-// The last layer's epilogue applies the residual add and activations and writes the rasterizer's inputs directly.
+// cores.  Persistent kernel, one 512-thread CTA per SM:
+//   * a CTA owns ONE of the three MLPs for its whole life and keeps that MLP's weights resident in shared memory
+//     (bf16 hi + lo planes in the UMMA no-swizzle K-major canonical layout, 116 KB); CTAs are split between the MLPs
+//     in proportion to their measured cost per tile;
+//   * two independent row groups of 128 Gaussians (UMMA M = 128 = TMEM lanes), two threads per row.  TMEM is fully
+//     allocated: per group 128 accumulator columns + 64 + 64 columns that hold the A operand (hi / lo bf16 planes,
+//     written with tcgen05.st).  tcgen05.mma takes A from TMEM and B from shared memory; hidden activations never touch
+//     shared memory or HBM.  While one group's layer is in the tensor core the other group runs its epilogue;
+//   * per tile: each thread builds its share of the layer-1 operand row (plane features + time embedding), the group's
+//     first warp issues the layer (all lanes run the unrolled sequence, one elected lane per tcgen05.mma), and after the
+//     tcgen05.commit -> mbarrier hand-shake every thread reads its half of its accumulator row with tcgen05.ld,
+//     applies bias + ReLU in packed f32x2 and writes the next layer's operand;
+//   * fp32 fidelity on bf16 tensor cores: every operand x is split as x = hi + lo (two bf16 values, 16 significand
+//     bits) and each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation — measured 7e-6 of the output
+//     range against float64, 13x inside the 1e-4 parity bar, at 3 MMAs per product instead of the 8x slower fp32 SIMT
+//     path (plain bf16 gives 4e-3);
+//   * the last layer's epilogue applies the residual add and activations and writes the rasterizer's inputs directly;
+//     the 48-float SH rows are gathered and written back coalesced through a shared staging buffer.
+// Descriptor encodings and the TMEM operand packing were pinned on hardware with tools/microbench/umma_probe.cu.
 #include "../../include/saro_gs_b200.h"
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -59,7 +68,8 @@ constexpr int STAGE_STRIDE = 49;                               // floats per sta
 constexpr int STAGE_BYTES = ROWS * STAGE_STRIDE * 4;           // 25 088 per row group
 constexpr int SMEM_BYTES = IMG_PAD + 2 * STAGE_BYTES + 64;     // weights + SH staging + two mbarriers + the TMEM base slot
 
-constexpr float COST_MOTION = 10.7f, COST_ROT = 11.9f, COST_SHS = 15.4f;   // re-measured below after each kernel change
+// measured k-clocks per tile of each MLP class (SGS_DEFORM_PROFILE=1); drives the CTA split
+constexpr float COST_MOTION = 10.7f, COST_ROT = 11.9f, COST_SHS = 15.4f;
 
 __host__ __device__ constexpr int n3_real(int mlp) { return mlp == 0 ? 3 : mlp == 1 ? 7 : 48; }
 __host__ __device__ constexpr int n3_pad(int mlp) { return mlp == 2 ? 48 : 16; }
