@@ -14,7 +14,11 @@ SRC = os.path.join(ROOT, "tests", "abi", "abi_driver.c")
 EXE = os.path.join(ROOT, "tests", "abi", "_build", "abi_driver")
 
 
-def build_driver():
+SRC_DEFORM = os.path.join(ROOT, "tests", "abi", "deform_driver.c")
+EXE_DEFORM = os.path.join(ROOT, "tests", "abi", "_build", "deform_driver")
+
+
+def build_driver(SRC=SRC, EXE=EXE):
     from saro_gs_b200 import build as native_build
     lib = native_build.build(verbose=False)
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
@@ -31,8 +35,9 @@ def build_driver():
 
 
 def test_c_driver_compiles_against_the_header():
-    """CPU: the header is valid C99 and every entry point the driver uses links against the built library."""
+    """CPU: the header is valid C99 and every entry point the drivers use links against the built library."""
     assert os.path.exists(build_driver())
+    assert os.path.exists(build_driver(SRC_DEFORM, EXE_DEFORM))
 
 
 @pytest.mark.gpu
@@ -85,3 +90,58 @@ def test_c_driver_matches_python_host_layer(tmp_path):
     for k, v in c.items():
         ref = grads[k].grad.cpu().numpy().ravel()
         assert np.abs(v - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-12, k     # float atomics: order-dependent
+
+
+@pytest.mark.gpu
+def test_c_driver_widened_rows_match_python_host_layer(tmp_path):
+    """Deformation hand-off and densification statistics from plain C == through the Python host layer (bit-equal:
+    both are deterministic)."""
+    import types
+    from saro_gs_b200 import deformation, synthetic
+    from saro_gs_b200.densify import BatchDensifyStats
+    exe = build_driver(SRC_DEFORM, EXE_DEFORM)
+    dev = torch.device("cuda:0")
+    scene, _ = synthetic.small_scene(P=1000, seed=9)
+    pc = synthetic.dynamic_model(scene, feat_dim=32, seed=4)
+    N, t = 1000, 0.35
+    g = torch.Generator().manual_seed(2)
+    dm2 = torch.randn(N, 3, generator=g) * 1e-3
+    radii = torch.where(torch.rand(N, generator=g) < 0.3, 0, torch.randint(1, 50, (N,), generator=g)).to(torch.int32)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<2if", N, 32, t))
+        for a in (pc._xyz, pc._rotation, pc._scaling, pc._opacity, pc._features_dc, pc._features_rest, pc.get_temporalpos,
+                  pc._lifespan, pc.hexplane_feature):
+            f.write(a.contiguous().numpy().astype("<f4").tobytes())
+        for m in (pc.motion_mlp, pc.rot_mlp, pc.shs_mlp):
+            for layer in (m[0], m[2], m[4]):
+                f.write(layer.weight.detach().contiguous().numpy().astype("<f4").tobytes())
+                f.write(layer.bias.detach().contiguous().numpy().astype("<f4").tobytes())
+        f.write(dm2.numpy().astype("<f4").tobytes())
+        f.write(radii.numpy().astype("<i4").tobytes())
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    raw = open(fout, "rb").read()
+    S = struct.unpack_from("<q", raw, 0)[0]
+    off = 8
+
+    def take(n):
+        nonlocal off
+        a = np.frombuffer(raw, dtype="<f4", count=n, offset=off)
+        off += a.nbytes
+        return a
+
+    c_out = [take(S * 3), take(S * 4), take(S * 3), take(S), take(S * 48)]
+    c_stats = [take(N), take(N), take(N)]
+    with torch.no_grad():
+        py = deformation.get_deformation_eval(synthetic.model_to(pc, dev), t)
+    assert py[0].shape[0] == S and 0 < S < N
+    for a, b in zip(c_out, py):
+        assert np.array_equal(a, b.cpu().numpy().ravel())
+    stats = BatchDensifyStats(N, dev)
+    stats.add_view(dm2.to(dev), radii.to(dev))
+    m = types.SimpleNamespace(max_radii2D=torch.zeros(N, device=dev), xyz_gradient_accum=torch.zeros(N, 1, device=dev),
+                              denom=torch.zeros(N, 1, device=dev))
+    stats.commit(m)
+    for a, b in zip(c_stats, (m.max_radii2D, m.xyz_gradient_accum, m.denom)):
+        assert np.array_equal(a, b.cpu().numpy().ravel())
