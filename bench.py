@@ -469,7 +469,7 @@ def densify_path_timing(dev, P=300_000, V=4, iters=20):
     b, mb = run(torch_ops)
     agree = torch.equal(ma.max_radii2D, mb.max_radii2D) and torch.equal(ma.denom, mb.denom) and \
         torch.allclose(ma.xyz_gradient_accum, mb.xyz_gradient_accum, rtol=1e-5)
-    return {"what": "densification statistics, %d views x %d Gaussians (8 launches: launch-latency bound)" % (V, P),
+    return {"what": "densification statistics, %d views x %d Gaussians (6 launches: launch-latency bound)" % (V, P),
             "fused_ms": a, "pytorch_ops_ms": b, "speedup": b / a, "agree": bool(agree)}
 
 

@@ -33,15 +33,15 @@ class BatchDensifyStats:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchDensifyStats needs a CUDA device (there is no CPU path)")
-        self.grad_sum = torch.zeros(self.P, dtype=torch.float32, device=self.device)
-        self.vis_count = torch.zeros(self.P, dtype=torch.int32, device=self.device)
-        self.radii_max = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        # one allocation, three [P] views: reset() is a single memset
+        self._buffers = torch.zeros(3, self.P, dtype=torch.int32, device=self.device)
+        self.grad_sum = self._buffers[0].view(torch.float32)
+        self.vis_count = self._buffers[1]
+        self.radii_max = self._buffers[2]
         self.views = 0
 
     def reset(self):
-        self.grad_sum.zero_()
-        self.vis_count.zero_()
-        self.radii_max.zero_()
+        self._buffers.zero_()
         self.views = 0
 
     def add_view(self, viewspace_point_grad, radii):

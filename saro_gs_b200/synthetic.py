@@ -191,9 +191,11 @@ def dynamic_model(scene, feat_dim=32, seed=0, lifespan=(0.15, 1.2), residual_gai
 
 def model_to(pc, device):
     """Move every tensor / module of a dynamic_model() to `device` (returns a new namespace)."""
+    import copy
     import types
     out = types.SimpleNamespace(args=pc.args)
     for k, v in vars(pc).items():
         if k != "args":
-            setattr(out, k, v.to(device))
+            # nn.Module.to() moves in place: copy first so that `pc` keeps its own (CPU) parameters
+            setattr(out, k, copy.deepcopy(v).to(device) if isinstance(v, torch.nn.Module) else v.to(device))
     return out
