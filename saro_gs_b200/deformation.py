@@ -75,10 +75,12 @@ class PackedMLPs:
         self.feat_dim = in_dim - TIME_DIMS
         self.buffer = torch.empty(lib.sgs_deform_packed_bytes(), dtype=torch.uint8, device=dev)
         self.versions = None
+        self._mlps = (motion_mlp, rot_mlp, shs_mlp)     # re-read on every refresh: modules may swap their parameters
         self._sources = params
         self.refresh()
 
     def _current_versions(self):
+        self._sources = [_linears(m) for m in self._mlps]
         return tuple((t.data_ptr(), t._version) for ps in self._sources for t in ps)
 
     def refresh(self):
