@@ -75,13 +75,20 @@ class PackedMLPs:
         self.feat_dim = in_dim - TIME_DIMS
         self.buffer = torch.empty(lib.sgs_deform_packed_bytes(), dtype=torch.uint8, device=dev)
         self.versions = None
-        self._mlps = (motion_mlp, rot_mlp, shs_mlp)     # re-read on every refresh: modules may swap their parameters
+        # modules are re-read on every refresh (they may swap their parameters); plain tuples are fixed
+        self._layers = [None if isinstance(m, (tuple, list)) else [l for l in m if hasattr(l, "weight")]
+                        for m in (motion_mlp, rot_mlp, shs_mlp)]
         self._sources = params
         self.refresh()
 
     def _current_versions(self):
-        self._sources = [_linears(m) for m in self._mlps]
-        return tuple((t.data_ptr(), t._version) for ps in self._sources for t in ps)
+        key = []
+        for i, layers in enumerate(self._layers):
+            if layers is not None:
+                self._sources[i] = tuple(t for l in layers for t in (l.weight, l.bias))
+            for t in self._sources[i]:
+                key.append((t.data_ptr(), t._version))
+        return key
 
     def refresh(self):
         """Re-pack if any weight tensor was written since the last call (optimizer step, load_state_dict)."""
@@ -99,23 +106,20 @@ class PackedMLPs:
         self.versions = cur
 
 
-def deformation_eval(timestamp, xyz, rotation, scaling, opacity, features_dc, features_rest, temporal_pos, lifespan,
-                     hexplane_feature, packed, workspace=None):
-    """Explicit-tensor form.  Returns (means3D [S,3], rotations [S,4], scales [S,3], opacity [S,1], shs [S,16,3])
-    for the S Gaussians whose survival state exceeds 0.001 at `timestamp`, in source order."""
-    lib = _lib.load()
+def _validate_inputs(packed, xyz, rotation, scaling, opacity, features_dc, features_rest, temporal_pos, lifespan,
+                     hexplane_feature):
     n = xyz.shape[0]
-    xyz = _check(xyz, "xyz", [(3,)], n)
-    rotation = _check(rotation, "rotation", [(4,)], n)
-    scaling = _check(scaling, "scaling", [(3,)], n)
-    opacity = _check(opacity, "opacity", [(1,), ()], n)
-    features_dc = _check(features_dc, "features_dc", [(1, 3), (3,)], n)
-    features_rest = _check(features_rest, "features_rest", [(15, 3), (45,)], n)
-    temporal_pos = _check(temporal_pos, "temporal_pos", [(1,), ()], n)
-    lifespan = _check(lifespan, "lifespan", [(1,), ()], n)
-    hexplane_feature = _check(hexplane_feature, "hexplane_feature", [(packed.feat_dim,)], n)
+    return n, (_check(xyz, "xyz", [(3,)], n), _check(rotation, "rotation", [(4,)], n), _check(scaling, "scaling", [(3,)], n),
+               _check(opacity, "opacity", [(1,), ()], n), _check(features_dc, "features_dc", [(1, 3), (3,)], n),
+               _check(features_rest, "features_rest", [(15, 3), (45,)], n),
+               _check(temporal_pos, "temporal_pos", [(1,), ()], n), _check(lifespan, "lifespan", [(1,), ()], n),
+               _check(hexplane_feature, "hexplane_feature", [(packed.feat_dim,)], n))
+
+
+def _run(timestamp, n, inputs, packed, workspace):
+    lib = _lib.load()
     packed.refresh()
-    dev = xyz.device
+    dev = inputs[0].device
     opts = dict(dtype=torch.float32, device=dev)
     means3D = torch.empty((n, 3), **opts)
     rot = torch.empty((n, 4), **opts)
@@ -129,14 +133,22 @@ def deformation_eval(timestamp, xyz, rotation, scaling, opacity, features_dc, fe
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        sel = lib.sgs_deform_eval(n, packed.feat_dim, float(timestamp), _ptr(xyz), _ptr(rotation), _ptr(scaling),
-                                  _ptr(opacity), _ptr(features_dc), _ptr(features_rest), _ptr(temporal_pos),
-                                  _ptr(lifespan), _ptr(hexplane_feature), _ptr(packed.buffer), _ptr(workspace),
-                                  workspace.numel(), _ptr(means3D), _ptr(rot), _ptr(scale), _ptr(opa), _ptr(shs), stream)
+        sel = lib.sgs_deform_eval(n, packed.feat_dim, float(timestamp), *[t.data_ptr() for t in inputs], _ptr(packed.buffer),
+                                  _ptr(workspace), workspace.numel(), _ptr(means3D), _ptr(rot), _ptr(scale), _ptr(opa),
+                                  _ptr(shs), stream)
     if sel < 0:
         raise RuntimeError(f"sgs_deform_eval failed ({sel}): {_lib.last_error()}")
     # `workspace` may be released by the caller right away: the caching allocator is stream-ordered, like any torch op
     return means3D[:sel], rot[:sel], scale[:sel], opa[:sel], shs[:sel]
+
+
+def deformation_eval(timestamp, xyz, rotation, scaling, opacity, features_dc, features_rest, temporal_pos, lifespan,
+                     hexplane_feature, packed, workspace=None):
+    """Explicit-tensor form.  Returns (means3D [S,3], rotations [S,4], scales [S,3], opacity [S,1], shs [S,16,3])
+    for the S Gaussians whose survival state exceeds 0.001 at `timestamp`, in source order."""
+    n, inputs = _validate_inputs(packed, xyz, rotation, scaling, opacity, features_dc, features_rest, temporal_pos, lifespan,
+                                 hexplane_feature)
+    return _run(timestamp, n, inputs, packed, workspace)
 
 
 def get_deformation_eval(self, timestamp, rays=None):
@@ -152,13 +164,20 @@ def get_deformation_eval(self, timestamp, rays=None):
     if cache is None or cache["key"] != key:
         cache = {"key": key, "packed": PackedMLPs(self.motion_mlp, self.rot_mlp, self.shs_mlp), "workspace": None}
         self._sgs_deform_cache = cache
-    n = self._xyz.shape[0]
+    # the model's tensors are validated once and re-used while the model keeps the same tensor objects and storage
+    # (densification, load_state_dict and .to() all replace them)
+    raw = (self._xyz, self._rotation, self._scaling, self._opacity, self._features_dc, self._features_rest,
+           self.get_temporalpos, self._lifespan, self.hexplane_feature)
+    known = cache.get("raw")
+    if known is None or any(a is not b for a, b in zip(raw, known)) or \
+            any(a.data_ptr() != b.data_ptr() for a, b in zip(raw, cache["inputs"])):
+        cache["n"], cache["inputs"] = _validate_inputs(cache["packed"], *raw)
+        cache["raw"] = raw
+    n = cache["n"]
     need = _lib.load().sgs_deform_workspace_bytes(n)
     ws = cache["workspace"]
     if ws is None or ws.numel() < need or ws.device != self._xyz.device:
         ws = cache["workspace"] = torch.empty(need, dtype=torch.uint8, device=self._xyz.device)
     if torch.is_tensor(timestamp):
         timestamp = float(timestamp)
-    return deformation_eval(timestamp, self._xyz, self._rotation, self._scaling, self._opacity, self._features_dc,
-                            self._features_rest, self.get_temporalpos, self._lifespan, self.hexplane_feature,
-                            cache["packed"], workspace=ws)
+    return _run(timestamp, n, cache["inputs"], cache["packed"], ws)
