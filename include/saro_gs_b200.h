@@ -169,7 +169,9 @@ int sgs_l1_dssim_loss_backward(int B, int C, int H, int W, const float* img, con
  *   Outputs have room for N rows; the first `return value` rows are written: out_means3D [.][3], out_rotations [.][4],
  *   out_scales [.][3], out_opacity [.], out_shs [.][48].  `workspace`: sgs_deform_workspace_bytes(N) bytes of device
  *   scratch.  Returns the number of selected Gaussians (the host waits only for the selection pass; the MLP kernel is
- *   still running on `stream` when the call returns) or a negative error code. */
+ *   still running on `stream` when the call returns) or a negative error code.  The call keeps a small pinned
+ *   read-back slot and an event per process: use it from one device per process (the deployment model of this
+ *   library); calls are serialised by an internal mutex. */
 size_t sgs_deform_packed_bytes(void);
 size_t sgs_deform_workspace_bytes(int N);
 int sgs_deform_pack_mlp(int mlp, int in_dim, const float* W1, const float* b1, const float* W2, const float* b2,
