@@ -3,7 +3,12 @@
 Frames/cameras of one scene are independent units: the Gaussians are replicated
 on every rank, rank r renders views r, r+world, ... and the only collective is one all-reduce of a
 small metrics vector at the end (NCCL on GPUs, gloo in the CPU tests).  There is deliberately no
-data-path collective.  The reference has no distributed code at all.
+data-path collective in rendering.  The reference has no distributed code at all.
+
+Data-parallel TRAINING (SURVEY.md §8(e) "training extension", §8(f) rank 4) maps the reference's batch of views
+(train.py:198-226) to one view per rank; its two exchange steps are `allreduce_batch_gradients` below (the
+distributed form of cache_gradient / set_batch_gradient, scene/saro_gaussian.py:224-294) and
+`saro_gs_b200.densify.BatchDensifyStats.all_reduce`.
 """
 from typing import Callable, Iterable, List, Sequence
 
@@ -55,3 +60,47 @@ def mean_metrics(total: torch.Tensor) -> List[float]:
     """[sum..., count] -> per-view means."""
     n = max(float(total[-1]), 1.0)
     return [float(v) / n for v in total[:-1]]
+
+
+def allreduce_batch_gradients(params: Iterable[torch.Tensor], batch: int, group=None, bucket_bytes: int = 64 << 20) -> int:
+    """Distributed form of the reference's batch-gradient cache (scene/saro_gaussian.py:224-294): the reference sums
+    every parameter's gradient over the views of a batch (`cache_gradient`, :224-245) and hands the optimizer
+    `sum * (1 / batch)` (`set_batch_gradient`, :263-294).  With one view per rank the sum over views is a SUM
+    all-reduce; gradients are packed into flat buckets (per dtype, <= bucket_bytes) so that ~25 small tensors and the
+    75 MB of per-Gaussian gradients cost a handful of collectives, then scaled by 1 / batch exactly as the reference
+    does (a multiplication by the reciprocal, not a division).  Parameters without a gradient are skipped on every
+    rank alike.  Returns the number of collectives issued; a no-op (scale only) when not distributed."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    ratio = 1 / batch
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    collectives = 0
+    by_type = {}
+    for g in grads:
+        by_type.setdefault((g.dtype, g.device), []).append(g)
+    for (dtype, device), gs in by_type.items():
+        bucket, size = [], 0
+        buckets = []
+        for g in gs:
+            nbytes = g.numel() * g.element_size()
+            if bucket and size + nbytes > bucket_bytes:
+                buckets.append(bucket)
+                bucket, size = [], 0
+            bucket.append(g)
+            size += nbytes
+        if bucket:
+            buckets.append(bucket)
+        for bucket in buckets:
+            if distributed:
+                flat = torch.cat([g.reshape(-1) for g in bucket])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                collectives += 1
+                flat *= ratio
+                offset = 0
+                for g in bucket:
+                    g.copy_(flat[offset:offset + g.numel()].view_as(g))
+                    offset += g.numel()
+            else:
+                for g in bucket:
+                    g *= ratio
+    return collectives

@@ -5,7 +5,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from saro_gs_b200.sharding import mean_metrics, reduce_metrics, render_shard, shard_indices
+from saro_gs_b200.sharding import (allreduce_batch_gradients, mean_metrics, reduce_metrics, render_shard,
+                                   shard_indices)
 
 
 def test_partition_covers_every_view_once():
@@ -53,3 +54,58 @@ def test_rank_without_views_contributes_zeros():
     res = _run(2, 1, 29543)   # rank 1 has nothing to render
     for _, tot in res:
         assert tot == [0.0, 0.0, 1.0]
+
+
+def _make_params(seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(1000, 3), (1000, 1, 3), (1000, 15, 3), (1000, 1), (128, 41), (128,), (48, 128), (48,)]
+    return [torch.nn.Parameter(torch.zeros(s)) for s in shapes], [torch.randn(s, generator=g) for s in shapes]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params, grads = _make_params(100 + rank)               # this rank's view
+    for p, g in zip(params, grads):
+        p.grad = g.clone()
+    params[3].grad = None                                   # a parameter without gradient is skipped everywhere
+    n = allreduce_batch_gradients(params, batch=world, bucket_bytes=40_000)      # small buckets: several collectives
+    q.put((rank, n, [None if p.grad is None else p.grad.clone() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_equals_the_reference_batch_cache():
+    """One view per rank + allreduce_batch_gradients == cache_gradient over the batch followed by
+    set_batch_gradient (scene/saro_gaussian.py:224-294): sum over views, times 1 / batch."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, 29549, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    views = [_make_params(100 + r)[1] for r in range(world)]
+    ratio = 1 / world
+    for _, n_coll, got in res:
+        assert n_coll > 1
+        for i, g in enumerate(got):
+            if i == 3:
+                assert g is None
+                continue
+            cache = torch.zeros_like(views[0][i])
+            for v in views:
+                cache += v[i].clone()                       # cache_gradient
+            assert torch.equal(g, cache * ratio)            # set_batch_gradient
+
+
+def test_gradient_scale_without_process_group():
+    params, grads = _make_params(7)
+    for p, g in zip(params, grads):
+        p.grad = g.clone()
+    assert allreduce_batch_gradients(params, batch=4) == 0
+    for p, g in zip(params, grads):
+        assert torch.equal(p.grad, g * (1 / 4))
