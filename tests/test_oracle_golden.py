@@ -78,3 +78,22 @@ def test_full_size_config1_tile_counts(oracle_mod):
     c = d["color_crop"].shape[-1]
     assert maxrel(r.color[:, h0:h0 + c, w0:w0 + c], d["color_crop"]) < 1e-4
     assert np.allclose(r.color.sum(axis=(1, 2)), d["color_sum"], rtol=1e-4)
+
+
+def test_f64_oracle_reproduces_full_size_pin(oracle_mod):
+    """configs[1] at FULL size on the CPU (about 6 s on 8 cores): the float64 oracle reproduces its committed pin
+    tests/golden/config2_bwd_f64.npz (made by tests/golden/make_golden_f64.py) — the arbiter the GPU test
+    test_full_size_backward_vs_f64_oracle holds the CUDA gradients to — and the bit-exact tile count of the
+    compiled reference (config2_fwd.npz: num_rendered)."""
+    import torch
+    from saro_gs_b200 import synthetic
+    d = load("config2_bwd_f64")
+    scene, cam = synthetic.config2_scene()
+    r = oracle_mod.forward_scene(scene, cam, torch.zeros(3), precision="f64")
+    assert r.num_rendered == int(d["num_rendered"]) == int(load("config2_fwd")["num_rendered"])
+    assert int((r.radii > 0).sum()) == int(d["visible"])
+    g = r.backward(synthetic.cotangent(cam.height, cam.width))
+    for k in ("means3D", "means2D", "scales", "rotations", "opacities", "shs"):
+        flat = np.asarray(g[k], dtype=np.float64).reshape(-1)
+        assert np.allclose(flat[d[f"idx_{k}"]], d[f"val_{k}"], rtol=1e-9, atol=1e-18), k
+        assert abs(np.linalg.norm(flat) - float(d[f"norm_{k}"])) <= 1e-9 * float(d[f"norm_{k}"]), k
