@@ -19,9 +19,16 @@
  *     (the C form of the reference's std::function<char*(size_t)>,
  *     $R/cuda_rasterizer/rasterizer.h:34-36) and handed back unchanged to sgs_backward;
  *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what the
- *     reference always uses); all work is enqueued on it.  sgs_forward synchronises the
- *     stream once to learn the number of tile instances, exactly where the reference does
- *     ($R/cuda_rasterizer/rasterizer_impl.cu:281-282).
+ *     reference always uses); all work is enqueued on it.  sgs_forward needs the number of
+ *     tile instances on the host like the reference does ($R/cuda_rasterizer/rasterizer_impl.cu:281-282),
+ *     but it does NOT drain the stream for it: the binning buffer is sized from a prediction
+ *     (previous call of the same thread), every kernel of the pass is queued, and only then
+ *     the host waits for the count, which the binning kernel writes into pinned host memory.
+ *     A prediction that turns out too small costs one re-launch of the binning + render
+ *     kernels, never a wrong result;
+ *   - alignment: every pointer must be 4-byte aligned.  16-byte alignment of shs / dL_dsh
+ *     (with M == 16) and of rotations / dL_drot enables 128-bit accesses; otherwise scalar
+ *     paths are taken.  The widened rows state their own (stricter) requirements.
  *
  * Differences from the reference ABI, all additive:
  *   - `stream` and `flags` parameters;
@@ -111,14 +118,24 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
  * Synchronises the stream. */
 int64_t sgs_debug_kept(char* binning_buffer, void* stream);
 
+/* Validation only: force the predicted capacity of the binning buffer (in tile instances) for the following
+ * sgs_forward calls, e.g. 0 to exercise the "prediction too small -> re-launch with the exact size" path;
+ * a negative value restores the predictor. */
+void sgs_debug_set_capacity(int64_t instances);
+
+/* Developer aid: phase timestamps (%globaltimer, ns) of the two persistent binning kernels, written by block 0 into
+ * pinned memory while enabled.  Slots 0.. : depth-sort kernel, 64.. : tile-sort kernel.  out128 (host, 128 entries,
+ * may be NULL) receives the timestamps of the most recent forward call; synchronises the device. */
+int sgs_debug_binning_profile(int enable, uint64_t* out128);
+
 /* Stage profiler (off by default): CUDA events on the launching stream around every stage.
  * sgs_profile_read synchronises the device, returns the summed milliseconds and call counts per
  * stage since the previous read, and the number of hand-written kernels this library launched. */
-#define SGS_STAGE_PREPROCESS_FWD 0   /* per-Gaussian preprocess + exact tile-cull count */
-#define SGS_STAGE_DEPTH_SORT_SCAN 1 /* CUB radix sort of P depth keys + CUB scan */
-#define SGS_STAGE_DUPLICATE 2
-#define SGS_STAGE_TILE_SORT 3       /* CUB radix sort of R tile keys */
-#define SGS_STAGE_TILE_RANGES 4
+#define SGS_STAGE_PREPROCESS_FWD 0   /* per-Gaussian preprocess + exact tile-cull count (+ zeroing of ranges / control block) */
+#define SGS_STAGE_DEPTH_SORT_SCAN 1 /* persistent kernel: radix sort of the P depth keys + scan of the kept tile counts */
+#define SGS_STAGE_DUPLICATE 2       /* unused since round 2 (fused into SGS_STAGE_TILE_SORT) */
+#define SGS_STAGE_TILE_SORT 3       /* persistent kernel: instance generation + radix sort by tile + tile ranges */
+#define SGS_STAGE_TILE_RANGES 4     /* unused since round 2 (fused into SGS_STAGE_TILE_SORT) */
 #define SGS_STAGE_RENDER_FWD 5
 #define SGS_STAGE_BWD_ZERO 6        /* memset of the [P][12] accumulator */
 #define SGS_STAGE_RENDER_BWD 7
@@ -168,7 +185,8 @@ int sgs_l1_dssim_loss_backward(int B, int C, int H, int W, const float* img, con
  *   features_dc [N][3], features_rest [N][45], temporal_pos [N], lifespan [N], hexplane_feature [N][feat_dim].
  *   Outputs have room for N rows; the first `return value` rows are written: out_means3D [.][3], out_rotations [.][4],
  *   out_scales [.][3], out_opacity [.], out_shs [.][48].  `workspace`: sgs_deform_workspace_bytes(N) bytes of device
- *   scratch.  Returns the number of selected Gaussians (the host waits only for the selection pass; the MLP kernel is
+ *   scratch.  rotation, hexplane_feature, out_rotations and out_shs must be 16-byte aligned (128-bit accesses;
+ *   SGS_ERR_INVALID_ARGUMENT otherwise).  Returns the number of selected Gaussians (the host waits only for the selection pass; the MLP kernel is
  *   still running on `stream` when the call returns) or a negative error code.  The call keeps a small pinned
  *   read-back slot and an event per process: use it from one device per process (the deployment model of this
  *   library); calls are serialised by an internal mutex. */

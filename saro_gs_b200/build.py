@@ -25,7 +25,10 @@ SOURCES = [
     "sgs_deform.cu",
     "sgs_densify.cu",
 ]
-HEADERS = ["sgs_common.cuh", os.path.join("..", "..", "include", "saro_gs_b200.h")]
+# every header a translation unit may include feeds the per-object rebuild digest (a stale object after a header edit
+# would let two kernels disagree on a shared record layout)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+    [os.path.join("..", "..", "include", "saro_gs_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -15,6 +15,7 @@
 #include <string>
 #include <chrono>
 #include <cstdlib>
+#include <atomic>
 
 namespace {
 
@@ -34,37 +35,6 @@ int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
         if (_e != cudaSuccess) return fail(SGS_ERR_CUDA, #expr, _e);             \
     } while (0)
 
-// CUB temp-size queries are pure host arithmetic but not free; cache them.
-std::mutex g_cache_mu;
-std::map<int, size_t> g_geom_temp;
-std::map<std::pair<size_t, int>, size_t> g_inst_temp;
-
-size_t geom_temp_bytes(int P) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    auto it = g_geom_temp.find(P);
-    if (it != g_geom_temp.end()) return it->second;
-    size_t b = 0;
-    sgs::binning_geom_temp_bytes(P, &b);
-    if (g_geom_temp.size() > 4096) g_geom_temp.clear();
-    g_geom_temp[P] = b;
-    return b;
-}
-
-size_t inst_temp_bytes(size_t R, int bits) {
-    // CUB's requirement grows monotonically with R: query on R rounded up to 64 Ki so that
-    // frames with slightly different R hit the cache.
-    const size_t Rq = (R + 65535) & ~(size_t)65535;
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    auto key = std::make_pair(Rq, bits);
-    auto it = g_inst_temp.find(key);
-    if (it != g_inst_temp.end()) return it->second;
-    size_t b = 0;
-    sgs::binning_inst_temp_bytes(Rq, bits, &b);
-    if (g_inst_temp.size() > 4096) g_inst_temp.clear();
-    g_inst_temp[key] = b;
-    return b;
-}
-
 sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::GeomState g;
     sgs::carve(chunk, g.depths, P);
@@ -75,13 +45,16 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.clamped, P);
     sgs::carve(chunk, g.tiles_touched, P);
     sgs::carve(chunk, g.rect_kept, P);
+    sgs::carve(chunk, g.depth_raw, P);
     sgs::carve(chunk, g.depth_keys[0], P);
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);
     sgs::carve(chunk, g.depth_vals[1], P);
-    sgs::carve(chunk, g.sorted_offsets, P);
-    g.temp_bytes = geom_temp_bytes((int)P);
-    sgs::carve(chunk, g.temp, g.temp_bytes);
+    sgs::carve(chunk, g.offs, P);
+    sgs::carve(chunk, g.ctl, 1);
+    g.depth_vblocks = sgs::binning_depth_vblocks((int)P);
+    sgs::carve(chunk, g.hist, (size_t)g.depth_vblocks * 512);
+    sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks * 3);
     return g;
 }
 
@@ -94,30 +67,24 @@ sgs::ImageState carve_image(char*& chunk, size_t N, size_t tiles) {
     return im;
 }
 
-struct BinningCarve {
+// Layout: header | packed records (only if backward will run) | sort ping-pong buffers | histogram matrix, all sized
+// for `cap` instances.  `packed` comes right after the header so that sgs_backward — which knows neither the
+// capacity nor the number of kept instances — finds it without a device->host read.
+sgs::BinningState carve_binning(char*& chunk, size_t cap, bool with_packed, bool header_and_packed_only = false) {
     sgs::BinningState b;
-    uint32_t* header;  // [32] word 0: selector of the sorted double buffer; word 1: kept instances; word 2: packed?
-};
-
-// Layout: header | packed records (only if backward will run) | sort double buffers | CUB temp.
-// `packed` comes right after the header so that sgs_backward — which knows only the API-visible
-// num_rendered, not the number of kept instances — can find it without a device->host read.
-BinningCarve carve_binning(char*& chunk, size_t Rk, int tile_bits, bool with_packed, bool header_and_packed_only = false) {
-    BinningCarve c;
-    sgs::carve(chunk, c.header, 32);
-    if (with_packed) sgs::carve(chunk, c.b.packed, Rk);
-    else c.b.packed = nullptr;
-    c.b.tile_keys[0] = c.b.tile_keys[1] = c.b.gauss_vals[0] = c.b.gauss_vals[1] = nullptr;
-    c.b.temp = nullptr;
-    c.b.temp_bytes = 0;
-    if (header_and_packed_only) return c;
-    sgs::carve(chunk, c.b.tile_keys[0], Rk);
-    sgs::carve(chunk, c.b.tile_keys[1], Rk);
-    sgs::carve(chunk, c.b.gauss_vals[0], Rk);
-    sgs::carve(chunk, c.b.gauss_vals[1], Rk);
-    c.b.temp_bytes = inst_temp_bytes(Rk, tile_bits);
-    sgs::carve(chunk, c.b.temp, c.b.temp_bytes);
-    return c;
+    sgs::carve(chunk, b.header, 32);
+    if (with_packed) sgs::carve(chunk, b.packed, cap);
+    else b.packed = nullptr;
+    b.tile_keys[0] = b.tile_keys[1] = b.gauss_vals[0] = b.gauss_vals[1] = nullptr;
+    b.hist = nullptr;
+    b.cap = cap;
+    if (header_and_packed_only) return b;
+    sgs::carve(chunk, b.tile_keys[0], cap);
+    sgs::carve(chunk, b.gauss_vals[0], cap);
+    sgs::carve(chunk, b.tile_keys[1], cap);
+    sgs::carve(chunk, b.gauss_vals[1], cap);
+    sgs::carve(chunk, b.hist, sgs::binning_tile_hist_words(cap));
+    return b;
 }
 
 template <typename F>
@@ -164,15 +131,81 @@ double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// pinned landing pad for the 4-byte num_rendered read-back
-uint32_t* pinned_slot() {
-    thread_local uint32_t* slot = nullptr;
-    if (!slot) {
-        if (cudaHostAlloc(&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
+// Pinned, device-mapped ring of report slots: the depth-sort kernel writes (kept, touched, visible) + the call's
+// ticket straight into host memory, and the host spins on the ticket — no stream synchronisation, no copy command
+// in the stream, and (because every kernel of the forward pass is already queued when the host starts waiting) no
+// GPU idle time around the one device->host dependency of the path ($R/cuda_rasterizer/rasterizer_impl.cu:281-286).
+constexpr int kSlots = 64;
+struct SlotRing {
+    sgs::HostSlot* host = nullptr;
+    sgs::HostSlot* dev = nullptr;
+    unsigned long long next = 1;
+};
+SlotRing* slot_ring() {
+    thread_local SlotRing ring;
+    if (!ring.host) {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(sgs::HostSlot) * kSlots, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess)
+            return nullptr;
+        memset(h, 0, sizeof(sgs::HostSlot) * kSlots);
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+            cudaFreeHost(h);
+            return nullptr;
+        }
+        ring.host = reinterpret_cast<sgs::HostSlot*>(h);
+        ring.dev = reinterpret_cast<sgs::HostSlot*>(d);
     }
-    return slot;
+    return &ring;
 }
 
+// spin until the kernel has published `ticket`; polls the stream now and then so that a failed launch or a sticky
+// device error ends the wait instead of hanging the caller
+int wait_for_ticket(const volatile sgs::HostSlot* hs, unsigned long long ticket, cudaStream_t s) {
+    unsigned spins = 0;
+    while (hs->ticket != ticket) {
+        if ((++spins & 0x1FFFu) == 0u) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) {
+                if (hs->ticket == ticket) break;
+                return fail(SGS_ERR_CUDA, "sgs_forward: the binning kernel finished without reporting its counts");
+            }
+            if (q != cudaErrorNotReady) return fail(SGS_ERR_CUDA, "sgs_forward: device error while waiting for the instance count", q);
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return 0;
+}
+
+// Capacity of the binning buffer is predicted from the previous call of this thread (frames of a sequence, views of
+// a training batch): 25 % head-room, scaled when the number of Gaussians grew.  A wrong guess is not an error — the
+// binning kernel leaves the buffer untouched and the host re-launches it with the exact size.
+struct CapPredictor {
+    size_t last_kept = 0;
+    int last_P = 0;
+};
+CapPredictor& cap_predictor() {
+    thread_local CapPredictor p;
+    return p;
+}
+std::atomic<long long> g_forced_cap{-1};   // sgs_debug_set_capacity: tests force the over-capacity path
+size_t predict_capacity(int P) {
+    const long long forced = g_forced_cap.load();
+    size_t cap;
+    const CapPredictor& pr = cap_predictor();
+    if (forced >= 0) cap = (size_t)forced;
+    else if (pr.last_P <= 0) cap = (size_t)P * 8 + 16384;
+    else {
+        const double grow = P > pr.last_P ? (double)P / pr.last_P : 1.0;
+        cap = (size_t)((double)pr.last_kept * 1.25 * grow) + 16384;
+    }
+    cap = (cap + 4095) & ~(size_t)4095;
+    if (cap > (size_t)0x7FFFF000u) cap = (size_t)0x7FFFF000u;
+    return cap;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Stage profiler: CUDA events recorded on the launching stream around every stage, summed per
@@ -294,71 +327,74 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     sgs::ImageState img = carve_image(ichunk, N, tiles);
 
     const int cull = (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1;
-    {
-        StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
-        sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
-                                   radii, g, cull, s);
-    }
-    {
-        StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 0);
-        SGS_CUDA_OK(sgs::launch_depth_sort_scan(P, g, s));
-    }
-
-    const double t_presync = tr ? now_us() : 0;
-    // The one device->host dependency of the path: the instance counts.  `kept` sizes the binning
-    // buffer; `num_rendered` (sum of tiles_touched) is what the reference returns to Python
-    // (same place as $R/cuda_rasterizer/rasterizer_impl.cu:281-282).
-    // (ranges + tile_count are zeroed here, off the critical path that follows the read-back)
-    {
-        char* z0 = reinterpret_cast<char*>(img.ranges);
-        char* z1 = reinterpret_cast<char*>(img.tile_count + tiles);
-        SGS_CUDA_OK(cudaMemsetAsync(z0, 0, (size_t)(z1 - z0), s));
-    }
-    uint32_t* slot = pinned_slot();
-    uint32_t local[2] = {0, 0};
-    uint32_t* dst = slot ? slot : local;
-    SGS_CUDA_OK(cudaMemcpyAsync(dst, g.sorted_offsets + (P - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    SGS_CUDA_OK(cudaStreamSynchronize(s));
-    const size_t Rk = dst[0];              // kept instances (what is binned, sorted and rendered)
-    const size_t R = dst[1];               // the reference's num_rendered
-    const int tile_bits = sgs::binning_tile_bits((int)tiles);
     const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
-    const double t_synced = tr ? now_us() : 0;
+    if (sgs::binning_grid_blocks() <= 0) return fail(SGS_ERR_CUDA, "sgs_forward: no CUDA device");
 
-    const size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, Rk, tile_bits, keep); });
+    // Binning buffer sized from a PREDICTION (see predict_capacity): every kernel of the pass is queued before the
+    // host learns the true instance count, so the GPU never idles while the host waits for it.
+    size_t cap = predict_capacity(P);
+    size_t bin_bytes = required_bytes([&](char*& p) { carve_binning(p, cap, keep); });
     char* bchunk = binning_buffer(binning_user, bin_bytes);
     if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
-    BinningCarve bc = carve_binning(bchunk, Rk, tile_bits, keep);
-    const double t_alloc = tr ? now_us() : 0;
+    sgs::BinningState bin = carve_binning(bchunk, cap, keep);
 
-    const uint32_t* point_list = bc.b.gauss_vals[0];
-    const uint32_t* sorted_tiles = bc.b.tile_keys[0];
-    const uint32_t hdr[4] = {0u, (uint32_t)Rk, keep ? 1u : 0u, 0u};   // word 0 is fixed up below
-    if (Rk > 0) {
-        {
-            StageScope sc(SGS_STAGE_DUPLICATE, s, 1);
-            SGS_CUDA_OK(sgs::launch_duplicate(P, vp, g, bc.b, s));
-        }
-        {
-            StageScope sc(SGS_STAGE_TILE_SORT, s, 0);
-            SGS_CUDA_OK(sgs::launch_tile_sort(Rk, (int)tiles, bc.b, &point_list, &sorted_tiles, s));
-        }
-        {
-            StageScope sc(SGS_STAGE_TILE_RANGES, s, 1);
-            const uint32_t hw[4] = {point_list == bc.b.gauss_vals[1] ? 1u : 0u, hdr[1], hdr[2], 0u};
-            SGS_CUDA_OK(sgs::launch_tile_ranges(Rk, (int)tiles, sorted_tiles, img, bc.header, hw, s));
-        }
-    } else {
-        SGS_CUDA_OK(cudaMemcpyAsync(bc.header, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+    SlotRing* ring = slot_ring();
+    if (!ring) return fail(SGS_ERR_ALLOC, "sgs_forward: pinned report slots unavailable");
+    const unsigned long long ticket = ring->next++;
+    const int slot_idx = (int)(ticket % kSlots);
+    const int side = sgs::binning_point_list_side((int)tiles);
+
+    {
+        StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
+        // ranges + tile_count are zeroed by the preprocess kernel (one span, alignment padding included)
+        uint32_t* z0 = reinterpret_cast<uint32_t*>(img.ranges);
+        uint32_t* z1 = reinterpret_cast<uint32_t*>(img.tile_count + tiles);
+        sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                                   radii, g, z0, (size_t)(z1 - z0), cull, s);
     }
     {
-        StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
-        sgs::launch_render_fwd(vp, g, bc.b, img, point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
+        StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 1);
+        SGS_CUDA_OK(sgs::launch_depth_sort(P, g, ring->dev + slot_idx, ticket, s));
     }
-    SGS_CUDA_OK(cudaGetLastError());
+    auto bin_and_render = [&]() -> int {
+        {
+            StageScope sc(SGS_STAGE_TILE_SORT, s, 1);
+            SGS_CUDA_OK(sgs::launch_tile_sort(P, vp, g, bin, img, keep ? 1 : 0, s));
+        }
+        {
+            StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
+            sgs::launch_render_fwd(vp, g, bin, img, bin.gauss_vals[side], keep ? 1 : 0, cull, out_color, out_depth, s);
+        }
+        SGS_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    if (int rc = bin_and_render()) return rc;
+    const double t_presync = tr ? now_us() : 0;
+
+    // The one device->host dependency of the path: the instance counts (same information as the reference's read
+    // at $R/cuda_rasterizer/rasterizer_impl.cu:281-282; `num_rendered` is what the reference returns to Python).
+    if (int rc = wait_for_ticket(ring->host + slot_idx, ticket, s)) return rc;
+    const unsigned long long Rk = ring->host[slot_idx].kept;       // kept instances (binned, sorted and rendered)
+    const unsigned long long R = ring->host[slot_idx].touched;     // the reference's num_rendered
+    const double t_synced = tr ? now_us() : 0;
+    if (Rk > 0x7FFFF000ull || R > 0x7FFFFFFFFFFFull)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: more than 2^31 tile instances");
+    if (Rk > cap) {
+        // prediction too small: the binning kernel left everything untouched (ranges still zero, barrier counter
+        // unused) and the render kernel drew background only — redo both with the exact size
+        cap = ((size_t)Rk + 4095) & ~(size_t)4095;
+        bin_bytes = required_bytes([&](char*& p) { carve_binning(p, cap, keep); });
+        bchunk = binning_buffer(binning_user, bin_bytes);
+        if (!bchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: binning buffer allocation failed");
+        bin = carve_binning(bchunk, cap, keep);
+        if (int rc = bin_and_render()) return rc;
+    }
+    CapPredictor& pr = cap_predictor();
+    pr.last_kept = (size_t)Rk;
+    pr.last_P = P;
     if (tr)
-        fprintf(stderr, "[sgs_forward] pre-sync launches %.1f us | wait %.1f us | binning alloc %.1f us | post-sync launches %.1f us\n",
-                t_presync - t_enter, t_synced - t_presync, t_alloc - t_synced, now_us() - t_alloc);
+        fprintf(stderr, "[sgs_forward] launches %.1f us | wait %.1f us | kept %llu cap %zu\n", t_presync - t_enter,
+                t_synced - t_presync, Rk, cap);
     return (int64_t)R;
 }
 
@@ -387,7 +423,7 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     sgs::GeomState g = carve_geom(geom_buffer, (size_t)P);
     sgs::ImageState img = carve_image(image_buffer, N, tiles);
     // only the header + packed records are needed: their position does not depend on the kept count
-    BinningCarve bc = carve_binning(binning_buffer, 0, 0, true, /*header_and_packed_only=*/true);
+    sgs::BinningState bin = carve_binning(binning_buffer, 0, true, /*header_and_packed_only=*/true);
 
     {
         StageScope sc(SGS_STAGE_BWD_ZERO, s, 0);
@@ -395,7 +431,7 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     }
     if (R > 0) {
         StageScope sc(SGS_STAGE_RENDER_BWD, s, 1);
-        sgs::launch_render_bwd(vp, bc.b, img, dL_dpix, dL_dacc, s);
+        sgs::launch_render_bwd(vp, bin, img, dL_dpix, dL_dacc, s);
     }
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
     {
@@ -435,14 +471,14 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
         if (tile_count) SGS_CUDA_OK(cudaMemcpyAsync(tile_count, img.tile_count, 4 * tiles, D2D, s));
     }
     if (binning_buffer && point_list && R > 0) {
-        uint32_t hdr[3] = {0, 0, 0};
+        uint32_t hdr[4] = {0, 0, 0, 0};
         SGS_CUDA_OK(cudaMemcpyAsync(hdr, binning_buffer + ((128 - (reinterpret_cast<size_t>(binning_buffer) & 127)) & 127),
                                     sizeof(hdr), cudaMemcpyDeviceToHost, s));
         SGS_CUDA_OK(cudaStreamSynchronize(s));
-        const size_t Rk = hdr[1];
+        const size_t Rk = hdr[1], cap = hdr[3];
         if (Rk > 0) {
-            BinningCarve bc = carve_binning(binning_buffer, Rk, sgs::binning_tile_bits((int)tiles), hdr[2] != 0);
-            SGS_CUDA_OK(cudaMemcpyAsync(point_list, bc.b.gauss_vals[(hdr[0] & 1) ? 1 : 0], 4 * Rk, D2D, s));
+            sgs::BinningState b = carve_binning(binning_buffer, cap, hdr[2] != 0);
+            SGS_CUDA_OK(cudaMemcpyAsync(point_list, b.gauss_vals[(hdr[0] & 1) ? 1 : 0], 4 * Rk, D2D, s));
         }
     }
     return 0;
@@ -456,6 +492,18 @@ int64_t sgs_debug_kept(char* binning_buffer, void* stream) {
                                 sizeof(hdr), cudaMemcpyDeviceToHost, s));
     SGS_CUDA_OK(cudaStreamSynchronize(s));
     return (int64_t)hdr[1];
+}
+
+void sgs_debug_set_capacity(int64_t instances) { g_forced_cap.store(instances < 0 ? -1 : (long long)instances); }
+
+int sgs_debug_binning_profile(int enable, uint64_t* out128) {
+    sgs::binning_profile_enable(enable != 0);
+    const unsigned long long* h = sgs::binning_profile(false);
+    if (out128 && h) {
+        if (cudaDeviceSynchronize() != cudaSuccess) return SGS_ERR_CUDA;
+        for (int i = 0; i < 128; i++) out128[i] = h[i];
+    }
+    return 0;
 }
 
 void sgs_profile_enable(int on) {

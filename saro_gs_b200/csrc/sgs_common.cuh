@@ -71,6 +71,33 @@ __forceinline__ __device__ void stage_view(ViewSmem& sm, const ViewParams& vp) {
     __syncthreads();
 }
 
+// Device-resident control block of one forward call (lives in the geometry buffer; zeroed by the preprocess
+// kernel, filled by the binning kernels).  The host never has to read it: the counts it needs travel through a
+// pinned host slot written by the depth-sort kernel (sgs_api.cu).
+struct BinCtl {
+    uint32_t bar_depth;   // grid-barrier arrival counter of depth_sort_kernel
+    uint32_t bar_tile;    // grid-barrier arrival counter of tile_sort_kernel
+    uint32_t key_max;     // max depth key over the visible Gaussians
+    uint32_t key_nmin;    // max of ~key  (min key = ~key_nmin)
+    unsigned long long kept;      // instances to bin: sum of area(rect_kept)
+    unsigned long long touched;   // the reference's num_rendered: sum of tiles_touched
+    uint32_t visible;     // Gaussians with radii > 0
+    uint32_t pad[23];
+};
+static_assert(sizeof(BinCtl) == 128, "BinCtl must be 128 bytes");
+
+// What the depth-sort kernel reports to the host through pinned, device-mapped memory (one 64-byte slot per
+// forward call in flight): payload first, then a system-scope fence, then the ticket the host is spinning on.
+struct HostSlot {
+    unsigned long long kept;
+    unsigned long long touched;
+    uint32_t visible;
+    uint32_t pad0;
+    unsigned long long pad1[4];
+    unsigned long long ticket;
+};
+static_assert(sizeof(HostSlot) == 64, "HostSlot must be 64 bytes");
+
 // Opaque "geometry" state: one entry per input Gaussian. SoA, every array 128-B aligned.
 // Replaces GeometryState of $R/cuda_rasterizer/rasterizer_impl.h:33-48 (layout is free:
 // the buffer is opaque to Python).
@@ -84,11 +111,14 @@ struct GeomState {
     uint32_t* tiles_touched;  // [P]   tiles of the 3-sigma rect (the reference's count; sums to num_rendered)
     ushort4*  rect_kept;      // [P]   tile rect [x0,x1) x [y0,y1) actually binned: the reference's 3-sigma rect
                               //       clipped to the exact bounding box of the alpha >= 1/255 ellipse
-    uint32_t* depth_keys[2];  // [P]   float bits of depth (0xFFFFFFFF when culled); CUB double buffer
-    uint32_t* depth_vals[2];  // [P]   Gaussian index; CUB double buffer
-    uint64_t* sorted_offsets; // [P]   inclusive scan in depth order of (area(rect_kept) | tiles_touched << 32)
-    char*     temp;           // CUB temp storage
-    size_t    temp_bytes;
+    uint32_t* depth_raw;      // [P]   float bits of depth (0xFFFFFFFF when culled), written by preprocess
+    uint32_t* depth_keys[2];  // [P]   radix-sort ping-pong: normalised keys
+    uint32_t* depth_vals[2];  // [P]   radix-sort ping-pong: Gaussian index; [0] ends up holding the depth order
+    uint32_t* offs;           // [P]   inclusive scan, in depth order, of area(rect_kept)
+    BinCtl*   ctl;            // control block (see above)
+    uint32_t* hist;           // [depth_vblocks][512] per-block digit histograms of the current radix pass
+    unsigned long long* blocksum;  // [depth_vblocks][3] per-block (kept, touched, visible) of the scan
+    int       depth_vblocks;  // virtual blocks of the depth sort (multiple of the grid size)
 };
 
 // Opaque "image" state: per pixel + per tile.  Replaces ImageState ($R/.../rasterizer_impl.h:50-57).
@@ -111,12 +141,15 @@ struct __align__(16) PackedInst {
 static_assert(sizeof(PackedInst) == 48, "PackedInst must be 48 bytes");
 
 // Opaque "binning" state: per tile instance.  Replaces BinningState ($R/.../rasterizer_impl.h:59-69).
+// Sized for `cap` instances (a prediction from the previous frame); the kernels read the true count from BinCtl.
 struct BinningState {
-    uint32_t*   tile_keys[2];   // [R] tile id (stored as u16 when the grid has <= 65536 tiles); CUB double buffer
-    uint32_t*   gauss_vals[2];  // [R] Gaussian index; CUB double buffer
-    PackedInst* packed;         // [R] tile-ordered packed records (tile t uses [ranges[t].x, +tile_count[t]))
-    char*       temp;
-    size_t      temp_bytes;
+    uint32_t*   tile_keys[2];   // [cap] tile id; radix-sort ping-pong
+    uint32_t*   gauss_vals[2];  // [cap] Gaussian index; radix-sort ping-pong
+    PackedInst* packed;         // [cap] tile-ordered packed records (tile t uses [ranges[t].x, +tile_count[t]))
+    uint32_t*   hist;           // [tile_vblocks(cap)][256] per-block digit histograms of the current radix pass
+    uint32_t*   header;         // [32] word 0: which ping-pong side holds point_list; 1: kept instances;
+                                //      2: packed records present; 3: cap
+    size_t      cap;
 };
 
 template <typename T>
@@ -208,18 +241,23 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii,
-                           GeomState g, int cull, cudaStream_t s);
+                           GeomState g, uint32_t* zero_words, size_t n_zero, int cull, cudaStream_t s);
 
-// depth sort of Gaussians + scan of area(rect_kept) in depth order; kept instances = sorted_offsets[P-1]
-void binning_geom_temp_bytes(int P, size_t* bytes);
-cudaError_t launch_depth_sort_scan(int P, GeomState g, cudaStream_t s);
-int  binning_tile_bits(int n_tiles);
-void binning_inst_temp_bytes(size_t R, int tile_bits, size_t* bytes);
-cudaError_t launch_duplicate(int P, const ViewParams& vp, GeomState g, BinningState b, cudaStream_t s);
-cudaError_t launch_tile_sort(size_t R, int n_tiles, BinningState b, const uint32_t** point_list,
-                             const uint32_t** sorted_tiles, cudaStream_t s);
-cudaError_t launch_tile_ranges(size_t R, int n_tiles, const uint32_t* sorted_tiles, ImageState img, uint32_t* header,
-                               const uint32_t header_words[4], cudaStream_t s);
+// Binning (sgs_binning.cu): two cooperative persistent kernels, no host-visible sizes in between.
+//   depth_sort: stable LSD radix sort of the P depth keys + scan of area(rect_kept) in depth order; reports
+//               (kept, touched, visible) to `slot` (pinned host memory) under `ticket`.
+//   tile_sort : emits the (tile, Gaussian) instances in depth order, stable radix sort by tile id, tile ranges,
+//               binning header.  Does nothing when kept > b.cap (the host then re-launches it with a larger buffer).
+unsigned long long* binning_profile(bool enable);   // developer aid: pinned buffer of 128 phase timestamps (ns)
+void   binning_profile_enable(bool on);
+int    binning_grid_blocks();                       // co-resident blocks of the persistent kernels (= #SMs)
+int    binning_depth_vblocks(int P);
+size_t binning_tile_hist_words(size_t cap);
+int    binning_tile_bits(int n_tiles);
+int    binning_point_list_side(int n_tiles);        // ping-pong side that ends up holding the sorted lists
+cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s);
+cudaError_t launch_tile_sort(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                             cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,

@@ -634,6 +634,11 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
         !hexplane_feature || !packed || !workspace || !out_means3D || !out_rotations || !out_scales || !out_opacity || !out_shs)
         return SGS_ERR_INVALID_ARGUMENT;
     if (workspace_bytes < sgs_deform_workspace_bytes(N)) return SGS_ERR_INVALID_ARGUMENT;
+    // the kernel reads rows of hexplane_feature / rotation and writes out_rotations / out_shs with 128-bit accesses:
+    // the alignment contract stated in include/saro_gs_b200.h is checked here instead of faulting on the device
+    if ((reinterpret_cast<size_t>(hexplane_feature) | reinterpret_cast<size_t>(rotation) |
+         reinterpret_cast<size_t>(out_rotations) | reinterpret_cast<size_t>(out_shs)) & 15)
+        return SGS_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_pinned_count) {

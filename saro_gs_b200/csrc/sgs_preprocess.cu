@@ -1,6 +1,9 @@
 // Forward per-Gaussian preprocess + markVisible.
 //
-// Follows, rule for rule (not line for line):
+// The per-Gaussian arithmetic (eval_sh, cov3d_from_scale_rot, cov2d_from_cov3d) deliberately keeps the reference's
+// expression trees — same association, same FMA contraction points — because radii / tile counts must be bit-identical
+// (SURVEY.md section 7 "hard parts"); the kernel around it (up-front loads, coalesced SH rows through shared memory,
+// alpha-box rect clip, fused housekeeping) is new.  Rules followed:
 //   near cull  z_view <= 0.2                          $R/cuda_rasterizer/auxiliary.h:139-164
 //   projection p_hom, p_w = 1/(w + 1e-7)              $R/cuda_rasterizer/forward.cu:196-200
 //   cov3D = (S R)^T (S R)                             $R/cuda_rasterizer/forward.cu:118-152
@@ -174,11 +177,17 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
-                      int* __restrict__ radii, GeomState g, int cull) {
+                      int* __restrict__ radii, GeomState g, uint32_t* __restrict__ zero_words, uint32_t n_zero,
+                      int cull, int rot_vec) {
     __shared__ ViewSmem cam;
     __shared__ float4 s_sh[VEC_SH ? (SGS_PRE_THREADS / 32) * 32 * SGS_SH_PAD4 : 1];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < P;
+
+    // Housekeeping that used to be two memsets: this kernel precedes every consumer in stream order, so it zeroes
+    // the binning control block (barrier counters, key range, totals) and the per-tile ranges / counts.
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(BinCtl) / 4) reinterpret_cast<uint32_t*>(g.ctl)[threadIdx.x] = 0u;
+    for (uint32_t i = (uint32_t)idx; i < n_zero; i += gridDim.x * blockDim.x) zero_words[i] = 0u;
 
     // The kernel is latency-bound (ncu: 44 % of the samples wait on global loads at 38 % occupancy), so every load a
     // Gaussian may need is issued up front — its own parameters and the warp's 32 SH rows (coalesced, through shared
@@ -191,7 +200,8 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         pre_o = opacities[idx];
         if (cov3D_precomp == nullptr) {
             pre_sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-            pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+            if (rot_vec) pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+            else pre_q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3]);
         }
     }
     if (VEC_SH && colors_precomp == nullptr) {
@@ -311,24 +321,28 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     radii[idx] = out_radius;
     g.tiles_touched[idx] = out_tiles;
     g.rect_kept[idx] = out_rect;
-    g.depth_keys[0][idx] = out_key;
-    g.depth_vals[0][idx] = (uint32_t)idx;
+    g.depth_raw[idx] = out_key;
 }
 
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii, GeomState g,
-                           int cull, cudaStream_t s) {
+                           uint32_t* zero_words, size_t n_zero, int cull, cudaStream_t s) {
     if (P <= 0) return;
     const int block = SGS_PRE_THREADS;
     const int grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0);
+    // 128-bit quaternion loads only when the caller's pointer allows them (a torch view with a storage offset, or a
+    // plain C caller, may hand over a 4-byte-aligned array: include/saro_gs_b200.h promises to accept that)
+    const int rot_vec = (reinterpret_cast<size_t>(rotations) & 15) == 0 ? 1 : 0;
     if (vec)
         preprocess_fwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
-                                                          cov3D_precomp, colors_precomp, radii, g, cull);
+                                                          cov3D_precomp, colors_precomp, radii, g, zero_words,
+                                                          (uint32_t)n_zero, cull, rot_vec);
     else
         preprocess_fwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, scales, rotations, opacities, shs,
-                                                           cov3D_precomp, colors_precomp, radii, g, cull);
+                                                           cov3D_precomp, colors_precomp, radii, g, zero_words,
+                                                           (uint32_t)n_zero, cull, rot_vec);
 }
 
 // markVisible: bool per point = (z_view > 0.2).  $R/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153

@@ -49,7 +49,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       const float4* __restrict__ conic_opacity, const float* __restrict__ acc, float* __restrict__ dL_dmean2D,
                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
-                      float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+                      float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int rot_vec) {
     __shared__ ViewSmem cam;
     // SH rows travel through shared memory so that both the 192-B reads and the 192-B gradient writes of a
     // warp are fully coalesced (32 consecutive rows = 6 KB contiguous)
@@ -76,7 +76,8 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         pre_cm = clamped[idx];
         if (scales != nullptr) {
             pre_sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-            pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+            if (rot_vec) pre_q = reinterpret_cast<const float4*>(rotations)[idx];
+            else pre_q = make_float4(rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3]);
         }
     }
     const bool visible = valid && pre_radius > 0;
@@ -353,7 +354,12 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         dL_dopacity[idx] = o_opacity;
 #pragma unroll
         for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = o_cov[i];
-        reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+        if (rot_vec) {
+            reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) dL_drot[4 * idx + i] = o_rot[i];
+        }
     }
     if (M > 0) {
         if (VEC_SH) {
@@ -404,14 +410,16 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
     const int block = SGS_PRE_THREADS, grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0) &&
                      ((reinterpret_cast<size_t>(dL_dsh) & 15) == 0);
+    // 128-bit accesses to the caller's rotations / dL_drot only when both pointers are 16-byte aligned
+    const int rot_vec = (((reinterpret_cast<size_t>(rotations) | reinterpret_cast<size_t>(dL_drot)) & 15) == 0) ? 1 : 0;
     if (vec)
         preprocess_bwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
                                                           g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+                                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec);
     else
         preprocess_bwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
                                                            g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec);
 }
 
 }  // namespace sgs

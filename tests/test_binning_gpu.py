@@ -1,0 +1,144 @@
+"""GPU tests of the round-2 binning kernels (csrc/sgs_binning.cu: persistent depth-sort + tile-sort kernels that
+replaced CUB).  The checker is independent of both kernels: the reference's key construction
+(`key = tile << 32 | float_bits(depth)`, $R/cuda_rasterizer/rasterizer_impl.cu:70-111) and ONE stable torch sort of the
+64-bit keys (:299-309) — exactly what the reference does — rebuilt here from the API-visible radii and the exported
+means2D / depth.  Under SGS_FLAG_NO_TILE_CULL the native point_list and ranges must equal it bit for bit, at sizes that
+drive the kernels through every mode: shared-memory-resident slices, multi-slice ("non-resident") depth sort
+(P > 2.4 M), multi-slice tile sort (> 3.0 M instances), > 65 536 tiles (3 radix passes), and the
+prediction-too-small re-launch path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def sgs(native_lib):
+    import saro_gs_b200
+    return saro_gs_b200
+
+
+def reference_lists(st, radii, W, H):
+    """(point_list, ranges) as the reference builds them, from radii + exported means2D / depth (torch, on device)."""
+    dev = radii.device
+    tx, ty = (W + 15) // 16, (H + 15) // 16
+    vis = radii > 0
+    gid = torch.nonzero(vis).squeeze(1)
+    m = st["means2D"][gid]
+    r = radii[gid].to(torch.float32)
+    # getRect, $R/cuda_rasterizer/auxiliary.h:46-56: float division, int truncation, clamp to the grid
+    x0 = ((m[:, 0] - r) / 16).to(torch.int32).clamp(0, tx)
+    y0 = ((m[:, 1] - r) / 16).to(torch.int32).clamp(0, ty)
+    x1 = ((((m[:, 0] + r) + 16.0) - 1.0) / 16).to(torch.int32).clamp(0, tx)
+    y1 = ((((m[:, 1] + r) + 16.0) - 1.0) / 16).to(torch.int32).clamp(0, ty)
+    w, h = (x1 - x0).long(), (y1 - y0).long()
+    n = w * h
+    assert torch.equal(n, st["tiles_touched"][gid].long())
+    owner = torch.repeat_interleave(torch.arange(gid.numel(), device=dev), n)
+    start = torch.cumsum(n, 0) - n
+    j = torch.arange(int(n.sum()), device=dev) - start[owner]
+    yy, xx = j // w[owner], j % w[owner]
+    tile = (y0[owner].long() + yy) * tx + x0[owner].long() + xx
+    depth_bits = st["rgbd"][gid, 3].contiguous().view(torch.int32).long() & 0xFFFFFFFF
+    key = (tile << 32) | depth_bits[owner]
+    order = torch.sort(key, stable=True)[1]        # instances were generated in ascending Gaussian index
+    point_list = gid[owner][order].to(torch.int32)
+    sorted_tile = tile[order]
+    counts = torch.bincount(sorted_tile, minlength=tx * ty)
+    ends = torch.cumsum(counts, 0)
+    ranges = torch.stack([ends - counts, ends], 1)
+    ranges[counts == 0] = 0
+    return point_list, ranges.to(torch.int32)
+
+
+def run_case(sgs, dev, scene, cam, no_cull=True):
+    e = torch.Tensor([])
+    args = (torch.zeros(3, device=dev), scene.means3D.to(dev), e, scene.opacities.to(dev), scene.scales.to(dev),
+            scene.rotations.to(dev), 1.0, e, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.tanfovx, cam.tanfovy,
+            cam.height, cam.width, scene.shs.to(dev), scene.sh_degree, cam.campos.to(dev), False)
+    R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(*args, _no_tile_cull=no_cull)
+    st = sgs._C.debug_export(scene.means3D.shape[0], cam.width, cam.height, R, gb, bb, ib)
+    return R, color, radii, depth, st
+
+
+def check_against_reference_order(sgs, dev, scene, cam):
+    R, color, radii, depth, st = run_case(sgs, dev, scene, cam, no_cull=True)
+    pl, rng = reference_lists(st, radii, cam.width, cam.height)
+    assert R == st["kept"] == pl.numel()
+    assert torch.equal(st["point_list"], pl)
+    assert torch.equal(st["ranges"], rng)
+    return R, color, depth
+
+
+def test_config2_lists_equal_one_stable_64bit_sort(sgs, dev):
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene()
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R == 3927052
+
+
+def test_multi_slice_depth_sort(sgs, dev):
+    """P = 2.6 M: more keys than the depth-sort blocks keep resident in shared memory (148 x 16 384)."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=2_600_000, seed=5, width=320, height=240, fx=180.0, log_scale_mean=-4.2)
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R > 0
+
+
+def test_multi_slice_tile_sort(sgs, dev):
+    """> 3.03 M instances: more than the tile-sort blocks keep resident (148 x 20 480); config 2 with 1.8x larger splats."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(log_scale_mean=-2.4)
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R > 6_000_000
+
+
+def test_three_pass_tile_sort(sgs, dev):
+    """> 65 536 tiles (17 tile bits = 3 radix passes): 4800 x 3600 image."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=60_000, seed=2, width=4800, height=3600, fx=2600.0, log_scale_mean=-3.4)
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R > 0
+
+
+@pytest.mark.parametrize("P", [1, 31, 1023, 1025, 70_001])
+def test_small_and_ragged_sizes(sgs, dev, P):
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.small_scene(P=P, seed=P)
+    check_against_reference_order(sgs, dev, scene, cam)
+
+
+def test_prediction_too_small_relaunches_with_exact_size(sgs, dev):
+    """sgs_debug_set_capacity(4096) forces the 'prediction too small' path: same image, same lists, bit for bit."""
+    from saro_gs_b200 import synthetic, _lib
+    scene, cam = synthetic.config2_scene()
+    lib = _lib.load()
+    R0, color0, radii0, depth0, st0 = run_case(sgs, dev, scene, cam, no_cull=False)
+    try:
+        lib.sgs_debug_set_capacity(4096)
+        R1, color1, radii1, depth1, st1 = run_case(sgs, dev, scene, cam, no_cull=False)
+    finally:
+        lib.sgs_debug_set_capacity(-1)
+    assert R0 == R1 and st0["kept"] == st1["kept"] > 4096
+    assert torch.equal(color0, color1) and torch.equal(depth0, depth1) and torch.equal(radii0, radii1)
+    assert torch.equal(st0["point_list"], st1["point_list"]) and torch.equal(st0["ranges"], st1["ranges"])
+    assert torch.equal(st0["n_contrib"], st1["n_contrib"])
+
+
+def test_nothing_visible_and_all_same_depth(sgs, dev):
+    """Degenerate key ranges: every Gaussian culled (zero radix passes) and every Gaussian at the same depth
+    (one-bit key range; ties keep ascending index)."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.small_scene(P=700, seed=3)
+    behind = scene._replace(means3D=scene.means3D * torch.tensor([1.0, 1.0, -1.0]) - torch.tensor([0.0, 0.0, 50.0]))
+    R, color, radii, depth, st = run_case(sgs, dev, behind, cam)
+    assert R == 0 and st["kept"] == 0 and int((radii != 0).sum()) == 0
+    flat = scene._replace(means3D=torch.cat([scene.means3D[:, :2], torch.full((700, 1), 3.0)], 1))
+    check_against_reference_order(sgs, dev, flat, cam)
