@@ -50,20 +50,21 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);
     sgs::carve(chunk, g.depth_vals[1], P);
-    sgs::carve(chunk, g.offs, P);
+    sgs::carve(chunk, g.coffs, P);
     sgs::carve(chunk, g.ctl, 1);
     g.depth_vblocks = sgs::binning_depth_vblocks((int)P);
-    sgs::carve(chunk, g.hist, (size_t)g.depth_vblocks * 512);
-    sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks * 3);
+    sgs::carve(chunk, g.hist, ((size_t)g.depth_vblocks + 1) * 512);
+    sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks * 4);
     return g;
 }
 
-sgs::ImageState carve_image(char*& chunk, size_t N, size_t tiles) {
+sgs::ImageState carve_image(char*& chunk, size_t N, size_t tiles, size_t supers) {
     sgs::ImageState im;
     sgs::carve(chunk, im.final_T, N);
     sgs::carve(chunk, im.n_contrib, N);
     sgs::carve(chunk, im.ranges, tiles);
     sgs::carve(chunk, im.tile_count, tiles);
+    sgs::carve(chunk, im.cranges, supers);
     return im;
 }
 
@@ -75,15 +76,18 @@ sgs::BinningState carve_binning(char*& chunk, size_t cap, bool with_packed, bool
     sgs::carve(chunk, b.header, 32);
     if (with_packed) sgs::carve(chunk, b.packed, cap);
     else b.packed = nullptr;
-    b.tile_keys[0] = b.tile_keys[1] = b.gauss_vals[0] = b.gauss_vals[1] = nullptr;
+    b.point_list = nullptr;
+    b.coarse_keys[0] = b.coarse_keys[1] = b.coarse_vals[0] = b.coarse_vals[1] = nullptr;
     b.hist = nullptr;
     b.cap = cap;
     if (header_and_packed_only) return b;
-    sgs::carve(chunk, b.tile_keys[0], cap);
-    sgs::carve(chunk, b.gauss_vals[0], cap);
-    sgs::carve(chunk, b.tile_keys[1], cap);
-    sgs::carve(chunk, b.gauss_vals[1], cap);
-    sgs::carve(chunk, b.hist, sgs::binning_tile_hist_words(cap));
+    sgs::carve(chunk, b.point_list, cap);
+    // coarse instances <= kept instances <= cap
+    sgs::carve(chunk, b.coarse_keys[0], cap);
+    sgs::carve(chunk, b.coarse_vals[0], cap);
+    sgs::carve(chunk, b.coarse_keys[1], cap);
+    sgs::carve(chunk, b.coarse_vals[1], cap);
+    sgs::carve(chunk, b.hist, sgs::binning_hist_words(cap));
     return b;
 }
 
@@ -321,10 +325,11 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (!gchunk) return fail(SGS_ERR_ALLOC, "sgs_forward: geometry buffer allocation failed");
     sgs::GeomState g = carve_geom(gchunk, (size_t)P);
 
-    const size_t img_bytes = required_bytes([&](char*& p) { carve_image(p, N, tiles); });
+    const size_t supers = (size_t)sgs::binning_supertiles(vp.tiles_x, vp.tiles_y, nullptr);
+    const size_t img_bytes = required_bytes([&](char*& p) { carve_image(p, N, tiles, supers); });
     char* ichunk = image_buffer(image_user, img_bytes);
     if (!ichunk) return fail(SGS_ERR_ALLOC, "sgs_forward: image buffer allocation failed");
-    sgs::ImageState img = carve_image(ichunk, N, tiles);
+    sgs::ImageState img = carve_image(ichunk, N, tiles, supers);
 
     const int cull = (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1;
     const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
@@ -342,13 +347,12 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     if (!ring) return fail(SGS_ERR_ALLOC, "sgs_forward: pinned report slots unavailable");
     const unsigned long long ticket = ring->next++;
     const int slot_idx = (int)(ticket % kSlots);
-    const int side = sgs::binning_point_list_side((int)tiles);
 
     {
         StageScope sc(SGS_STAGE_PREPROCESS_FWD, s, 1);
-        // ranges + tile_count are zeroed by the preprocess kernel (one span, alignment padding included)
+        // ranges + tile_count + supertile buckets are zeroed by the preprocess kernel (one span, padding included)
         uint32_t* z0 = reinterpret_cast<uint32_t*>(img.ranges);
-        uint32_t* z1 = reinterpret_cast<uint32_t*>(img.tile_count + tiles);
+        uint32_t* z1 = reinterpret_cast<uint32_t*>(img.cranges + supers);
         sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
                                    radii, g, z0, (size_t)(z1 - z0), cull, s);
     }
@@ -358,12 +362,12 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     }
     auto bin_and_render = [&]() -> int {
         {
-            StageScope sc(SGS_STAGE_TILE_SORT, s, 1);
-            SGS_CUDA_OK(sgs::launch_tile_sort(P, vp, g, bin, img, keep ? 1 : 0, s));
+            StageScope sc(SGS_STAGE_TILE_SORT, s, 3);
+            SGS_CUDA_OK(sgs::launch_tile_binning(P, vp, g, bin, img, keep ? 1 : 0, s));
         }
         {
             StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
-            sgs::launch_render_fwd(vp, g, bin, img, bin.gauss_vals[side], keep ? 1 : 0, cull, out_color, out_depth, s);
+            sgs::launch_render_fwd(vp, g, bin, img, bin.point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
         }
         SGS_CUDA_OK(cudaGetLastError());
         return 0;
@@ -421,7 +425,7 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     const size_t N = (size_t)width * height;
     const size_t tiles = (size_t)vp.tiles_x * vp.tiles_y;
     sgs::GeomState g = carve_geom(geom_buffer, (size_t)P);
-    sgs::ImageState img = carve_image(image_buffer, N, tiles);
+    sgs::ImageState img = carve_image(image_buffer, N, tiles, (size_t)sgs::binning_supertiles(vp.tiles_x, vp.tiles_y, nullptr));
     // only the header + packed records are needed: their position does not depend on the kept count
     sgs::BinningState bin = carve_binning(binning_buffer, 0, true, /*header_and_packed_only=*/true);
 
@@ -464,7 +468,7 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
         if (cov3D) SGS_CUDA_OK(cudaMemcpyAsync(cov3D, g.cov3D, 24 * (size_t)P, D2D, s));
     }
     if (image_buffer) {
-        sgs::ImageState img = carve_image(image_buffer, N, tiles);
+        sgs::ImageState img = carve_image(image_buffer, N, tiles, (size_t)sgs::binning_supertiles(tx, ty, nullptr));
         if (ranges) SGS_CUDA_OK(cudaMemcpyAsync(ranges, img.ranges, 8 * tiles, D2D, s));
         if (n_contrib) SGS_CUDA_OK(cudaMemcpyAsync(n_contrib, img.n_contrib, 4 * N, D2D, s));
         if (final_T) SGS_CUDA_OK(cudaMemcpyAsync(final_T, img.final_T, 4 * N, D2D, s));
@@ -478,7 +482,7 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
         const size_t Rk = hdr[1], cap = hdr[3];
         if (Rk > 0) {
             sgs::BinningState b = carve_binning(binning_buffer, cap, hdr[2] != 0);
-            SGS_CUDA_OK(cudaMemcpyAsync(point_list, b.gauss_vals[(hdr[0] & 1) ? 1 : 0], 4 * Rk, D2D, s));
+            SGS_CUDA_OK(cudaMemcpyAsync(point_list, b.point_list, 4 * Rk, D2D, s));
         }
     }
     return 0;

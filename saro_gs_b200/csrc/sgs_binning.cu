@@ -5,28 +5,30 @@
 //   $R/cuda_rasterizer/rasterizer_impl.cu:299-309 (SortPairs on bits [0, 32+bit))
 //   $R/cuda_rasterizer/rasterizer_impl.cu:116-138 (identifyTileRanges)
 //
-// B200 design: a TWO-LEVEL sort over a CULLED instance set, done by TWO persistent kernels.
+// B200 design: the R = 3.9 M (tile, depth) instances of the reference are NEVER sorted.
 //   0. (in the preprocess kernel) the reference's 3-sigma tile rect of every Gaussian is clipped to
 //      the exact axis-aligned bounding box of its  alpha >= 1/255  ellipse (`rect_kept`).  The
 //      reference's own count (`tiles_touched`) is kept for the API-visible num_rendered; a dropped
 //      instance would `continue` on all 256 pixels of its tile in the reference, so image, depth and
 //      gradients are unchanged bit for bit.  (SGS_FLAG_NO_TILE_CULL keeps the full rect: then ranges /
 //      point_list / n_contrib equal the reference's bit for bit.)
-//   1. depth_sort_kernel: stable LSD radix sort of the P Gaussians (not the R >> P instances) by their depth
-//      bits, normalised to the frame's [min, max] key range (26 bits = 3 passes of 9 at config 2 instead of 4 x 8),
-//      then the scan of area(rect_kept) in depth order.  The totals go to the host through a pinned slot.
-//   2. tile_sort_kernel: every block GENERATES its slice of the depth-ordered (tile, Gaussian) instance stream
-//      straight into shared memory (the unsorted stream never exists in HBM), then a stable LSD radix sort on
-//      ceil(log2 #tiles) bits (13 bits = 7 + 6 at 1352x1014), then the per-tile ranges.
-//   A stable sort by tile of a depth-ordered stream is ordered by (tile, depth, index): the reference order
-//   restricted to the kept instances.
+//   1. depth_sort_kernel (persistent, cooperative): stable LSD radix sort of the P Gaussians by their depth bits,
+//      normalised to the frame's [min, max] key range (26 bits = 3 passes of 9 at config 2), then the scan, in depth
+//      order, of the number of SUPERTILES (4x4 tiles = 64x64 pixels) each Gaussian's kept rect overlaps.  The
+//      totals (kept instances, the reference's num_rendered, visible Gaussians) go to the host through a pinned slot.
+//   2. coarse_sort_kernel (persistent, cooperative): every block generates its slice of the depth-ordered
+//      (supertile, Gaussian) stream straight into shared memory and ONE stable radix pass (9 bits: 352 supertiles at
+//      1352x1014) buckets it: ~0.75 M coarse instances instead of 2.2 M tile instances, 4 bytes scattered each.
+//   3. tile_count_kernel / tile_fill_kernel (one block per supertile): stream the supertile's depth-ordered list and
+//      expand it into its 16 per-tile lists with ballot-based stable compaction — the only per-instance cost of the
+//      whole binning is one coalesced 4-byte store.  Per-tile ranges come from the counts (scan by the last block).
+//   A stable bucketing of a depth-ordered stream is ordered by (bucket, depth, index), and the expansion keeps the
+//   order inside every tile: the reference order restricted to the kept instances.
 //
-// Why not CUB (round 1): both sorts are tiny (2.4 MB and 17 MB per pass) and CUB's onesweep spends its time in
-// launch gaps and in 34-CTA decoupled look-back chains (10 launches, 170 us at config 2).  Here one pass is:
-// every block ranks its slice in shared memory (warp-private histograms + match.any), publishes its digit
-// histogram, ONE grid-wide barrier, every block derives its global offsets from the histogram matrix and scatters.
-// The kernels are launched cooperatively with one 1024-thread block per SM; all counts (P-dependent pass count,
-// number of instances) are read on the device, so the host never waits between the stages.
+// One radix pass = every block ranks its slice in shared memory (warp-private histograms, ballot-based peer
+// masks), publishes its digit histogram, grid-wide barrier, the blocks share the column scans of the histogram
+// matrix, grid-wide barrier, every block scatters.  All counts are read on the device: the host never waits between
+// the stages (see sgs_api.cu).  Round 1 used CUB here: 10 launches and 34-CTA decoupled look-back chains, 205 us.
 #include "sgs_common.cuh"
 #include <cstring>
 
@@ -34,11 +36,11 @@ namespace sgs {
 
 #define SGS_SORT_THREADS 1024
 #define SGS_SORT_WARPS 32
-#define SGS_DEPTH_ND 512       // max digits per pass, depth sort (9 bits)
-#define SGS_TILE_ND 256        // max digits per pass, tile sort (8 bits)
-#define SGS_DEPTH_CHUNK 16384  // keys a block keeps resident in shared memory (depth sort)
-#define SGS_TILE_CHUNK 20480   // instances a block keeps resident in shared memory (tile sort)
-#define SGS_DUP_SMALL 8
+#define SGS_SORT_ND 512        // max digits per pass (9 bits)
+#define SGS_SORT_CHUNK 16384   // items a block keeps resident in shared memory
+#define SGS_DUP_SMALL 4
+#define SGS_ST 4               // supertile edge in tiles
+#define SGS_EXP_THREADS 512    // expansion kernels: threads per supertile block
 
 // ------------------------------------------------------------------------------------------------
 // grid-wide barrier (all blocks co-resident: cooperative launch, one block per SM)
@@ -75,31 +77,30 @@ __device__ __forceinline__ void prof_mark(unsigned long long* prof, int& slot) {
 // ------------------------------------------------------------------------------------------------
 // One radix pass over a slice held in shared memory
 // ------------------------------------------------------------------------------------------------
-template <int NDMAX, int CHUNK>
 struct SortSmem {
-    uint16_t whist[SGS_SORT_WARPS][NDMAX + 2];   // per-warp digit counts -> exclusive prefix over warps (+ dump bin)
-    uint32_t cnt[NDMAX];                          // digit counts of the slice
-    uint32_t base[NDMAX];                         // global offset of the slice's first element of every digit
-    uint32_t red[2][SGS_SORT_THREADS];            // reduction scratch
+    uint16_t whist[SGS_SORT_WARPS][SGS_SORT_ND];   // per-warp digit counts -> exclusive prefix over the warps
+    uint32_t cnt[SGS_SORT_ND];                      // digit counts of the slice
+    uint32_t base[SGS_SORT_ND];                     // global offset of the slice's first element of every digit
     uint32_t wsum[32];
-    uint32_t key[CHUNK];
-    uint32_t val[CHUNK];
-    uint16_t rank[CHUNK];
+    uint32_t key[SGS_SORT_CHUNK];
+    uint32_t val[SGS_SORT_CHUNK];
+    uint16_t rank[SGS_SORT_CHUNK];
 };
 
 __device__ __forceinline__ uint32_t keys_per_warp(uint32_t n) {
     return (((n + SGS_SORT_WARPS - 1) / SGS_SORT_WARPS) + 31u) & ~31u;
 }
 
-// Stable ranks of sm.key[0..n) on digit (key >> shift) & (nd - 1).  Warp w owns the contiguous keys
+// Stable ranks of sm.key[0..n) on digit (key >> shift) & (nd - 1), nd = 1 << dbits.  Warp w owns the contiguous keys
 // [w * per, (w + 1) * per); on return  position within the slice's digit group = whist[w][d] + rank[i], and
-// sm.cnt[d] holds the slice's digit histogram.
-template <int NDMAX, int CHUNK>
-__device__ __forceinline__ void rank_slice(SortSmem<NDMAX, CHUNK>& sm, uint32_t n, uint32_t shift, uint32_t nd) {
+// sm.cnt[d] holds the slice's digit histogram.  Peer masks are built from one ballot per digit bit (match.any costs
+// ~200 cycles per step on sm_100 when the 32 digits differ, which is the common case here).
+__device__ __forceinline__ void rank_slice(SortSmem& sm, uint32_t n, uint32_t shift, uint32_t dbits) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nd = 1u << dbits;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&sm.whist[0][0]);
-        constexpr uint32_t words = SGS_SORT_WARPS * (NDMAX + 2) / 2;
+        constexpr uint32_t words = SGS_SORT_WARPS * SGS_SORT_ND / 2;
         for (uint32_t i = tid; i < words; i += SGS_SORT_THREADS) z[i] = 0u;
     }
     __syncthreads();
@@ -110,56 +111,94 @@ __device__ __forceinline__ void rank_slice(SortSmem<NDMAX, CHUNK>& sm, uint32_t 
     for (uint32_t i0 = beg; i0 < end; i0 += 32) {
         const uint32_t i = i0 + lane;
         const bool valid = i < end;
-        const uint32_t d = valid ? ((sm.key[i] >> shift) & (nd - 1u)) : nd;   // nd = dump bin of the idle lanes
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t d = valid ? ((sm.key[i] >> shift) & (nd - 1u)) : 0u;
+        uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+        for (uint32_t b = 0; b < 9; b++) {
+            if (b < dbits) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? m : ~m;
+            }
+        }
         const uint32_t before = peers & lt_mask;
-        const uint32_t old = wh[d];
+        uint32_t old = 0;
+        if (valid) old = wh[d];
         __syncwarp();
-        if (before == 0u) wh[d] = (uint16_t)(old + __popc(peers));
+        if (valid && before == 0u) wh[d] = (uint16_t)(old + __popc(peers));
         __syncwarp();
         if (valid) sm.rank[i] = (uint16_t)(old + __popc(before));
     }
     __syncthreads();
-    for (uint32_t d = tid; d < nd; d += SGS_SORT_THREADS) {
+    // exclusive prefix over the 32 warps, per digit: (digit, half) pairs so that all 1024 threads work
+    {
+        const uint32_t d = tid & (SGS_SORT_ND - 1u), half = tid >> 9;   // warps [16 half, 16 half + 16)
         uint32_t run = 0;
+        if (d < nd) {
 #pragma unroll 8
-        for (int w = 0; w < SGS_SORT_WARPS; w++) {
-            const uint32_t c = sm.whist[w][d];
-            sm.whist[w][d] = (uint16_t)run;
-            run += c;
+            for (int w = 0; w < 16; w++) {
+                const uint32_t c = sm.whist[half * 16 + w][d];
+                sm.whist[half * 16 + w][d] = (uint16_t)run;
+                run += c;
+            }
+            if (half == 0) sm.cnt[d] = run;
         }
-        sm.cnt[d] = run;
+        __syncthreads();
+        if (d < nd && half == 1) {
+            const uint32_t first = sm.cnt[d];
+            sm.cnt[d] = first + run;
+#pragma unroll 8
+            for (int w = 16; w < 32; w++) sm.whist[w][d] = (uint16_t)(sm.whist[w][d] + first);
+        }
     }
     __syncthreads();
 }
 
-// sm.base[d] = (number of keys with a smaller digit anywhere) + (keys with digit d in slices before `v`),
-// from the published histogram matrix hist[vblocks][nd].
-template <int NDMAX, int CHUNK>
-__device__ __forceinline__ void slice_bases(SortSmem<NDMAX, CHUNK>& sm, const uint32_t* __restrict__ hist, uint32_t v,
-                                            uint32_t vblocks, uint32_t nd) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t parts = SGS_SORT_THREADS / nd;    // nd is a power of two <= 512
-    const uint32_t d = tid & (nd - 1u), part = tid / nd;
-    uint32_t tot = 0, below = 0;
-#pragma unroll 4
-    for (uint32_t vv = part; vv < vblocks; vv += parts) {
-        const uint32_t x = __ldcg(hist + (size_t)vv * nd + d);
-        tot += x;
-        if (vv < v) below += x;
-    }
-    sm.red[0][tid] = tot;
-    sm.red[1][tid] = below;
-    __syncthreads();
-    // digit totals + exclusive scan over the digits (threads 0..511 take part in the shuffles, idle ones add 0)
-    uint32_t T = 0, Bl = 0;
-    if (tid < nd) {
-        for (uint32_t p = 0; p < parts; p++) {
-            T += sm.red[0][p * nd + tid];
-            Bl += sm.red[1][p * nd + tid];
+// hist layout: [vblocks + 1][nd]; row `vblocks` receives the digit totals
+__device__ __forceinline__ void publish_hist(const uint32_t* cnt, uint32_t* __restrict__ hist, uint32_t v, uint32_t nd) {
+    for (uint32_t d = threadIdx.x; d < nd; d += SGS_SORT_THREADS) __stcg(hist + (size_t)v * nd + d, cnt[d]);
+}
+
+// Column scans of the histogram matrix, shared by the blocks: block b owns the digits [b dpb, (b + 1) dpb), one warp
+// per digit; hist[v][d] becomes the number of keys with digit d in the slices before v, row `vblocks` the totals.
+__device__ __forceinline__ void column_scans(uint32_t* __restrict__ hist, uint32_t vblocks, uint32_t nd) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t dpb = (nd + gridDim.x - 1) / gridDim.x;
+    for (uint32_t dd = warp; dd < dpb; dd += SGS_SORT_WARPS) {
+        const uint32_t d = blockIdx.x * dpb + dd;
+        if (d >= nd) break;
+        uint32_t carry = 0;
+        for (uint32_t v0 = 0; v0 < vblocks; v0 += 128) {
+            uint32_t x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t v = v0 + u * 32 + lane;
+                x[u] = v < vblocks ? __ldcg(hist + (size_t)v * nd + d) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t v = v0 + u * 32 + lane;
+                uint32_t inc = x[u];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                if (v < vblocks) __stcg(hist + (size_t)v * nd + d, carry + inc - x[u]);
+                carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
         }
+        if (lane == 0) __stcg(hist + (size_t)vblocks * nd + d, carry);
     }
+}
+
+// sm.base[d] = (number of keys with a smaller digit anywhere) + (keys with digit d in the slices before `v`);
+// also leaves the exclusive scan of the digit totals in sm.cnt (the bucket starts of a single-pass sort).
+__device__ __forceinline__ void slice_bases(SortSmem& sm, const uint32_t* __restrict__ hist, uint32_t v, uint32_t vblocks,
+                                            uint32_t nd) {
+    const uint32_t tid = threadIdx.x;
     if (tid < 512) {
+        const uint32_t T = tid < nd ? __ldcg(hist + (size_t)vblocks * nd + tid) : 0u;
+        const uint32_t pre = tid < nd ? __ldcg(hist + (size_t)v * nd + tid) : 0u;
         const uint32_t lane = tid & 31, warp = tid >> 5;
         uint32_t inc = T;
 #pragma unroll
@@ -171,13 +210,15 @@ __device__ __forceinline__ void slice_bases(SortSmem<NDMAX, CHUNK>& sm, const ui
         asm volatile("bar.sync 1, 512;");
         uint32_t woff = 0;
         for (uint32_t w = 0; w < warp; w++) woff += sm.wsum[w];
-        if (tid < nd) sm.base[tid] = woff + inc - T + Bl;
+        if (tid < nd) {
+            sm.cnt[tid] = woff + inc - T;
+            sm.base[tid] = woff + inc - T + pre;
+        }
     }
     __syncthreads();
 }
 
-template <int NDMAX, int CHUNK>
-__device__ __forceinline__ void scatter_slice(SortSmem<NDMAX, CHUNK>& sm, uint32_t n, uint32_t shift, uint32_t nd,
+__device__ __forceinline__ void scatter_slice(SortSmem& sm, uint32_t n, uint32_t shift, uint32_t nd,
                                               uint32_t* __restrict__ out_key, uint32_t* __restrict__ out_val) {
     const uint32_t per = keys_per_warp(n);
     for (uint32_t i = threadIdx.x; i < n; i += SGS_SORT_THREADS) {
@@ -189,12 +230,15 @@ __device__ __forceinline__ void scatter_slice(SortSmem<NDMAX, CHUNK>& sm, uint32
     }
 }
 
-__device__ __forceinline__ void publish_hist(const uint32_t* cnt, uint32_t* __restrict__ hist, uint32_t v, uint32_t nd) {
-    for (uint32_t d = threadIdx.x; d < nd; d += SGS_SORT_THREADS) __stcg(hist + (size_t)v * nd + d, cnt[d]);
+// supertiles a kept tile rect overlaps: [x0, x1) x [y0, y1) in supertile units
+__device__ __forceinline__ uint4 super_rect(const ushort4 r) {
+    if (r.y <= r.x || r.w <= r.z) return make_uint4(0u, 0u, 0u, 0u);
+    return make_uint4((uint32_t)r.x / SGS_ST, ((uint32_t)r.y + SGS_ST - 1) / SGS_ST, (uint32_t)r.z / SGS_ST,
+                      ((uint32_t)r.w + SGS_ST - 1) / SGS_ST);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel 1: depth sort of the Gaussians + scan of the kept tile counts in depth order
+// Kernel 1: depth sort of the Gaussians + scan of their supertile counts in depth order
 // ------------------------------------------------------------------------------------------------
 struct DepthArgs {
     int P;
@@ -205,7 +249,7 @@ struct DepthArgs {
     uint32_t* vals[2];
     const ushort4* rect_kept;
     const uint32_t* tiles_touched;
-    uint32_t* offs;
+    uint32_t* coffs;
     uint32_t* hist;
     unsigned long long* blocksum;
     BinCtl* ctl;
@@ -214,25 +258,39 @@ struct DepthArgs {
     unsigned long long* prof;
 };
 
-using DepthSmem = SortSmem<SGS_DEPTH_ND, SGS_DEPTH_CHUNK>;
-
-struct Tri {
+struct Quad {
     unsigned long long kept, touched;
-    uint32_t vis;
+    uint32_t vis, coarse;
 };
-__device__ __forceinline__ Tri tri_add(const Tri& a, const Tri& b) { return {a.kept + b.kept, a.touched + b.touched, a.vis + b.vis}; }
-__device__ __forceinline__ Tri tri_shfl_up(const Tri& a, int o) {
-    Tri r;
-    r.kept = __shfl_up_sync(0xFFFFFFFFu, a.kept, o);
-    r.touched = __shfl_up_sync(0xFFFFFFFFu, a.touched, o);
-    r.vis = __shfl_up_sync(0xFFFFFFFFu, a.vis, o);
+__device__ __forceinline__ Quad quad_add(const Quad& a, const Quad& b) {
+    return {a.kept + b.kept, a.touched + b.touched, a.vis + b.vis, a.coarse + b.coarse};
+}
+__device__ __forceinline__ Quad quad_xor(const Quad& a, int o) {
+    Quad r;
+    r.kept = __shfl_xor_sync(0xFFFFFFFFu, a.kept, o);
+    r.touched = __shfl_xor_sync(0xFFFFFFFFu, a.touched, o);
+    r.vis = __shfl_xor_sync(0xFFFFFFFFu, a.vis, o);
+    r.coarse = __shfl_xor_sync(0xFFFFFFFFu, a.coarse, o);
     return r;
+}
+// block-wide sum (every thread gets it)
+__device__ __forceinline__ Quad block_sum(Quad q, Quad* s_w) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q = quad_add(q, quad_xor(q, o));
+    __syncthreads();
+    if (lane == 0) s_w[warp] = q;
+    __syncthreads();
+    Quad t = s_w[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = quad_add(t, quad_xor(t, o));
+    return t;
 }
 
 __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const DepthArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DepthSmem& sm = *reinterpret_cast<DepthSmem*>(smem_raw);
-    __shared__ Tri s_w[32], s_p[32];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    __shared__ Quad s_w[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t P = (uint32_t)a.P, VB = (uint32_t)a.vblocks, SL = (uint32_t)a.slice;
     const bool resident = VB == gridDim.x;
@@ -257,19 +315,21 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
         kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
         knmin = __reduce_max_sync(0xFFFFFFFFu, knmin);
         if (lane == 0) {
-            sm.red[0][warp] = kmax;
-            sm.red[1][warp] = knmin;
+            sm.base[warp] = kmax;
+            sm.cnt[warp] = knmin;
         }
         __syncthreads();
         if (warp == 0) {
-            kmax = __reduce_max_sync(0xFFFFFFFFu, sm.red[0][lane]);
-            knmin = __reduce_max_sync(0xFFFFFFFFu, sm.red[1][lane]);
+            kmax = __reduce_max_sync(0xFFFFFFFFu, sm.base[lane]);
+            knmin = __reduce_max_sync(0xFFFFFFFFu, sm.cnt[lane]);
             if (lane == 0) {
                 if (kmax) atomicMax(&a.ctl->key_max, kmax);
                 if (knmin) atomicMax(&a.ctl->key_nmin, knmin);
             }
         }
-        { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_depth, bar_target); prof_mark(a.prof, pslot); }
+        prof_mark(a.prof, pslot);
+        grid_barrier(&a.ctl->bar_depth, bar_target);
+        prof_mark(a.prof, pslot);
     }
     const uint32_t key_max = __ldcg(&a.ctl->key_max), key_nmin = __ldcg(&a.ctl->key_nmin);
     const uint32_t key_min = ~key_nmin;
@@ -285,6 +345,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
             const uint32_t lo = v * SL, hi = min(P, lo + SL);
             for (uint32_t i = lo + tid; i < hi; i += SGS_SORT_THREADS) a.vals[0][i] = i;
         }
+        grid_barrier(&a.ctl->bar_depth, bar_target);
     }
 
     for (uint32_t p = 1; p <= npass; p++) {
@@ -295,8 +356,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
         uint32_t* out_key = (p == npass) ? nullptr : a.keys[out];   // the keys are dead after the last pass
         uint32_t* out_val = a.vals[out];
 
-        auto load = [&](uint32_t v, uint32_t lo, uint32_t n) {
-            (void)v;
+        auto load = [&](uint32_t lo, uint32_t n) {
             if (p == 1u) {
                 for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) {
                     const uint32_t k = resident ? sm.key[i] : a.raw[lo + i];
@@ -314,110 +374,106 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
 
         for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
             const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
-            load(v, lo, n);
-            prof_mark(a.prof, pslot);
-            rank_slice(sm, n, shift, nd);
+            load(lo, n);
+            rank_slice(sm, n, shift, dbits);
             publish_hist(sm.cnt, a.hist, v, nd);
         }
-        { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_depth, bar_target); prof_mark(a.prof, pslot); }
+        prof_mark(a.prof, pslot);
+        grid_barrier(&a.ctl->bar_depth, bar_target);
+        column_scans(a.hist, VB, nd);
+        grid_barrier(&a.ctl->bar_depth, bar_target);
+        prof_mark(a.prof, pslot);
         for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
             const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
             if (!resident) {
-                load(v, lo, n);
-                rank_slice(sm, n, shift, nd);
+                load(lo, n);
+                rank_slice(sm, n, shift, dbits);
             }
             slice_bases(sm, a.hist, v, VB, nd);
-            prof_mark(a.prof, pslot);
             scatter_slice(sm, n, shift, nd, out_key, out_val);
             __syncthreads();
         }
-        { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_depth, bar_target); prof_mark(a.prof, pslot); }
+        prof_mark(a.prof, pslot);
+        grid_barrier(&a.ctl->bar_depth, bar_target);
+        prof_mark(a.prof, pslot);
     }
-    if (npass == 0u) { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_depth, bar_target); prof_mark(a.prof, pslot); }
 
-    // ---- scan of (area(rect_kept), tiles_touched, visible) in depth order
+    // ---- scan, in depth order, of the supertile counts; totals of (kept tiles, touched tiles, visible)
     const uint32_t* order = a.vals[0];
-    auto slice_scan = [&](uint32_t lo, uint32_t n, Tri& mine_excl, Tri& block_total, uint32_t& ipt) {
-        ipt = (n + SGS_SORT_THREADS - 1) / SGS_SORT_THREADS;
-        Tri t = {0ull, 0ull, 0u};
-        const uint32_t b = lo + tid * ipt, e = min(lo + n, b + ipt);
-        for (uint32_t k = b; k < e; k++) {
-            const uint32_t gid = __ldcg(order + k);
+    // gathers of one slice (all loads independent); supertile count of every item -> sm.key
+    auto gather = [&](uint32_t lo, uint32_t n) -> Quad {
+        Quad q = {0ull, 0ull, 0u, 0u};
+        for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) {
+            const uint32_t gid = __ldcg(order + lo + i);
             const ushort4 r = a.rect_kept[gid];
             const uint32_t tt = a.tiles_touched[gid];
-            t.kept += (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
-            t.touched += tt;
-            t.vis += tt ? 1u : 0u;
+            const uint4 sr = super_rect(r);
+            const uint32_t cc = (sr.y - sr.x) * (sr.w - sr.z);
+            sm.key[i] = cc;
+            q.kept += (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
+            q.touched += tt;
+            q.vis += tt ? 1u : 0u;
+            q.coarse += cc;
         }
-        Tri inc = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const Tri y = tri_shfl_up(inc, o);
-            if (lane >= (uint32_t)o) inc = tri_add(inc, y);
-        }
-        __syncthreads();
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        Tri woff = {0ull, 0ull, 0u}, tot = {0ull, 0ull, 0u};
-        for (uint32_t w = 0; w < 32; w++) {
-            if (w < warp) woff = tri_add(woff, s_w[w]);
-            tot = tri_add(tot, s_w[w]);
-        }
-        mine_excl = tri_add(woff, inc);
-        mine_excl.kept -= t.kept;
-        mine_excl.touched -= t.touched;
-        mine_excl.vis -= t.vis;
-        block_total = tot;
+        return q;
     };
     for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
         const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
-        Tri ex, tot;
-        uint32_t ipt;
-        slice_scan(lo, n, ex, tot, ipt);
+        const Quad tot = block_sum(gather(lo, n), s_w);
         if (tid == 0) {
-            __stcg(a.blocksum + 3 * (size_t)v, tot.kept);
-            __stcg(a.blocksum + 3 * (size_t)v + 1, tot.touched);
-            __stcg(a.blocksum + 3 * (size_t)v + 2, (unsigned long long)tot.vis);
+            __stcg(a.blocksum + 4 * (size_t)v, tot.kept);
+            __stcg(a.blocksum + 4 * (size_t)v + 1, tot.touched);
+            __stcg(a.blocksum + 4 * (size_t)v + 2, (unsigned long long)tot.vis);
+            __stcg(a.blocksum + 4 * (size_t)v + 3, (unsigned long long)tot.coarse);
         }
     }
-    { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_depth, bar_target); prof_mark(a.prof, pslot); }
+    prof_mark(a.prof, pslot);
+    grid_barrier(&a.ctl->bar_depth, bar_target);
+    prof_mark(a.prof, pslot);
     for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
         const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
-        // slices before this one
-        Tri pre = {0ull, 0ull, 0u};
+        Quad pre = {0ull, 0ull, 0u, 0u};     // slices before this one
         for (uint32_t vv = tid; vv < v; vv += SGS_SORT_THREADS) {
-            pre.kept += __ldcg(a.blocksum + 3 * (size_t)vv);
-            pre.touched += __ldcg(a.blocksum + 3 * (size_t)vv + 1);
-            pre.vis += (uint32_t)__ldcg(a.blocksum + 3 * (size_t)vv + 2);
+            pre.kept += __ldcg(a.blocksum + 4 * (size_t)vv);
+            pre.touched += __ldcg(a.blocksum + 4 * (size_t)vv + 1);
+            pre.vis += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)vv + 2);
+            pre.coarse += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)vv + 3);
         }
+        pre = block_sum(pre, s_w);
+        if (!resident) (void)gather(lo, n);
+        __syncthreads();
+        // block-wide inclusive scan of sm.key[0..n): contiguous segment per thread
+        const uint32_t ipt = (n + SGS_SORT_THREADS - 1) / SGS_SORT_THREADS;
+        const uint32_t b = min(n, tid * ipt), e = min(n, b + ipt);
+        uint32_t mine = 0;
+        for (uint32_t i = b; i < e; i++) mine += sm.key[i];
+        uint32_t inc = mine;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            pre.kept += __shfl_xor_sync(0xFFFFFFFFu, pre.kept, o);
-            pre.touched += __shfl_xor_sync(0xFFFFFFFFu, pre.touched, o);
-            pre.vis += __shfl_xor_sync(0xFFFFFFFFu, pre.vis, o);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        if (lane == 31) sm.wsum[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (uint32_t w = 0; w < warp; w++) woff += sm.wsum[w];
+        uint32_t run = pre.coarse + woff + inc - mine;
+        for (uint32_t i = b; i < e; i++) {
+            run += sm.key[i];
+            sm.val[i] = run;
         }
         __syncthreads();
-        if (lane == 0) s_p[warp] = pre;
-        __syncthreads();
-        Tri base = {0ull, 0ull, 0u};
-        for (uint32_t w = 0; w < 32; w++) base = tri_add(base, s_p[w]);
-
-        Tri ex, tot;
-        uint32_t ipt;
-        slice_scan(lo, n, ex, tot, ipt);
-        unsigned long long run = base.kept + ex.kept;
-        const uint32_t b = lo + tid * ipt, e = min(lo + n, b + ipt);
-        for (uint32_t k = b; k < e; k++) {
-            const uint32_t gid = __ldcg(order + k);
-            const ushort4 r = a.rect_kept[gid];
-            run += (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
-            a.offs[k] = (uint32_t)run;
-        }
+        for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) a.coffs[lo + i] = sm.val[i];
         if (v == VB - 1u && tid == 0) {
-            const Tri all = tri_add(base, tot);
+            Quad all = pre;
+            all.kept += __ldcg(a.blocksum + 4 * (size_t)v);
+            all.touched += __ldcg(a.blocksum + 4 * (size_t)v + 1);
+            all.vis += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)v + 2);
+            all.coarse += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)v + 3);
             a.ctl->kept = all.kept;
             a.ctl->touched = all.touched;
             a.ctl->visible = all.vis;
+            a.ctl->coarse = all.coarse;
             if (a.slot) {
                 volatile HostSlot* hs = a.slot;
                 hs->kept = all.kept;
@@ -433,41 +489,39 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel 2: instance generation + stable sort by tile + tile ranges
+// Kernel 2: (supertile, Gaussian) instance generation + stable bucketing by supertile
 // ------------------------------------------------------------------------------------------------
-struct TileArgs {
+struct CoarseArgs {
     int P;
-    int tiles_x;
-    int n_tiles;
-    int tile_bits;
+    int super_x;      // supertiles per row
+    int n_super;
+    int super_bits;
     int keep;
     unsigned long long cap;
     const uint32_t* order;      // Gaussians in depth order
-    const uint32_t* offs;       // inclusive scan of the kept tile counts, in depth order
+    const uint32_t* coffs;      // inclusive scan of the supertile counts, in depth order
     const ushort4* rect_kept;
     uint32_t* keys[2];
     uint32_t* vals[2];
     uint32_t* hist;
-    uint2* ranges;
+    uint2* cranges;             // [n_super] bucket of every supertile in the coarse list
     uint32_t* header;
     BinCtl* ctl;
     unsigned long long* prof;
 };
 
-using TileSmem = SortSmem<SGS_TILE_ND, SGS_TILE_CHUNK>;
-
-// Fill sm.key / sm.val with the instances [s, e) of the depth-ordered stream: Gaussian k (depth order) owns the
-// instances [offs[k] - area_k, offs[k]), row-major over its kept tile rect.
-__device__ __forceinline__ void generate_slice(TileSmem& sm, const TileArgs& a, uint32_t s, uint32_t e) {
+// Fill sm.key / sm.val with the instances [s, e) of the depth-ordered coarse stream: Gaussian k (depth order) owns
+// the instances [coffs[k] - cc_k, coffs[k]), row-major over the supertiles its kept rect overlaps.
+__device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a, uint32_t s, uint32_t e) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t P = (uint32_t)a.P;
-    // first Gaussian whose inclusive offset exceeds s: 1024-ary search on the monotone offs[]
+    // first Gaussian whose inclusive offset exceeds s: 1024-ary search on the monotone coffs[]
     uint32_t lo = 0, len = P;
     while (len > 1u) {
         const uint32_t step = (len + SGS_SORT_THREADS - 1) / SGS_SORT_THREADS;
         const uint64_t idx = (uint64_t)lo + (uint64_t)(tid + 1u) * step - 1u;
         const bool probe = idx < (uint64_t)lo + len;
-        const int le = (probe && __ldcg(a.offs + idx) <= s) ? 1 : 0;
+        const int le = (probe && __ldcg(a.coffs + idx) <= s) ? 1 : 0;
         const uint32_t c = (uint32_t)__syncthreads_count(le);
         const uint32_t nlo = lo + c * step;
         const uint32_t end = lo + len;
@@ -475,28 +529,27 @@ __device__ __forceinline__ void generate_slice(TileSmem& sm, const TileArgs& a, 
         len = (nlo >= end) ? 0u : min(step, end - nlo);
         if (len == 0u) break;
     }
-    // lo = first Gaussian (in depth order) with offs > s
     for (uint32_t kb = lo;; kb += SGS_SORT_THREADS) {
         const uint32_t k = kb + tid;
         uint32_t n = 0, start = 0, gid = 0;
-        ushort4 r = {0, 0, 0, 0};
+        uint4 sr = make_uint4(0u, 0u, 0u, 0u);
         bool beyond = true;    // this Gaussian's instances end at or after e (nothing more to do past it)
         if (k < P) {
-            const uint32_t incl = __ldcg(a.offs + k);
+            const uint32_t incl = __ldcg(a.coffs + k);
             gid = __ldcg(a.order + k);
-            r = a.rect_kept[gid];
-            n = (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
+            sr = super_rect(a.rect_kept[gid]);
+            n = (sr.y - sr.x) * (sr.w - sr.z);
             start = incl - n;
             beyond = incl >= e;
             if (start >= e) n = 0;
         }
-        const uint32_t w = (uint32_t)(r.y - r.x);
+        const uint32_t w = sr.y - sr.x;
         if (n > 0 && n <= SGS_DUP_SMALL) {
             uint32_t j = start;
-            for (uint32_t y = r.z; y < r.w; y++)
-                for (uint32_t x = r.x; x < r.y; x++, j++)
+            for (uint32_t y = sr.z; y < sr.w; y++)
+                for (uint32_t x = sr.x; x < sr.y; x++, j++)
                     if (j >= s && j < e) {
-                        sm.key[j - s] = y * (uint32_t)a.tiles_x + x;
+                        sm.key[j - s] = y * (uint32_t)a.super_x + x;
                         sm.val[j - s] = gid;
                     }
         }
@@ -507,14 +560,13 @@ __device__ __forceinline__ void generate_slice(TileSmem& sm, const TileArgs& a, 
             const uint32_t sn = __shfl_sync(0xFFFFFFFFu, n, src);
             const uint32_t sstart = __shfl_sync(0xFFFFFFFFu, start, src);
             const uint32_t sgid = __shfl_sync(0xFFFFFFFFu, gid, src);
-            const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.x, src);
-            const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.z, src);
+            const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, sr.x, src);
+            const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, sr.z, src);
             const uint32_t sw = __shfl_sync(0xFFFFFFFFu, w, src);
-            // instances of this Gaussian that fall inside [s, e)
             const uint32_t j0 = max(sstart, s) - sstart, j1 = min(sstart + sn, e) - sstart;
             for (uint32_t i = j0 + lane; i < j1; i += 32) {
                 const uint32_t yy = i / sw, xx = i - yy * sw;
-                sm.key[sstart + i - s] = (sy0 + yy) * (uint32_t)a.tiles_x + (sx0 + xx);
+                sm.key[sstart + i - s] = (sy0 + yy) * (uint32_t)a.super_x + (sx0 + xx);
                 sm.val[sstart + i - s] = sgid;
             }
         }
@@ -523,32 +575,33 @@ __device__ __forceinline__ void generate_slice(TileSmem& sm, const TileArgs& a, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) tile_sort_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const CoarseArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     int pslot = 64;
     prof_mark(a.prof, pslot);
     const unsigned long long kept64 = __ldcg(&a.ctl->kept);
-    const uint32_t npass = (uint32_t)(a.tile_bits + 7) / 8u;
+    const uint32_t Rc = __ldcg(&a.ctl->coarse);
+    const uint32_t npass = (uint32_t)(a.super_bits + 8) / 9u;
     const uint32_t side_final = (npass & 1u) ^ 1u;     // pass p writes side (p - 1) & 1
     if (kept64 > a.cap || kept64 == 0ull) {
         // over capacity: the host re-launches with a larger buffer; nothing may be written beyond the header
+        // (the supertile buckets stay empty, so the expansion kernels and the render kernel see empty tiles)
         if (blockIdx.x == 0 && tid == 0)
             *reinterpret_cast<uint4*>(a.header) = make_uint4(side_final, 0u, (uint32_t)a.keep, (uint32_t)a.cap);
         return;
     }
-    const uint32_t Rk = (uint32_t)kept64;
     if (blockIdx.x == 0 && tid == 0)
-        *reinterpret_cast<uint4*>(a.header) = make_uint4(side_final, Rk, (uint32_t)a.keep, (uint32_t)a.cap);
+        *reinterpret_cast<uint4*>(a.header) = make_uint4(side_final, (uint32_t)kept64, (uint32_t)a.keep, (uint32_t)a.cap);
 
     const uint32_t G = gridDim.x;
-    const uint32_t per_block = (Rk + G - 1) / G;
-    const uint32_t slices_per_block = (per_block + SGS_TILE_CHUNK - 1) / SGS_TILE_CHUNK;
+    const uint32_t per_block = (Rc + G - 1) / G;
+    const uint32_t slices_per_block = (per_block + SGS_SORT_CHUNK - 1) / SGS_SORT_CHUNK;
     const uint32_t VB = G * slices_per_block;
-    const uint32_t SL = (Rk + VB - 1) / VB;
+    const uint32_t SL = (Rc + VB - 1) / VB;
     const bool resident = slices_per_block == 1u;
-    const uint32_t dbits = ((uint32_t)a.tile_bits + npass - 1u) / npass;
+    const uint32_t dbits = ((uint32_t)a.super_bits + npass - 1u) / npass;
     const uint32_t nd = 1u << dbits;
     uint32_t bar_target = 0;
 
@@ -557,6 +610,9 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) tile_sort_kernel(const Ti
         const uint32_t out = (p - 1u) & 1u;
         const uint32_t* in_key = a.keys[out ^ 1u];
         const uint32_t* in_val = a.vals[out ^ 1u];
+        // single-pass sort (digit = supertile id): the keys are dead, the buckets come from the digit totals;
+        // multi-pass: the last pass keeps its keys for coarse_ranges_kernel
+        uint32_t* out_key = (npass == 1u) ? nullptr : a.keys[out];
         auto load = [&](uint32_t lo, uint32_t n) {
             if (p == 1u) {
                 generate_slice(sm, a, lo, lo + n);
@@ -569,54 +625,206 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) tile_sort_kernel(const Ti
             }
         };
         for (uint32_t v = blockIdx.x; v < VB; v += G) {
-            const uint32_t lo = min(Rk, v * SL), hi = min(Rk, lo + SL), n = hi - lo;
+            const uint32_t lo = min(Rc, v * SL), hi = min(Rc, lo + SL), n = hi - lo;
             if (n) load(lo, n);
             prof_mark(a.prof, pslot);
-            rank_slice(sm, n, shift, nd);
+            rank_slice(sm, n, shift, dbits);
             publish_hist(sm.cnt, a.hist, v, nd);
         }
-        { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_tile, bar_target); prof_mark(a.prof, pslot); }
+        prof_mark(a.prof, pslot);
+        grid_barrier(&a.ctl->bar_tile, bar_target);
+        column_scans(a.hist, VB, nd);
+        grid_barrier(&a.ctl->bar_tile, bar_target);
+        prof_mark(a.prof, pslot);
         for (uint32_t v = blockIdx.x; v < VB; v += G) {
-            const uint32_t lo = min(Rk, v * SL), hi = min(Rk, lo + SL), n = hi - lo;
+            const uint32_t lo = min(Rc, v * SL), hi = min(Rc, lo + SL), n = hi - lo;
             if (!resident) {
                 if (n) load(lo, n);
-                rank_slice(sm, n, shift, nd);
+                rank_slice(sm, n, shift, dbits);
             }
             slice_bases(sm, a.hist, v, VB, nd);
-            prof_mark(a.prof, pslot);
-            scatter_slice(sm, n, shift, nd, a.keys[out], a.vals[out]);
+            if (npass == 1u && v == 0u) {
+                for (uint32_t d = tid; d < (uint32_t)a.n_super; d += SGS_SORT_THREADS) {
+                    const uint32_t st = sm.cnt[d];
+                    const uint32_t tot = __ldcg(a.hist + (size_t)VB * nd + d);
+                    a.cranges[d] = tot ? make_uint2(st, st + tot) : make_uint2(0u, 0u);
+                }
+            }
+            scatter_slice(sm, n, shift, nd, out_key, a.vals[out]);
             __syncthreads();
         }
-        { prof_mark(a.prof, pslot); grid_barrier(&a.ctl->bar_tile, bar_target); prof_mark(a.prof, pslot); }
-    }
-
-    // ---- per-tile [start, end) from the sorted tile ids
-    const uint32_t* sorted = a.keys[side_final];
-    for (uint32_t v = blockIdx.x; v < VB; v += G) {
-        const uint32_t lo = min(Rk, v * SL), hi = min(Rk, lo + SL);
-        for (uint32_t i = lo + tid; i < hi; i += SGS_SORT_THREADS) {
-            const uint32_t cur = __ldcg(sorted + i);
-            const uint32_t prev = i ? __ldcg(sorted + i - 1) : 0xFFFFFFFFu;
-            if (cur != prev) {
-                a.ranges[cur].x = i;
-                if (i) a.ranges[prev].y = i;
-            }
-            if (i == Rk - 1u) a.ranges[cur].y = Rk;
-        }
+        prof_mark(a.prof, pslot);
+        if (p < npass) grid_barrier(&a.ctl->bar_tile, bar_target);
     }
     prof_mark(a.prof, pslot);
+}
+
+// multi-pass sorts only (more than 512 supertiles): supertile buckets from the sorted keys, one thread per instance
+__global__ void __launch_bounds__(256) coarse_ranges_kernel(const uint32_t* __restrict__ sorted, const BinCtl* ctl,
+                                                            unsigned long long cap, uint2* __restrict__ cranges) {
+    if (__ldcg(&ctl->kept) > cap) return;
+    const uint32_t Rc = __ldcg(&ctl->coarse);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Rc; i += gridDim.x * blockDim.x) {
+        const uint32_t cur = sorted[i];
+        const uint32_t prev = i ? sorted[i - 1] : 0xFFFFFFFFu;
+        if (cur != prev) {
+            cranges[cur].x = i;
+            if (i) cranges[prev].y = i;
+        }
+        if (i == Rc - 1u) cranges[cur].y = Rc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernels 3a / 3b: expansion of every supertile's depth-ordered list into its 16 per-tile lists
+// ------------------------------------------------------------------------------------------------
+struct ExpandArgs {
+    int tiles_x, tiles_y, super_x, n_tiles;
+    const uint32_t* coarse_list;
+    const uint2* cranges;
+    const ushort4* rect_kept;
+    uint2* ranges;          // [n_tiles]: the count kernel writes .y = count, its last block turns that into [start, end)
+    uint32_t* point_list;
+    uint32_t* done;         // last-block ticket (zero before and after the kernel)
+};
+
+// bit (4 ly + lx) set  <=>  the kept rect covers tile (tx0 + lx, ty0 + ly)
+__device__ __forceinline__ uint32_t tile_mask16(const ushort4 r, uint32_t tx0, uint32_t ty0) {
+    uint32_t xm = 0, ym = 0;
+#pragma unroll
+    for (uint32_t l = 0; l < SGS_ST; l++) {
+        xm |= ((tx0 + l >= r.x) && (tx0 + l < r.y)) ? (1u << l) : 0u;
+        ym |= ((ty0 + l >= r.z) && (ty0 + l < r.w)) ? (1u << l) : 0u;
+    }
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t l = 0; l < SGS_ST; l++) m |= ((ym >> l) & 1u) ? (xm << (4 * l)) : 0u;
+    return m;
+}
+
+__global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const ExpandArgs a) {
+    __shared__ uint32_t s_cnt[16];
+    __shared__ uint32_t s_last;
+    __shared__ uint32_t s_scan[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t s = blockIdx.x;
+    const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    const uint2 cr = a.cranges[s];
+    if (tid < 16) s_cnt[tid] = 0;
+    __syncthreads();
+    uint32_t mine = 0;   // lane t < 16 of every warp accumulates tile t
+    for (uint32_t i0 = cr.x + (tid & ~31u); i0 < cr.y; i0 += SGS_EXP_THREADS) {
+        const uint32_t i = i0 + lane;
+        uint32_t m = 0;
+        if (i < cr.y) m = tile_mask16(a.rect_kept[__ldcg(a.coarse_list + i)], tx0, ty0);
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) {
+            const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, (m >> t) & 1u));
+            if (lane == t) mine += c;
+        }
+    }
+    if (lane < 16 && mine) atomicAdd(&s_cnt[lane], mine);
+    __syncthreads();
+    if (tid < 16) {
+        const uint32_t tx = tx0 + (tid & 3u), ty = ty0 + (tid >> 2);
+        if (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) a.ranges[ty * a.tiles_x + tx].y = s_cnt[tid];
+    }
+    // the last block to finish turns the counts into [start, end) ranges (exclusive scan over the tile ids)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t n = (uint32_t)a.n_tiles;
+    const uint32_t ipt = (n + SGS_EXP_THREADS - 1) / SGS_EXP_THREADS;
+    const uint32_t b = min(n, tid * ipt), e = min(n, b + ipt);
+    uint32_t sum = 0;
+    for (uint32_t t = b; t < e; t++) sum += __ldcg(&a.ranges[t].y);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    if (lane == 31) s_scan[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < (tid >> 5); w++) woff += s_scan[w];
+    uint32_t run = woff + inc - sum;
+    for (uint32_t t = b; t < e; t++) {
+        const uint32_t c = __ldcg(&a.ranges[t].y);
+        a.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+        run += c;
+    }
+    if (tid == 0) *a.done = 0u;
+}
+
+__global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const ExpandArgs a) {
+    constexpr int NW = SGS_EXP_THREADS / 32;
+    __shared__ uint32_t s_wc[16][NW];     // per chunk: instances of tile t found by warp w
+    __shared__ uint32_t s_run[16];        // next free position of every tile list
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s = blockIdx.x;
+    const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    const uint2 cr = a.cranges[s];
+    if (cr.y == cr.x) return;
+    if (tid < 16) {
+        const uint32_t tx = tx0 + (tid & 3u), ty = ty0 + (tid >> 2);
+        s_run[tid] = (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) ? a.ranges[ty * a.tiles_x + tx].x : 0u;
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t i0 = cr.x; i0 < cr.y; i0 += SGS_EXP_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint32_t m = 0, gid = 0;
+        if (i < cr.y) {
+            gid = __ldcg(a.coarse_list + i);
+            m = tile_mask16(a.rect_kept[gid], tx0, ty0);
+        }
+        uint32_t before[16];
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (m >> t) & 1u);
+            before[t] = __popc(bal & lt_mask);
+            if (lane == t) s_wc[t][warp] = __popc(bal);
+        }
+        __syncthreads();   // also: s_run of the previous chunk is final
+        // lane t < 16: this warp's offset in the list of tile t
+        uint32_t myoff = 0, total = 0;
+        if (lane < 16) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const uint32_t c = s_wc[lane][w];
+                if ((uint32_t)w < warp) myoff += c;
+                total += c;
+            }
+            myoff += s_run[lane];
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) {
+            const uint32_t off = __shfl_sync(0xFFFFFFFFu, myoff, t);
+            if ((m >> t) & 1u) a.point_list[off + before[t]] = gid;
+        }
+        __syncthreads();   // every warp has read s_wc / s_run of this chunk
+        if (warp == 0 && lane < 16) s_run[lane] += total;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-static int bits_for_tiles(int n_tiles) {
+static int bits_for(int n) {
     int b = 1;
-    while ((1 << b) < n_tiles) b++;
+    while ((1 << b) < n) b++;
     return b;
 }
-int binning_tile_bits(int n_tiles) { return bits_for_tiles(n_tiles); }
-int binning_point_list_side(int n_tiles) { return (((bits_for_tiles(n_tiles) + 7) / 8) & 1) ^ 1; }
+int binning_supertiles(int tiles_x, int tiles_y, int* super_x) {
+    const int sx = (tiles_x + SGS_ST - 1) / SGS_ST, sy = (tiles_y + SGS_ST - 1) / SGS_ST;
+    if (super_x) *super_x = sx;
+    return sx * sy;
+}
+static int coarse_passes(int n_super) { return (bits_for(n_super) + 8) / 9; }
+int binning_coarse_list_side(int n_super) { return (coarse_passes(n_super) & 1) ^ 1; }
 
 static unsigned long long* g_prof_host = nullptr;   // 128 timestamps, pinned + mapped; allocated by binning_profile()
 unsigned long long* binning_profile(bool enable) {
@@ -630,7 +838,10 @@ unsigned long long* binning_profile(bool enable) {
     return g_prof_host;
 }
 static bool g_prof_on = false;
-void binning_profile_enable(bool on) { g_prof_on = on; if (on) binning_profile(true); }
+void binning_profile_enable(bool on) {
+    g_prof_on = on;
+    if (on) binning_profile(true);
+}
 
 int binning_grid_blocks() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -639,29 +850,24 @@ int binning_grid_blocks() {
     if (dev != cached_dev) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DepthSmem));
-        cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+        cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        cudaFuncSetAttribute(coarse_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cached = sms;
         cached_dev = dev;
     }
     return cached;
 }
 
-int binning_depth_vblocks(int P) {
-    const int G = binning_grid_blocks();
-    if (G <= 0) return 0;
-    const long per_block = ((long)P + G - 1) / G;
-    const long slices = per_block > 0 ? (per_block + SGS_DEPTH_CHUNK - 1) / SGS_DEPTH_CHUNK : 1;
-    return (int)(G * (slices > 0 ? slices : 1));
-}
-
-size_t binning_tile_hist_words(size_t cap) {
+static int vblocks_for(size_t n) {
     const size_t G = (size_t)binning_grid_blocks();
-    const size_t per_block = (cap + G - 1) / (G ? G : 1);
-    size_t slices = (per_block + SGS_TILE_CHUNK - 1) / SGS_TILE_CHUNK;
+    if (G == 0) return 0;
+    const size_t per_block = (n + G - 1) / G;
+    size_t slices = (per_block + SGS_SORT_CHUNK - 1) / SGS_SORT_CHUNK;
     if (slices == 0) slices = 1;
-    return G * slices * SGS_TILE_ND;
+    return (int)(G * slices);
 }
+int binning_depth_vblocks(int P) { return vblocks_for((size_t)P); }
+size_t binning_hist_words(size_t n) { return ((size_t)vblocks_for(n) + 1) * SGS_SORT_ND; }
 
 cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s) {
     const int G = binning_grid_blocks();
@@ -677,7 +883,7 @@ cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long 
     a.vals[1] = g.depth_vals[1];
     a.rect_kept = g.rect_kept;
     a.tiles_touched = g.tiles_touched;
-    a.offs = g.offs;
+    a.coffs = g.coffs;
     a.hist = g.hist;
     a.blocksum = g.blocksum;
     a.ctl = g.ctl;
@@ -686,35 +892,52 @@ cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long 
     a.prof = g_prof_on ? g_prof_host : nullptr;
     void* args[] = {&a};
     return cudaLaunchCooperativeKernel((const void*)depth_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
-                                       sizeof(DepthSmem), s);
+                                       sizeof(SortSmem), s);
 }
 
-cudaError_t launch_tile_sort(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
-                             cudaStream_t s) {
+cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                                cudaStream_t s) {
     const int G = binning_grid_blocks();
     if (G <= 0) return cudaErrorInvalidDevice;
-    TileArgs a;
+    CoarseArgs a;
     a.P = P;
-    a.tiles_x = vp.tiles_x;
-    a.n_tiles = vp.tiles_x * vp.tiles_y;
-    a.tile_bits = bits_for_tiles(a.n_tiles);
+    a.n_super = binning_supertiles(vp.tiles_x, vp.tiles_y, &a.super_x);
+    a.super_bits = bits_for(a.n_super);
     a.keep = keep;
     a.cap = (unsigned long long)b.cap;
     a.order = g.depth_vals[0];
-    a.offs = g.offs;
+    a.coffs = g.coffs;
     a.rect_kept = g.rect_kept;
-    a.keys[0] = b.tile_keys[0];
-    a.keys[1] = b.tile_keys[1];
-    a.vals[0] = b.gauss_vals[0];
-    a.vals[1] = b.gauss_vals[1];
+    a.keys[0] = b.coarse_keys[0];
+    a.keys[1] = b.coarse_keys[1];
+    a.vals[0] = b.coarse_vals[0];
+    a.vals[1] = b.coarse_vals[1];
     a.hist = b.hist;
-    a.ranges = img.ranges;
+    a.cranges = img.cranges;
     a.header = b.header;
     a.ctl = g.ctl;
     a.prof = g_prof_on ? g_prof_host : nullptr;
+    const int side = binning_coarse_list_side(a.n_super);
     void* args[] = {&a};
-    return cudaLaunchCooperativeKernel((const void*)tile_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
-                                       sizeof(TileSmem), s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)coarse_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
+                                                sizeof(SortSmem), s);
+    if (e != cudaSuccess) return e;
+    if (coarse_passes(a.n_super) > 1)
+        coarse_ranges_kernel<<<4 * G, 256, 0, s>>>(b.coarse_keys[side], g.ctl, a.cap, img.cranges);
+    ExpandArgs x;
+    x.tiles_x = vp.tiles_x;
+    x.tiles_y = vp.tiles_y;
+    x.super_x = a.super_x;
+    x.n_tiles = vp.tiles_x * vp.tiles_y;
+    x.coarse_list = b.coarse_vals[side];
+    x.cranges = img.cranges;
+    x.rect_kept = g.rect_kept;
+    x.ranges = img.ranges;
+    x.point_list = b.point_list;
+    x.done = &g.ctl->expand_done;
+    tile_count_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
+    tile_fill_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
+    return cudaGetLastError();
 }
 
 }  // namespace sgs

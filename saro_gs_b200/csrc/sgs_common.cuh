@@ -82,7 +82,9 @@ struct BinCtl {
     unsigned long long kept;      // instances to bin: sum of area(rect_kept)
     unsigned long long touched;   // the reference's num_rendered: sum of tiles_touched
     uint32_t visible;     // Gaussians with radii > 0
-    uint32_t pad[23];
+    uint32_t coarse;      // (supertile, Gaussian) instances: sum over Gaussians of the supertiles their kept rect overlaps
+    uint32_t expand_done; // last-block ticket of tile_count_kernel (self-resetting)
+    uint32_t pad[21];
 };
 static_assert(sizeof(BinCtl) == 128, "BinCtl must be 128 bytes");
 
@@ -114,10 +116,10 @@ struct GeomState {
     uint32_t* depth_raw;      // [P]   float bits of depth (0xFFFFFFFF when culled), written by preprocess
     uint32_t* depth_keys[2];  // [P]   radix-sort ping-pong: normalised keys
     uint32_t* depth_vals[2];  // [P]   radix-sort ping-pong: Gaussian index; [0] ends up holding the depth order
-    uint32_t* offs;           // [P]   inclusive scan, in depth order, of area(rect_kept)
+    uint32_t* coffs;          // [P]   inclusive scan, in depth order, of the supertiles each kept rect overlaps
     BinCtl*   ctl;            // control block (see above)
-    uint32_t* hist;           // [depth_vblocks][512] per-block digit histograms of the current radix pass
-    unsigned long long* blocksum;  // [depth_vblocks][3] per-block (kept, touched, visible) of the scan
+    uint32_t* hist;           // [depth_vblocks + 1][512] per-block digit histograms of the current radix pass
+    unsigned long long* blocksum;  // [depth_vblocks][4] per-block (kept, touched, visible, coarse) of the scan
     int       depth_vblocks;  // virtual blocks of the depth sort (multiple of the grid size)
 };
 
@@ -127,6 +129,7 @@ struct ImageState {
     uint32_t* n_contrib;   // [W*H]  1-based list position of last blended instance (original list index)
     uint2*    ranges;      // [tiles] [start, end) into the sorted instance list
     uint32_t* tile_count;  // [tiles] number of packed (tile-culled) records written by forward render
+    uint2*    cranges;     // [supertiles] [start, end) of every 4x4-tile supertile in the coarse list
 };
 
 // One packed, tile-ordered instance record (48 B, 16-B aligned) written by the forward
@@ -143,12 +146,12 @@ static_assert(sizeof(PackedInst) == 48, "PackedInst must be 48 bytes");
 // Opaque "binning" state: per tile instance.  Replaces BinningState ($R/.../rasterizer_impl.h:59-69).
 // Sized for `cap` instances (a prediction from the previous frame); the kernels read the true count from BinCtl.
 struct BinningState {
-    uint32_t*   tile_keys[2];   // [cap] tile id; radix-sort ping-pong
-    uint32_t*   gauss_vals[2];  // [cap] Gaussian index; radix-sort ping-pong
+    uint32_t*   header;         // [32] word 1: kept instances; 2: packed records present; 3: cap
     PackedInst* packed;         // [cap] tile-ordered packed records (tile t uses [ranges[t].x, +tile_count[t]))
-    uint32_t*   hist;           // [tile_vblocks(cap)][256] per-block digit histograms of the current radix pass
-    uint32_t*   header;         // [32] word 0: which ping-pong side holds point_list; 1: kept instances;
-                                //      2: packed records present; 3: cap
+    uint32_t*   point_list;     // [cap] Gaussian index of every kept instance, tile-major, depth order inside a tile
+    uint32_t*   coarse_keys[2]; // [cap] supertile id; radix-sort ping-pong (only touched when > 512 supertiles)
+    uint32_t*   coarse_vals[2]; // [cap] Gaussian index; one side ends up holding the supertile-major coarse list
+    uint32_t*   hist;           // per-block digit histograms of the coarse radix pass
     size_t      cap;
 };
 
@@ -243,21 +246,22 @@ void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, co
                            const float* cov3D_precomp, const float* colors_precomp, int* radii,
                            GeomState g, uint32_t* zero_words, size_t n_zero, int cull, cudaStream_t s);
 
-// Binning (sgs_binning.cu): two cooperative persistent kernels, no host-visible sizes in between.
-//   depth_sort: stable LSD radix sort of the P depth keys + scan of area(rect_kept) in depth order; reports
-//               (kept, touched, visible) to `slot` (pinned host memory) under `ticket`.
-//   tile_sort : emits the (tile, Gaussian) instances in depth order, stable radix sort by tile id, tile ranges,
-//               binning header.  Does nothing when kept > b.cap (the host then re-launches it with a larger buffer).
+// Binning (sgs_binning.cu): no host-visible sizes between the stages.
+//   depth_sort  : persistent kernel; stable radix sort of the P depth keys + scan of the supertile counts in depth
+//                 order; reports (kept, touched, visible) to `slot` (pinned host memory) under `ticket`.
+//   tile_binning: persistent kernel bucketing the (supertile, Gaussian) stream + two expansion kernels that write
+//                 the per-tile lists and ranges.  Writes nothing when kept > b.cap (the host then re-launches it
+//                 with a larger buffer).
 unsigned long long* binning_profile(bool enable);   // developer aid: pinned buffer of 128 phase timestamps (ns)
 void   binning_profile_enable(bool on);
 int    binning_grid_blocks();                       // co-resident blocks of the persistent kernels (= #SMs)
 int    binning_depth_vblocks(int P);
-size_t binning_tile_hist_words(size_t cap);
-int    binning_tile_bits(int n_tiles);
-int    binning_point_list_side(int n_tiles);        // ping-pong side that ends up holding the sorted lists
+size_t binning_hist_words(size_t n);
+int    binning_supertiles(int tiles_x, int tiles_y, int* super_x);
+int    binning_coarse_list_side(int n_super);
 cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s);
-cudaError_t launch_tile_sort(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
-                             cudaStream_t s);
+cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                                cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,

@@ -62,19 +62,38 @@ def mean_metrics(total: torch.Tensor) -> List[float]:
     return [float(v) / n for v in total[:-1]]
 
 
-def allreduce_batch_gradients(params: Iterable[torch.Tensor], batch: int, group=None, bucket_bytes: int = 64 << 20) -> int:
+def allreduce_batch_gradients(params: Iterable[torch.Tensor], batch: int, group=None, bucket_bytes: int = 64 << 20,
+                              check_layout: bool = True) -> int:
     """Distributed form of the reference's batch-gradient cache (scene/saro_gaussian.py:224-294): the reference sums
     every parameter's gradient over the views of a batch (`cache_gradient`, :224-245) and hands the optimizer
     `sum * (1 / batch)` (`set_batch_gradient`, :263-294).  With one view per rank the sum over views is a SUM
     all-reduce; gradients are packed into flat buckets (per dtype, <= bucket_bytes) so that ~25 small tensors and the
     75 MB of per-Gaussian gradients cost a handful of collectives, then scaled by 1 / batch exactly as the reference
-    does (a multiplication by the reciprocal, not a division).  Parameters without a gradient are skipped on every
-    rank alike.  Returns the number of collectives issued; a no-op (scale only) when not distributed."""
+    does (a multiplication by the reciprocal, not a division).
+
+    The bucket layout is derived from the PARAMETERS, never from which of them happen to hold a gradient on this rank:
+    a parameter that requires a gradient but received none (its view saw nothing of it) contributes zeros, so every
+    rank builds the same buckets.  With `check_layout` one extra 2-element MAX all-reduce verifies that all ranks
+    agree on the number of gradient elements (replicated Gaussians can drift apart if ranks densify differently) and
+    raises instead of summing misaligned gradients.  Returns the number of data collectives issued; a no-op (scale
+    only) when not distributed."""
     import torch.distributed as dist
-    grads = [p.grad for p in params if p.grad is not None]
+    params = [p for p in params if p.requires_grad or p.grad is not None]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     ratio = 1 / batch
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     collectives = 0
+    if distributed and check_layout and grads:
+        n = float(sum(g.numel() for g in grads))
+        sig = torch.tensor([n, -n], dtype=torch.float64, device=grads[0].device)
+        dist.all_reduce(sig, op=dist.ReduceOp.MAX, group=group)
+        if float(sig[0]) != n or float(sig[1]) != -n:
+            raise RuntimeError("allreduce_batch_gradients: ranks disagree on the gradient layout "
+                               f"({int(n)} elements here, between {int(-float(sig[1]))} and {int(float(sig[0]))} elsewhere): "
+                               "the replicated Gaussians have diverged")
     by_type = {}
     for g in grads:
         by_type.setdefault((g.dtype, g.device), []).append(g)

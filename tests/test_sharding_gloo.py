@@ -68,7 +68,8 @@ def _grad_worker(rank, world, port, q):
     params, grads = _make_params(100 + rank)               # this rank's view
     for p, g in zip(params, grads):
         p.grad = g.clone()
-    params[3].grad = None                                   # a parameter without gradient is skipped everywhere
+    if rank == 1:
+        params[3].grad = None                               # no gradient on ONE rank only: must contribute zeros
     n = allreduce_batch_gradients(params, batch=world, bucket_bytes=40_000)      # small buckets: several collectives
     q.put((rank, n, [None if p.grad is None else p.grad.clone() for p in params]))
     dist.barrier()
@@ -93,13 +94,41 @@ def test_gradient_allreduce_equals_the_reference_batch_cache():
     for _, n_coll, got in res:
         assert n_coll > 1
         for i, g in enumerate(got):
-            if i == 3:
-                assert g is None
-                continue
             cache = torch.zeros_like(views[0][i])
-            for v in views:
-                cache += v[i].clone()                       # cache_gradient
+            for r, v in enumerate(views):
+                if not (i == 3 and r == 1):                 # rank 1 had no gradient for parameter 3
+                    cache += v[i].clone()                   # cache_gradient
             assert torch.equal(g, cache * ratio)            # set_batch_gradient
+
+
+def _mismatch_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1000 if rank == 0 else 1001                         # the replicated Gaussians have diverged
+    p = torch.nn.Parameter(torch.zeros(n, 3))
+    p.grad = torch.ones(n, 3)
+    try:
+        allreduce_batch_gradients([p], batch=world)
+        q.put((rank, "no error"))
+    except RuntimeError as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_diverged_layouts_raise_instead_of_summing_misaligned_gradients():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mismatch_worker, args=(r, world, 29551, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, msg in res:
+        assert "disagree on the gradient layout" in msg
 
 
 def test_gradient_scale_without_process_group():
