@@ -216,6 +216,46 @@ int sgs_densify_add_view(int P, const float* dL_dmeans2D, const int* radii, floa
 int sgs_densify_commit(int P, const float* grad_sum, const int* vis_count, const int* radii_max, float* max_radii2D,
                        float* xyz_gradient_accum, float* denom, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Scale-aware plane sampler — replaces ScaleAwareResField.forward of the reference
+ * (scene/hexplane.py:258-286: normalize_aabb / normalize_time, get_level :231-242, interpolate_ms_features :91-137,
+ * grid_sample_wrapper :26-60) including the third-party op it calls,
+ *   nvdiffrast.torch.texture(tex, uv, mip_level_bias = min level of the plane's two axes, boundary_mode = "clamp",
+ *                            max_mip_level = 7 for the three space planes, 0 for the three time planes),
+ * rebuilt from its published algorithm (linear-mipmap-linear at an explicit level, texel centres at half-integers,
+ * clamp-to-edge, 2x2 box mip stack; extents must be even at every level that is built).
+ *
+ * A plane is an nn.Parameter [1][C][H][W] (W follows coordinate dim_u, H follows dim_v; 0 x, 1 y, 2 z, 3 t).
+ *   sgs_plane_levels / sgs_plane_pyramid_floats: mip levels (1..8) and floats of the channels-last pyramid of a plane.
+ *   sgs_plane_build: NCHW parameter -> channels-last mip pyramid (run when the parameter changed, not per call).
+ *   sgs_plane_sample_forward: out[n][out_offset + c] = sum over the n_planes planes of the sample at point n, for
+ *     c < C; pts [N][3], timestamps [N], scales [N][3] (activated), aabb [2][3] (row 0 = xyz_max, row 1 = xyz_min) and
+ *     base_scale [3] are DEVICE pointers (the module's buffers), time_scale = duration / (duration - 1), reso0 = HOST
+ *     int[3], resolution of the coarsest grid; `planes` is a HOST array.  One call per resolution level of the field.
+ *   sgs_plane_sample_backward: scatters w * dout[n][out_offset + c] into the GRADIENT pyramids (same layout, must be
+ *     zero-initialised by the caller) given as `grad_planes`; positions and scales carry no gradient (the reference
+ *     samples at detached inputs, scene/saro_gaussian.py:765,780,865).
+ *   sgs_plane_fold: gradient pyramid -> dL/dplane [1][C][H][W] (fully written).
+ * C must be a power of two below 32 or a multiple of 32 (and C * 132 bytes of shared memory <= 48 KB). */
+typedef struct {
+    float* pyramid;      /* device: channels-last levels, level l at the offset of all levels before it */
+    int H, W;
+    int dim_u, dim_v;
+    int max_mip_level;   /* 7 or 0 in the reference */
+} sgs_plane_t;
+int sgs_plane_levels(int H, int W, int max_mip_level);
+size_t sgs_plane_pyramid_floats(int C, int H, int W, int max_mip_level);
+int sgs_plane_build(int C, int H, int W, int max_mip_level, const float* plane_nchw, float* pyramid, void* stream);
+int sgs_plane_sample_forward(int N, int C, const float* pts, const float* timestamps, const float* scales,
+                             const float* aabb, const float* base_scale, float time_scale, const int* reso0,
+                             int n_planes, const sgs_plane_t* planes, int out_stride, int out_offset, float* out,
+                             void* stream);
+int sgs_plane_sample_backward(int N, int C, const float* pts, const float* timestamps, const float* scales,
+                              const float* aabb, const float* base_scale, float time_scale, const int* reso0,
+                              int n_planes, const sgs_plane_t* grad_planes, int out_stride, int out_offset,
+                              const float* dout, void* stream);
+int sgs_plane_fold(int C, int H, int W, int max_mip_level, const float* grad_pyramid, float* dplane_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

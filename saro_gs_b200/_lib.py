@@ -49,12 +49,26 @@ ABI = {
     "sgs_deform_eval": (_i64, [_i, _i, _f] + [_vp] * 10 + [_vp, ctypes.c_size_t] + [_vp] * 5 + [_vp]),
     "sgs_densify_add_view": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_densify_commit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_plane_levels": (_i, [_i, _i, _i]),
+    "sgs_plane_pyramid_floats": (ctypes.c_size_t, [_i, _i, _i, _i]),
+    "sgs_plane_build": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    "sgs_plane_sample_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "sgs_plane_sample_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "sgs_plane_fold": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "sgs_profile_enable": (None, [_i]),
     "sgs_profile_read": (_i, [_vp, _vp, _vp]),
 }
 
 STAGES = ["preprocess_fwd", "depth_sort_scan", "duplicate", "tile_sort", "tile_ranges", "render_fwd", "bwd_zero",
           "render_bwd", "preprocess_bwd"]
+
+
+
+class PlaneDesc(ctypes.Structure):
+    """sgs_plane_t of include/saro_gs_b200.h"""
+    _fields_ = [("pyramid", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int), ("dim_u", ctypes.c_int),
+                ("dim_v", ctypes.c_int), ("max_mip_level", ctypes.c_int)]
+
 
 _lib = None
 

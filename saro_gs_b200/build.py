@@ -24,6 +24,7 @@ SOURCES = [
     "sgs_loss.cu",
     "sgs_deform.cu",
     "sgs_densify.cu",
+    "sgs_plane.cu",
 ]
 # every header a translation unit may include feeds the per-object rebuild digest (a stale object after a header edit
 # would let two kernels disagree on a shared record layout)
