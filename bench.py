@@ -16,14 +16,21 @@ Timed numbers:
                         on the launching stream; L2 flushed (256 MiB memset) between steps,
                         outside the event pairs.
   e2e                 : the same step through the same API, but every step first copies the
-                        per-view inputs (camera matrices, background, dL/dcolor image) from pinned
-                        host memory and ends with a device->host read of the rendered image and a
-                        gradient checksum.  The Gaussian parameters stay resident: the reference
-                        API only accepts CUDA tensors for them.
+                        per-view inputs (camera matrices, background, the 16 MB dL/dcolor image) from
+                        pinned host memory and ends with a device->host read of 8 bytes: a loss-like
+                        scalar of the rendered image and a gradient checksum (the image itself stays on
+                        the device, as in training).  The Gaussian parameters stay resident: the
+                        reference API only accepts CUDA tensors for them.
   roofline            : dominant kernel (backward render) — algorithmic bytes / CUDA-event duration
                         measured by the library's stage profiler over a second pass of the same K steps
-                        (the headline pass runs without the ~20 extra event records per step).
-  cpu_baseline        : CPU oracle port (oracle/, float32, OpenMP) on one forward+backward.
+                        (the headline pass runs without the extra event records).  V, R and the kept
+                        instance count come from the library (sgs_last_forward_counts), the ncu traffic /
+                        instruction figures from the profiles/*.csv named in the object.  `hbm_stages`
+                        adds the same figure for every HBM-bound stage; the worst is named.
+  forward_only        : inference render, back to back; `sequence` = BASELINE configs[2] protocol
+                        (300 frames, 4 passes, frames with index <= 10 dropped, test.py:155-163).
+  cpu_baseline        : CPU oracle port (oracle/, float32, OpenMP) on one forward+backward, plus the
+                        configs[0] case (10 k Gaussians @400x400, forward only) on the same cores.
 
 --impl reference times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, compiled from
 /root/reference by oracle/build_ref.py) through the identical host layer, same config/metric.
@@ -102,10 +109,11 @@ class ClockSampler(threading.Thread):
 def make_inputs(dev, rank):
     from saro_gs_b200 import synthetic
     scene, cam0 = synthetic.config2_scene()
-    # every rank renders its own views of the replicated scene (config 5 arc around the cloud)
-    cams = [synthetic.yaw_camera(cam0.width, cam0.height, 729.0, yaw=0.004 * (k + 4 * rank), pivot=(0.0, 0.0, 22.0))
+    # every rank renders the SAME four views of the replicated scene: the weak-scaling number then measures the
+    # system, not a per-rank difference in workload (round 1 gave every rank its own cameras)
+    cams = [synthetic.yaw_camera(cam0.width, cam0.height, 729.0, yaw=0.004 * k, pivot=(0.0, 0.0, 22.0))
             for k in range(4)]
-    cams[0] = cam0 if rank == 0 else cams[0]
+    cams[0] = cam0
     params = {k: getattr(scene, k).to(dev).requires_grad_(True)
               for k in ("means3D", "scales", "rotations", "opacities", "shs")}
     cot = synthetic.cotangent(cam0.height, cam0.width)
@@ -150,14 +158,21 @@ def run_native_or_ref(args, impl):
         for p in list(params.values()) + [means2D]:
             p.grad = None
 
+    counts_log = []          # (kept, num_rendered, visible) of every step of the profiled pass
+
     def step_resident(i):
         c = cams[i % len(cams)]
         v, p, cp = cams_dev[i % len(cams)]
         rs = Settings(H, W, c.tanfovx, c.tanfovy, bg_dev, 1.0, v, p, scene.sh_degree, cp, False)
         color, radii, depth = Rast(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                                        shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        if step_resident.log_counts:
+            c5 = (ctypes.c_int64 * 5)()
+            _lib.load().sgs_last_forward_counts(c5)      # no synchronisation: read during the forward call
+            counts_log.append((int(c5[0]), int(c5[1]), int(c5[2]), int(c5[4])))
         color.backward(cot_dev)
         zero_grads()
+    step_resident.log_counts = False
 
     # e2e leg = one training-style step through the public API with HOST inputs: the per-view inputs (camera,
     # background and the 16 MB dL/dcolor image — the stand-in for the ground-truth image a training step uploads)
@@ -217,7 +232,9 @@ def run_native_or_ref(args, impl):
             evs.append((e0, e1))
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        dev_ms = sum(per_step)
+        timed.last_per_step = per_step
         stage = None
         if profile:
             ms = (ctypes.c_float * len(_lib.STAGES))()
@@ -243,17 +260,68 @@ def run_native_or_ref(args, impl):
             Rast(rs)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"], shs=params["shs"],
                      scales=params["scales"], rotations=params["rotations"])
 
+    def sequence_fps(frames=300, passes=4):
+        """BASELINE.json configs[2] protocol (test.py:155-163 of the reference): `passes` passes over a `frames`-frame
+        sequence of the cloud (alive set changes per frame, synthetic.DeviceSequence), one synchronised render per
+        frame, frames with index <= 10 of every pass dropped, mean of the rest.  CUDA events around the rasterizer call
+        (the reference's wall clock also covers its PyTorch deformation ops, which are not on this path)."""
+        from saro_gs_b200 import synthetic
+        seq = synthetic.DeviceSequence(scene, dev)
+        c = cams[0]
+        v, p, cp = cams_dev[0]
+        rs = Settings(H, W, c.tanfovx, c.tanfovy, bg_dev, 1.0, v, p, scene.sh_degree, cp, False)
+        rast = Rast(rs)
+        times = []
+        with torch.no_grad():
+            for _ in range(passes):
+                for idx in range(frames):
+                    sc = seq.frame(idx / frames)
+                    m2 = torch.zeros_like(sc.means3D)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rast(means3D=sc.means3D, means2D=m2, opacities=sc.opacities, shs=sc.shs, scales=sc.scales,
+                         rotations=sc.rotations)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if idx > 10:
+                        times.append(e0.elapsed_time(e1))
+        mean_ms = sum(times) / len(times)
+        return {"frames": frames, "passes": passes, "timed_frames": len(times), "ms_per_frame": mean_ms,
+                "frames_per_s": 1e3 / mean_ms,
+                "protocol": "test.py:155-163 of the reference: 4 passes, frames with index <= 10 dropped, one "
+                            "synchronised render per frame (launch latency included on both arms)"}
+
     K, W_ = args.steps, max(3, args.warmup)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None      # one nvidia-smi sampler per node, not one per rank
+    if sampler:
+        sampler.start()
     dev_ms, wall_ms, stage = timed(step_resident, K, W_, profile=False)
+    per_step_headline = list(timed.last_per_step)
     if impl != "reference":
         # the same K steps again with the library's per-stage CUDA events switched on: the per-kernel durations
         # behind `roofline` (kept out of the headline pass: ~20 extra event records per step cost host time)
+        step_resident.log_counts = True
         prof_ms, _, stage = timed(step_resident, K, 3, profile=True)
+        step_resident.log_counts = False
+        del counts_log[:3]                                # the 3 warm-up steps of that pass
     e2e_ms, _, _ = timed(step_e2e, K, W_)
     fwd_ms, _, _ = timed(step_forward_only, K, 3)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
+    seq = sequence_fps() if (rank == 0 and not args.no_sequence) else None
+
+    # per-rank view of the headline pass: min / median / max step time and the instance counts every rank saw
+    counts = (ctypes.c_int64 * 5)()
+    if impl != "reference":
+        _lib.load().sgs_last_forward_counts(counts)
+    ps = sorted(per_step_headline)
+    mine = {"rank": rank, "min_ms": ps[0], "median_ms": ps[len(ps) // 2], "max_ms": ps[-1],
+            "kept": int(counts[0]), "num_rendered": int(counts[1])}
+    rank_stats = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        rank_stats = [None] * world
+        dist.all_gather_object(rank_stats, mine)
 
     ms_per_step = dev_ms / K
     value = dev_ms / (K * world)
@@ -272,8 +340,9 @@ def run_native_or_ref(args, impl):
                         "(same code for both arms)"},
         "clocks": clocks, "wall_ms_timed_region": wall_ms,
         "forward_only": {"ms_per_frame": fwd_ms / (K * world), "frames_per_s": 1e3 * K * world / fwd_ms,
-                         "note": "inference render of the same views (no_grad), inputs resident; BASELINE.json "
-                                 "configs[2] reports FPS with this protocol"},
+                         "note": "inference render of the same views (no_grad), inputs resident, back to back",
+                         "sequence": seq},
+        "per_rank": rank_stats,
     }
     if impl == "reference":
         line["impl"] = "reference"
@@ -290,35 +359,65 @@ def run_native_or_ref(args, impl):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        Rn = 3927052
-        T = ((W + 15) // 16) * ((H + 15) // 16)
-        V = 253700
+        clocks = clocks or {}
         P = params["means3D"].shape[0]
-        # SURVEY.md §8d algorithmic bytes of the backward render kernel
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        # instance counts measured by the library during the profiled pass (mean over its steps / cameras)
+        nlog = max(1, len(counts_log))
+        Rk = sum(c[0] for c in counts_log) / nlog         # kept instances: binned, sorted, rendered
+        Rn = sum(c[1] for c in counts_log) / nlog         # num_rendered as the reference counts it
+        V = sum(c[2] for c in counts_log) / nlog          # visible Gaussians
+        relaunches = sum(c[3] for c in counts_log)
+        # SURVEY.md section 8(d) algorithmic bytes of the backward render kernel (the reference's instance count)
         alg = 8 * T + 40 * Rn + 20 * H * W + 44 * V + 44 * P
         calls = max(1, stage["calls"]["render_bwd"])
         k_ms = stage["ms"]["render_bwd"] / calls
         achieved = alg / (k_ms * 1e-3) / 1e9
-        # measured once per round with `ncu --set full` on this exact workload (profiles/r02f_render_ncu_summary.csv)
-        NCU_TRAFFIC_BYTES = 93_804_544        # dram__bytes_read.sum + dram__bytes_write.sum of one launch
-        NCU_WARP_INSTRUCTIONS = 349_131_307   # smsp__inst_executed.sum of one launch
+        ncu = load_ncu_summary("render_bwd_kernel")
         sm_mhz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
         issue_peak = 148 * 4 * sm_mhz * 1e6   # one warp-instruction per SM sub-partition per clock
         line["roofline"] = {"kernel": "render_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": ncu.get("traffic_bytes"),
+                            "traffic_source": ncu.get("file"),
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                            "counts": {"P": P, "visible": V, "num_rendered": Rn, "kept": Rk, "tiles": T,
+                                       "source": "sgs_last_forward_counts, mean over the profiled pass"},
                             "avg_launch_ms": k_ms,
                             "note": "reported against HBM as the contract asks, but this kernel is instruction-issue "
-                                    "bound (ncu: issue-active 85 %, DRAM 1.7 %): ~95 blended pixel x Gaussian pairs "
-                                    "are evaluated per 48-byte record (DESIGN.md section 3); see `issue`",
-                            "issue": {"warp_instructions_per_launch": NCU_WARP_INSTRUCTIONS,
-                                      "achieved_Tinst_s": NCU_WARP_INSTRUCTIONS / (k_ms * 1e-3) / 1e12,
-                                      "peak_Tinst_s": issue_peak / 1e12,
-                                      "frac": NCU_WARP_INSTRUCTIONS / (k_ms * 1e-3) / issue_peak}}
+                                    "bound (ncu: issue-active ~85 %, DRAM < 3 %): ~95 blended pixel x Gaussian pairs "
+                                    "are evaluated per 48-byte record (DESIGN.md section 3); see `issue`"}
+        if ncu.get("warp_instructions"):
+            wi = ncu["warp_instructions"]
+            line["roofline"]["issue"] = {"warp_instructions_per_launch": wi, "source": ncu.get("file"),
+                                         "achieved_Tinst_s": wi / (k_ms * 1e-3) / 1e12,
+                                         "peak_Tinst_s": issue_peak / 1e12, "frac": wi / (k_ms * 1e-3) / issue_peak}
+        # the HBM-bound stages, each against the same measured copy bandwidth; bytes = what THIS implementation has to
+        # move at minimum, not the reference's 172 B per instance of sort traffic
+        Rc = 0.35 * Rk                                    # (supertile, Gaussian) instances: ~0.35 per kept instance
+        stage_bytes = {
+            "preprocess_fwd": 52 * P + (192 + 67) * V,
+            "depth_sort_scan": (4 + 3 * 16 + 16) * P,
+            "tile_sort": 4 * Rk + 28 * Rc + 12 * P,
+            "preprocess_bwd": 48 * P + (107 + 192) * V + (40 + 192) * P,
+        }
+        hbm = {}
+        for n, byts in stage_bytes.items():
+            c_ = max(1, stage["calls"][n])
+            ms_ = stage["ms"][n] / c_
+            if ms_ > 0:
+                hbm[n] = {"algorithmic_bytes": byts, "ms": ms_, "GBps": byts / (ms_ * 1e-3) / 1e9,
+                          "frac": byts / (ms_ * 1e-3) / 1e9 / peak}
+        if hbm:
+            worst = min(hbm, key=lambda n: hbm[n]["frac"])
+            line["hbm_stages"] = {"stages": hbm, "worst": worst, "peak": peak, "unit": "GB/s",
+                                  "note": "stage times include launch gaps (CUDA events around each stage)"}
+        line["binning_relaunches_in_profiled_pass"] = relaunches
         line["stage_ms_per_step"] = {n: stage["ms"][n] / K for n in stage["ms"]}
         line["ms_per_step_with_stage_events"] = prof_ms / K
         line["gpu_launches"] = stage["own_launches"]
-        line["gpu_launches_note"] = "hand-written kernels only (6/step); CUB sort/scan kernels launched by the library are extra"
+        line["gpu_launches_note"] = "hand-written kernels only (9 per step: preprocess, depth sort, coarse sort, tile " \
+                                    "count, tile fill, render | render bwd, preprocess bwd + one 14 MB memset); no " \
+                                    "library (CUB / cuBLAS) kernels on this path since round 2"
         if rank == 0:
             line["loss_path"] = loss_path_timing(dev, H, W)
             line["deform_path"] = deform_path_timing(dev)
@@ -331,6 +430,30 @@ def run_native_or_ref(args, impl):
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+# newest `ncu --set full` capture of the render kernels on this exact workload (tools/ncu_summary.py output)
+NCU_SUMMARIES = ["profiles/r2_render_ncu_summary.csv", "profiles/r02f_render_ncu_summary.csv"]
+
+
+def load_ncu_summary(kernel):
+    """{traffic_bytes, warp_instructions, file} of `kernel` from the newest committed ncu summary (per launch)."""
+    import csv
+    for rel in NCU_SUMMARIES:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        out = {"file": rel}
+        for row in csv.DictReader(open(path)):
+            if not row["kernel"].startswith(kernel):
+                continue
+            if row["metric"] == "traffic_bytes(read+write)":
+                out["traffic_bytes"] = int(float(row["value"]))
+            if row["metric"] == "smsp__inst_executed.sum":
+                out["warp_instructions"] = float(row["value"])
+        if "traffic_bytes" in out:
+            return out
+    return {"file": None}
 
 
 def loss_path_timing(dev, H, W, iters=20):
@@ -484,8 +607,18 @@ def cpu_baseline(precision="f32"):
     r = oracle.forward_scene(scene, cam, torch.zeros(3), precision=precision)
     r.backward(cot)
     ms = (time.perf_counter() - t0) * 1e3
+    # BASELINE.json configs[0]: 10 k random Gaussians, one pinhole camera @400x400, forward RGB only, CPU splat
+    s0, c0 = synthetic.config1_scene()
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        oracle.forward_scene(s0, c0, torch.zeros(3), precision=precision)
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
     return {"value": ms, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": "1 full frame (forward + backward) of the same workload, C oracle float32 + OpenMP"}
+            "sample": "1 full frame (forward + backward) of the same workload, C oracle float32 + OpenMP",
+            "config0_cpu_splat_forward_ms": best,
+            "config0": "BASELINE.json configs[0]: 10k Gaussians @400x400, forward only, same CPU oracle, best of 3"}
 
 
 def run_cpu_reference(args, rank, world, why):
@@ -511,6 +644,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sequence", action="store_true", help="skip the 300-frame configs[2] FPS protocol")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path (by design)")

@@ -118,6 +118,12 @@ int sgs_debug_export(int P, int width, int height, int64_t R, char* geom_buffer,
  * Synchronises the stream. */
 int64_t sgs_debug_kept(char* binning_buffer, void* stream);
 
+/* Counts of the calling thread's most recent sgs_forward (no synchronisation: they were read during that call):
+ * out5 = { kept tile instances (binned + rendered), num_rendered as the reference counts it, visible Gaussians
+ * (radii > 0), capacity the binning buffer was sized for, 1 if the prediction was too small and the binning + render
+ * kernels were launched a second time }. */
+int sgs_last_forward_counts(int64_t* out5);
+
 /* Validation only: force the predicted capacity of the binning buffer (in tile instances) for the following
  * sgs_forward calls, e.g. 0 to exercise the "prediction too small -> re-launch with the exact size" path;
  * a negative value restores the predictor. */

@@ -190,6 +190,8 @@ int wait_for_ticket(const volatile sgs::HostSlot* hs, unsigned long long ticket,
 struct CapPredictor {
     size_t last_kept = 0;
     int last_P = 0;
+    // counts of the most recent forward call of this thread (sgs_last_forward_counts)
+    unsigned long long kept = 0, touched = 0, visible = 0, cap = 0, relaunched = 0;
 };
 CapPredictor& cap_predictor() {
     thread_local CapPredictor p;
@@ -383,7 +385,9 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     const double t_synced = tr ? now_us() : 0;
     if (Rk > 0x7FFFF000ull || R > 0x7FFFFFFFFFFFull)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: more than 2^31 tile instances");
+    bool relaunched = false;
     if (Rk > cap) {
+        relaunched = true;
         // prediction too small: the binning kernel left everything untouched (ranges still zero, barrier counter
         // unused) and the render kernel drew background only — redo both with the exact size
         cap = ((size_t)Rk + 4095) & ~(size_t)4095;
@@ -396,6 +400,11 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     CapPredictor& pr = cap_predictor();
     pr.last_kept = (size_t)Rk;
     pr.last_P = P;
+    pr.kept = Rk;
+    pr.touched = R;
+    pr.visible = ring->host[slot_idx].visible;
+    pr.cap = cap;
+    pr.relaunched = relaunched ? 1 : 0;
     if (tr)
         fprintf(stderr, "[sgs_forward] launches %.1f us | wait %.1f us | kept %llu cap %zu\n", t_presync - t_enter,
                 t_synced - t_presync, Rk, cap);
@@ -496,6 +505,17 @@ int64_t sgs_debug_kept(char* binning_buffer, void* stream) {
                                 sizeof(hdr), cudaMemcpyDeviceToHost, s));
     SGS_CUDA_OK(cudaStreamSynchronize(s));
     return (int64_t)hdr[1];
+}
+
+int sgs_last_forward_counts(int64_t* out5) {
+    if (!out5) return SGS_ERR_INVALID_ARGUMENT;
+    const CapPredictor& pr = cap_predictor();
+    out5[0] = (int64_t)pr.kept;
+    out5[1] = (int64_t)pr.touched;
+    out5[2] = (int64_t)pr.visible;
+    out5[3] = (int64_t)pr.cap;
+    out5[4] = (int64_t)pr.relaunched;
+    return 0;
 }
 
 void sgs_debug_set_capacity(int64_t instances) { g_forced_cap.store(instances < 0 ? -1 : (long long)instances); }

@@ -155,6 +155,32 @@ def temporal_frame(scene, t, seed=7):
                  scene.sh_degree)
 
 
+class DeviceSequence:
+    """BASELINE.json configs[2] at its stated size (300 frames): `temporal_frame` evaluated with torch ops ON THE
+    DEVICE, so that a 300-frame sequence of a 300 k cloud does not have to be built and uploaded from the host.
+    The per-Gaussian temporal parameters are the CPU-generated ones of `temporal_frame` (same seed); the elementwise
+    arithmetic runs on the GPU, so fixtures made from it (tests/golden/config3_seq300.npz) are tied to the platform
+    that made them (B200, this image) — every frame's alive count is stored as a guard."""
+
+    def __init__(self, scene, device, seed=7):
+        gen = torch.Generator().manual_seed(seed)
+        P = scene.means3D.shape[0]
+        self.centre = torch.rand(P, generator=gen).to(device)
+        self.life = (torch.rand(P, generator=gen) * 0.9 + 0.1).to(device)
+        self.phase = (torch.rand(P, generator=gen) * 2 * math.pi).to(device)
+        direction = torch.randn(P, 3, generator=gen)
+        self.direction = (direction / direction.norm(dim=1, keepdim=True)).to(device)
+        self.scene = Scene(*[x.to(device) if torch.is_tensor(x) else x for x in scene])
+
+    def frame(self, t):
+        sc = self.scene
+        survival = torch.exp(-4.0 * ((t - self.centre) / self.life) ** 2)
+        keep = survival > 0.001
+        means = sc.means3D + 0.05 * torch.sin(2 * math.pi * t + self.phase)[:, None] * self.direction
+        return Scene(means[keep].contiguous(), sc.scales[keep].contiguous(), sc.rotations[keep].contiguous(),
+                     (sc.opacities * survival[:, None])[keep].contiguous(), sc.shs[keep].contiguous(), sc.sh_degree)
+
+
 def dynamic_model(scene, feat_dim=32, seed=0, lifespan=(0.15, 1.2), residual_gain=0.05):
     """A stand-in for the reference's dynamic GaussianModel after get_deformfeature() (scene/saro_gaussian.py:863-869):
     the attributes get_deformation_eval reads (:871-921) — raw (pre-activation) parameters derived from `scene`, a

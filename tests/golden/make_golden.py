@@ -170,6 +170,34 @@ def run_seq(RefRast, dev, name):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def run_seq300(RefRast, dev, name, frames=300):
+    """BASELINE.json configs[2] at its stated size: a 300-frame sequence (timestamp = frame / 300, like the reference's
+    Camera.timestamp for a duration of 300), inputs from synthetic.DeviceSequence; per frame the alive count, the
+    reference's num_rendered and SHA-256 of colour, depth and radii."""
+    base, cam = synthetic.config2_scene()
+    rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                       cam.viewmatrix.to(dev), cam.projmatrix.to(dev), base.sh_degree,
+                                       cam.campos.to(dev), False)
+    seq = synthetic.DeviceSequence(base, dev)
+    refC = ref_loader.load_ref_C()
+    e = torch.Tensor([])
+    P, R, sc_, sd_, sr_ = [], [], [], [], []
+    with torch.no_grad():
+        for k in range(frames):
+            sc = seq.frame(k / frames)
+            r, color, radii, gb, bb, ib, depth = refC.rasterize_gaussians(
+                rs.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, cam.height, cam.width, sc.shs, sc.sh_degree, rs.campos, False)
+            P.append(sc.means3D.shape[0])
+            R.append(r)
+            sc_.append(sha(color))
+            sd_.append(sha(depth))
+            sr_.append(sha(radii))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), frames=np.int64(frames), P=np.array(P, np.int64),
+                        R=np.array(R, np.int64), sha_color=np.array(sc_), sha_depth=np.array(sd_), sha_radii=np.array(sr_))
+    print(name, "frames", frames, "P", min(P), "..", max(P), "R", min(R), "..", max(R), flush=True)
+
+
 def run_big_grad(RefRast, dev, name, scene, cam, n_samples=4096):
     """Full-size backward of the reference (configs[1], standard cotangent): per-tensor norms, max |.| and a
     seeded sample of entries.  The reference sums with float atomics, so these are reproducible to ~1e-6 only."""
@@ -206,12 +234,16 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     dev = torch.device("cuda:0")
     RefRast = ref_loader.ref_api()[1]
+    if len(sys.argv) > 1 and sys.argv[1] == "seq300":       # only the 300-frame sequence (round 2 addition)
+        run_seq300(RefRast, dev, "config3_seq300")
+        return
     for name, spec in CASES.items():
         run_case(RefRast, dev, name, spec)
     run_big(RefRast, dev, "config1_fwd", *synthetic.config1_scene())
     run_big(RefRast, dev, "config2_fwd", *synthetic.config2_scene())
     run_big_grad(RefRast, dev, "config2_bwd", *synthetic.config2_scene())
     run_seq(RefRast, dev, "config3_seq")
+    run_seq300(RefRast, dev, "config3_seq300")
 
 
 if __name__ == "__main__":

@@ -310,6 +310,37 @@ def test_config3_sequence_bit_exact(sgs, dev):
             assert _sha(color2) == str(d[f"sha_color_life_{k}"])
 
 
+def test_config3_sequence_300_frames_bit_exact(sgs, dev):
+    """BASELINE.json configs[2] at its stated size: 300 frames of the 300 k cloud with a varying number of live
+    Gaussians (synthetic.DeviceSequence); colour, depth and radii hash-equal to the compiled reference on every frame
+    (tests/golden/config3_seq300.npz, made on a B200 by tests/golden/make_golden.py seq300), and the API-visible
+    num_rendered equal."""
+    from saro_gs_b200 import synthetic
+    d = load("config3_seq300")
+    base, cam = synthetic.config2_scene()
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
+                                           1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), base.sh_degree,
+                                           cam.campos.to(dev), False)
+    seq = synthetic.DeviceSequence(base, dev)
+    frames = int(d["frames"])
+    e = torch.Tensor([])
+    bad = []
+    with torch.no_grad():
+        for k in range(frames):
+            sc = seq.frame(k / frames)
+            assert sc.means3D.shape[0] == int(d["P"][k]), \
+                f"frame {k}: synthetic inputs are not reproducible on this platform (alive count differs from the fixture)"
+            R, color, radii, gb, bb, ib, depth = sgs._C.rasterize_gaussians(
+                rs.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, cam.height, cam.width, sc.shs, sc.sh_degree, rs.campos, False,
+                keep_for_backward=False)
+            ok = (R == int(d["R"][k]) and _sha(color) == str(d["sha_color"][k]) and _sha(depth) == str(d["sha_depth"][k])
+                  and _sha(radii) == str(d["sha_radii"][k]))
+            if not ok:
+                bad.append(k)
+    assert not bad, f"frames differing from the reference: {bad[:10]} ({len(bad)} of {frames})"
+
+
 def test_full_size_backward_properties(sgs, dev):
     """configs[1] backward at full size: linear in the cotangent, zero for culled Gaussians,
     deterministic forward."""
