@@ -63,9 +63,9 @@ __forceinline__ __device__ void grad_pixels2(BwdPix2& s, float2 pw, bool act0, b
     // accurate expf() and a < 1 ulp reciprocal, like forward / the reference: alpha must equal forward's bit for
     // bit and T is recovered by a long product of 1/(1-alpha) factors — a bare ex2.approx / rcp.approx (~1e-7
     // each, but biased) drifts T by ~n * 1e-7 over n blended instances (measured: 2.5x the error on dL/dmeans3D).
-    float2 G = {0.f, 0.f};
-    if (act0) G.x = expf(pw.x);
-    if (act1) G.y = expf(pw.y);
+    float2 G = expf2_exact(pw);        // both pixels, branch-free, bit-identical to expf (sgs_render_common.cuh)
+    if (!act0) G.x = 0.f;
+    if (!act1) G.y = 0.f;
     float2 alpha = __fmul2_rn(bcast2(o), G);
     alpha.x = min(0.99f, alpha.x);
     alpha.y = min(0.99f, alpha.y);

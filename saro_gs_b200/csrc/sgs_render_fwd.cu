@@ -26,27 +26,44 @@
 
 namespace sgs {
 
-struct FwdPix {
-    float T, C0, C1, C2, D;
-    uint32_t last;
-    bool done;
+// State of the two pixels of a thread as f32x2 pairs: the whole blend step runs on packed FMUL2 / FFMA2 / FADD2
+// instructions and selects instead of two divergent scalar paths.
+struct FwdPix2 {
+    float2 T, C0, C1, C2, D;
+    uint32_t last0, last1;
+    bool done0, done1;
 };
 
-// one pixel x one instance, exactly the reference's sequence of tests and roundings
-__forceinline__ __device__ void blend_pixel(FwdPix& s, float power, float o, const float4 c, uint32_t pos) {
-    const float alpha = min(0.99f, o * expf(power));
-    if (alpha < 1.0f / 255.0f) return;
-    const float test_T = s.T * (1 - alpha);
-    if (test_T < 0.0001f) {
-        s.done = true;
-        return;
+// two pixels x one instance, exactly the reference's sequence of tests and roundings per pixel
+// ($R/cuda_rasterizer/forward.cu:342-379).  A pixel that does not blend (inactive, alpha < 1/255, or saturating)
+// runs through the same packed code with alpha = 0: then test_T = T * 1 = T and C += (c * 0) * T = C exactly
+// (C is never -0: it starts at +0 and a round-to-nearest sum that cancels gives +0).
+__forceinline__ __device__ void blend_pixels2(FwdPix2& s, float2 pw, bool act0, bool act1, float o, const float4 c,
+                                              uint32_t pos) {
+    const float2 e = expf2_exact(pw);
+    float2 alpha = __fmul2_rn(make_float2(o, o), e);
+    alpha.x = min(0.99f, alpha.x);
+    alpha.y = min(0.99f, alpha.y);
+    bool go0 = act0 && !(alpha.x < 1.0f / 255.0f);
+    bool go1 = act1 && !(alpha.y < 1.0f / 255.0f);
+    const float2 test_T = __fmul2_rn(s.T, __fadd2_rn(make_float2(1.f, 1.f), make_float2(-alpha.x, -alpha.y)));
+    if (go0 && test_T.x < 0.0001f) { s.done0 = true; go0 = false; }
+    if (go1 && test_T.y < 0.0001f) { s.done1 = true; go1 = false; }
+    if (!go0) alpha.x = 0.f;
+    if (!go1) alpha.y = 0.f;
+    s.C0 = __ffma2_rn(__fmul2_rn(make_float2(c.x, c.x), alpha), s.T, s.C0);
+    s.C1 = __ffma2_rn(__fmul2_rn(make_float2(c.y, c.y), alpha), s.T, s.C1);
+    s.C2 = __ffma2_rn(__fmul2_rn(make_float2(c.z, c.z), alpha), s.T, s.C2);
+    if (go0) {
+        if (s.T.x > 0.5f && test_T.x < 0.5) s.D.x = c.w;
+        s.T.x = test_T.x;
+        s.last0 = pos + 1u;
     }
-    s.C0 += c.x * alpha * s.T;
-    s.C1 += c.y * alpha * s.T;
-    s.C2 += c.z * alpha * s.T;
-    if (s.T > 0.5f && test_T < 0.5) s.D = c.w;
-    s.T = test_T;
-    s.last = pos + 1u;
+    if (go1) {
+        if (s.T.y > 0.5f && test_T.y < 0.5) s.D.y = c.w;
+        s.T.y = test_T.y;
+        s.last1 = pos + 1u;
+    }
 }
 
 template <bool WRITE_PACKED, bool TILE_CULL>
@@ -84,10 +101,15 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const int n = (int)(range.y - range.x);
 
     // reference defaults: T = 1, depth 15.0 when the median is never crossed ($R/.../forward.cu:303-308)
-    FwdPix p0 = {1.0f, 0.f, 0.f, 0.f, 15.0f, 0u, !in0};
-    FwdPix p1 = {1.0f, 0.f, 0.f, 0.f, 15.0f, 0u, !in1};
+    FwdPix2 px2;
+    px2.T = make_float2(1.0f, 1.0f);
+    px2.C0 = px2.C1 = px2.C2 = make_float2(0.f, 0.f);
+    px2.D = make_float2(15.0f, 15.0f);
+    px2.last0 = px2.last1 = 0u;
+    px2.done0 = !in0;
+    px2.done1 = !in1;
     uint32_t packed_count = 0;
-    bool both_done = p0.done && p1.done;
+    bool both_done = px2.done0 && px2.done1;
 
     for (int base = 0; base < n; base += SGS_R_BATCH) {
         // also the barrier that protects the staging buffers of the previous round
@@ -152,7 +174,7 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
         // ---- composite -------------------------------------------------------------------
         for (int k = 0; k < SGS_R_BATCH / 32; k++) {
             // saturation of the whole quadrant is tested once per 32 staged slots, not once per visit
-            both_done = p0.done && p1.done;
+            both_done = px2.done0 && px2.done1;
             if (__all_sync(0xFFFFFFFFu, both_done)) break;
             uint32_t word = __shfl_sync(0xFFFFFFFFu, mywords, k);
             while (word) {
@@ -164,37 +186,36 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 float2 dy;
                 const float2 pw = power2(g0, g1.x, pxf, npy, dx, dy);
                 // same tests as the reference: power > 0 -> skip; power < thr -> provably alpha < 1/255
-                const bool act0 = !p0.done && !(pw.x > 0.0f) && !(pw.x < g1.y);
-                const bool act1 = !p1.done && !(pw.y > 0.0f) && !(pw.y < g1.y);
+                const bool act0 = !px2.done0 && !(pw.x > 0.0f) && !(pw.x < g1.y);
+                const bool act1 = !px2.done1 && !(pw.y > 0.0f) && !(pw.y < g1.y);
                 if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;
                 const float4 c = lds128(a2 + j * 16u);
                 const uint32_t pos = __float_as_uint(g1.z);
-                if (act0) blend_pixel(p0, pw.x, g1.w, c, pos);
-                if (act1) blend_pixel(p1, pw.y, g1.w, c, pos);
+                blend_pixels2(px2, pw, act0, act1, g1.w, c, pos);
             }
         }
-        both_done = p0.done && p1.done;
+        both_done = px2.done0 && px2.done1;
     }
 
     if (WRITE_PACKED && tid == 0) tile_count[tile] = packed_count;
     const size_t HW = (size_t)H * W;
     if (in0) {
         const uint32_t pix_id = (uint32_t)W * py0 + px;
-        final_T[pix_id] = p0.T;
-        n_contrib[pix_id] = p0.last;
-        out_color[pix_id] = p0.C0 + p0.T * vp.bg[0];
-        out_color[HW + pix_id] = p0.C1 + p0.T * vp.bg[1];
-        out_color[2 * HW + pix_id] = p0.C2 + p0.T * vp.bg[2];
-        out_depth[pix_id] = p0.D;
+        final_T[pix_id] = px2.T.x;
+        n_contrib[pix_id] = px2.last0;
+        out_color[pix_id] = px2.C0.x + px2.T.x * vp.bg[0];
+        out_color[HW + pix_id] = px2.C1.x + px2.T.x * vp.bg[1];
+        out_color[2 * HW + pix_id] = px2.C2.x + px2.T.x * vp.bg[2];
+        out_depth[pix_id] = px2.D.x;
     }
     if (in1) {
         const uint32_t pix_id = (uint32_t)W * py1 + px;
-        final_T[pix_id] = p1.T;
-        n_contrib[pix_id] = p1.last;
-        out_color[pix_id] = p1.C0 + p1.T * vp.bg[0];
-        out_color[HW + pix_id] = p1.C1 + p1.T * vp.bg[1];
-        out_color[2 * HW + pix_id] = p1.C2 + p1.T * vp.bg[2];
-        out_depth[pix_id] = p1.D;
+        final_T[pix_id] = px2.T.y;
+        n_contrib[pix_id] = px2.last1;
+        out_color[pix_id] = px2.C0.y + px2.T.y * vp.bg[0];
+        out_color[HW + pix_id] = px2.C1.y + px2.T.y * vp.bg[1];
+        out_color[2 * HW + pix_id] = px2.C2.y + px2.T.y * vp.bg[2];
+        out_depth[pix_id] = px2.D.y;
     }
 }
 
