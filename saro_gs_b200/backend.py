@@ -55,6 +55,18 @@ def _resize_dispatch(user, nbytes):
 _RESIZE_CB = _lib.RESIZE_FN(_resize_dispatch)
 _GEOM, _BINNING, _IMAGE = 1, 2, 3
 
+# Which binning buffers were filled by an inference-mode forward (no packed per-tile records): keyed by the buffer's
+# device address, not by a Python attribute on the tensor object — autograd's saved_tensors may hand back a different
+# tensor object for the same storage.  A later forward that reuses the address overwrites the entry, so the table
+# stays as small as the set of live addresses (bounded anyway).
+_inference_only = {}
+
+
+def _note_binning_buffer(buf, kept_for_backward):
+    if len(_inference_only) > 8192:
+        _inference_only.clear()
+    _inference_only[(buf.device.index, buf.data_ptr())] = not kept_for_backward
+
 
 def _check(code, what):
     if code < 0:
@@ -129,8 +141,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             _ptr(out_color), _ptr(out_depth), _ptr(radii), flags, ctypes.c_void_p(stream))
     _tls.bufs = None
     _check(rendered, "sgs_forward")
-    # remembered on the (opaque) binning buffer so that a backward call on inference-only state fails loudly
-    bufs[_BINNING]._sgs_kept_for_backward = bool(keep_for_backward)
+    # remembered per binning-buffer address so that a backward call on inference-only state fails loudly
+    _note_binning_buffer(bufs[_BINNING], bool(keep_for_backward))
     return int(rendered), out_color, radii, bufs[_GEOM], bufs[_BINNING], bufs[_IMAGE], out_depth
 
 
@@ -150,7 +162,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     if P == 0:
         z = lambda *s: torch.zeros(s, **opts)
         return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, M, 3), z(0, 3), z(0, 4)
-    if getattr(binningBuffer, "_sgs_kept_for_backward", True) is False:
+    if _inference_only.get((binningBuffer.device.index, binningBuffer.data_ptr()), False):
         raise RuntimeError("rasterize_gaussians_backward: the forward call ran with keep_for_backward=False "
                            "(inference mode) — its state buffers do not hold the per-tile lists backward needs")
 

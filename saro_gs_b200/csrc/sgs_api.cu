@@ -46,6 +46,8 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.tiles_touched, P);
     sgs::carve(chunk, g.rect_kept, P);
     sgs::carve(chunk, g.depth_raw, P);
+    g.n_blk_range = sgs::preprocess_blocks((int)P);
+    sgs::carve(chunk, g.blk_range, (size_t)g.n_blk_range);
     sgs::carve(chunk, g.depth_keys[0], P);
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);

@@ -245,6 +245,8 @@ struct DepthArgs {
     int vblocks;      // virtual blocks (slices); multiple of gridDim.x; == gridDim.x  <=>  slices stay resident
     int slice;        // keys per slice
     const uint32_t* raw;
+    const uint2* blk_range;   // per-preprocess-block (max key, max ~key) of the visible Gaussians
+    int n_blk_range;
     uint32_t* keys[2];
     uint32_t* vals[2];
     const ushort4* rect_kept;
@@ -298,19 +300,15 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
     int pslot = 0;
     prof_mark(a.prof, pslot);
 
-    // ---- phase 0: key range of the visible Gaussians (resident mode: the raw keys stay in shared memory)
+    // ---- phase 0: key range of the visible Gaussians from the preprocess kernel's per-block partials; every block
+    // reduces all of them itself (a few KB from L2), so no grid-wide barrier is needed for the range
+    uint32_t key_max, key_nmin;
     {
         uint32_t kmax = 0u, knmin = 0u;
-        for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
-            const uint32_t lo = v * SL, hi = min(P, lo + SL);
-            for (uint32_t i = lo + tid; i < hi; i += SGS_SORT_THREADS) {
-                const uint32_t k = a.raw[i];
-                if (resident) sm.key[i - lo] = k;
-                if (k != 0xFFFFFFFFu) {
-                    kmax = max(kmax, k);
-                    knmin = max(knmin, ~k);
-                }
-            }
+        for (int i = tid; i < a.n_blk_range; i += SGS_SORT_THREADS) {
+            const uint2 r = __ldcg(a.blk_range + i);
+            kmax = max(kmax, r.x);
+            knmin = max(knmin, r.y);
         }
         kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
         knmin = __reduce_max_sync(0xFFFFFFFFu, knmin);
@@ -319,19 +317,11 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
             sm.cnt[warp] = knmin;
         }
         __syncthreads();
-        if (warp == 0) {
-            kmax = __reduce_max_sync(0xFFFFFFFFu, sm.base[lane]);
-            knmin = __reduce_max_sync(0xFFFFFFFFu, sm.cnt[lane]);
-            if (lane == 0) {
-                if (kmax) atomicMax(&a.ctl->key_max, kmax);
-                if (knmin) atomicMax(&a.ctl->key_nmin, knmin);
-            }
-        }
-        prof_mark(a.prof, pslot);
-        grid_barrier(&a.ctl->bar_depth, bar_target);
+        key_max = __reduce_max_sync(0xFFFFFFFFu, sm.base[lane]);
+        key_nmin = __reduce_max_sync(0xFFFFFFFFu, sm.cnt[lane]);
+        __syncthreads();
         prof_mark(a.prof, pslot);
     }
-    const uint32_t key_max = __ldcg(&a.ctl->key_max), key_nmin = __ldcg(&a.ctl->key_nmin);
     const uint32_t key_min = ~key_nmin;
     // normalised key: visible -> raw - min in [0, span) ; culled -> span (sorted behind everything, stable)
     const uint32_t span = (key_nmin != 0u && key_max >= key_min) ? key_max - key_min + 1u : 0u;
@@ -359,7 +349,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
         auto load = [&](uint32_t lo, uint32_t n) {
             if (p == 1u) {
                 for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) {
-                    const uint32_t k = resident ? sm.key[i] : a.raw[lo + i];
+                    const uint32_t k = a.raw[lo + i];
                     sm.key[i] = (k == 0xFFFFFFFFu) ? span : k - key_min;
                     sm.val[i] = lo + i;
                 }
@@ -877,6 +867,8 @@ cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long 
     a.vblocks = g.depth_vblocks;
     a.slice = (P + a.vblocks - 1) / a.vblocks;
     a.raw = g.depth_raw;
+    a.blk_range = g.blk_range;
+    a.n_blk_range = g.n_blk_range;
     a.keys[0] = g.depth_keys[0];
     a.keys[1] = g.depth_keys[1];
     a.vals[0] = g.depth_vals[0];

@@ -114,6 +114,8 @@ struct GeomState {
     ushort4*  rect_kept;      // [P]   tile rect [x0,x1) x [y0,y1) actually binned: the reference's 3-sigma rect
                               //       clipped to the exact bounding box of the alpha >= 1/255 ellipse
     uint32_t* depth_raw;      // [P]   float bits of depth (0xFFFFFFFF when culled), written by preprocess
+    uint2*    blk_range;      // [preprocess blocks] (max key, max ~key) over the block's visible Gaussians
+    int       n_blk_range;
     uint32_t* depth_keys[2];  // [P]   radix-sort ping-pong: normalised keys
     uint32_t* depth_vals[2];  // [P]   radix-sort ping-pong: Gaussian index; [0] ends up holding the depth order
     uint32_t* coffs;          // [P]   inclusive scan, in depth order, of the supertiles each kept rect overlaps
@@ -241,6 +243,7 @@ namespace sgs {
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                          cudaStream_t s);
 
+int  preprocess_blocks(int P);
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii,

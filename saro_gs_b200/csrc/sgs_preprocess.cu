@@ -317,6 +317,27 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
         g.clamped[idx] = 0;
     }
 
+    // per-block range of the visible depth keys: the depth-sort kernel normalises its keys to the frame's
+    // [min, max] (fewer radix passes) and gets that range from these partials without a pass over the keys
+    {
+        __shared__ uint32_t s_kmax[SGS_PRE_THREADS / 32], s_knmin[SGS_PRE_THREADS / 32];
+        const uint32_t kx = __reduce_max_sync(0xFFFFFFFFu, visible ? out_key : 0u);
+        const uint32_t kn = __reduce_max_sync(0xFFFFFFFFu, visible ? ~out_key : 0u);
+        if ((threadIdx.x & 31) == 0) {
+            s_kmax[threadIdx.x >> 5] = kx;
+            s_knmin[threadIdx.x >> 5] = kn;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t a = 0u, b = 0u;
+#pragma unroll
+            for (int w = 0; w < SGS_PRE_THREADS / 32; w++) {
+                a = max(a, s_kmax[w]);
+                b = max(b, s_knmin[w]);
+            }
+            g.blk_range[blockIdx.x] = make_uint2(a, b);
+        }
+    }
     if (!valid) return;
     radii[idx] = out_radius;
     g.tiles_touched[idx] = out_tiles;
@@ -324,13 +345,15 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     g.depth_raw[idx] = out_key;
 }
 
+int preprocess_blocks(int P) { return (P + SGS_PRE_THREADS - 1) / SGS_PRE_THREADS; }
+
 void launch_preprocess_fwd(int P, const ViewParams& vp, const float* means3D, const float* scales,
                            const float* rotations, const float* opacities, const float* shs,
                            const float* cov3D_precomp, const float* colors_precomp, int* radii, GeomState g,
                            uint32_t* zero_words, size_t n_zero, int cull, cudaStream_t s) {
     if (P <= 0) return;
     const int block = SGS_PRE_THREADS;
-    const int grid = (P + block - 1) / block;
+    const int grid = preprocess_blocks(P);
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0);
     // 128-bit quaternion loads only when the caller's pointer allows them (a torch view with a storage offset, or a
     // plain C caller, may hand over a 4-byte-aligned array: include/saro_gs_b200.h promises to accept that)
