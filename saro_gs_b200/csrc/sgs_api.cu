@@ -360,23 +360,37 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
         sgs::launch_preprocess_fwd(P, vp, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
                                    radii, g, z0, (size_t)(z1 - z0), cull, s);
     }
-    {
-        StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 1);
-        SGS_CUDA_OK(sgs::launch_depth_sort(P, g, ring->dev + slot_idx, ticket, s));
-    }
-    auto bin_and_render = [&]() -> int {
+    auto render = [&]() -> int {
+        StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
+        sgs::launch_render_fwd(vp, g, bin, img, bin.point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
+        SGS_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    auto bin_and_render = [&]() -> int {      // stand-alone binning stage: capacity re-launch and per-stage profiling
         {
             StageScope sc(SGS_STAGE_TILE_SORT, s, 3);
             SGS_CUDA_OK(sgs::launch_tile_binning(P, vp, g, bin, img, keep ? 1 : 0, s));
         }
-        {
-            StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
-            sgs::launch_render_fwd(vp, g, bin, img, bin.point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
-        }
-        SGS_CUDA_OK(cudaGetLastError());
-        return 0;
+        return render();
     };
-    if (int rc = bin_and_render()) return rc;
+    bool split_stages;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        split_stages = g_prof.enabled;            // the stage profiler wants one launch per stage
+    }
+    if (split_stages) {
+        {
+            StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 1);
+            SGS_CUDA_OK(sgs::launch_depth_sort(P, g, ring->dev + slot_idx, ticket, s));
+        }
+        if (int rc = bin_and_render()) return rc;
+    } else {
+        {
+            StageScope sc(SGS_STAGE_DEPTH_SORT_SCAN, s, 3);
+            SGS_CUDA_OK(sgs::launch_binning_fused(P, vp, g, bin, img, keep ? 1 : 0, ring->dev + slot_idx, ticket, s));
+        }
+        if (int rc = render()) return rc;
+    }
     const double t_presync = tr ? now_us() : 0;
 
     // The one device->host dependency of the path: the instance counts (same information as the reference's read

@@ -289,14 +289,11 @@ __device__ __forceinline__ Quad block_sum(Quad q, Quad* s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const DepthArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
-    __shared__ Quad s_w[32];
+__device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& sm, Quad* s_w, uint32_t* bar,
+                                                  uint32_t& bar_target) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t P = (uint32_t)a.P, VB = (uint32_t)a.vblocks, SL = (uint32_t)a.slice;
     const bool resident = VB == gridDim.x;
-    uint32_t bar_target = 0;
     int pslot = 0;
     prof_mark(a.prof, pslot);
 
@@ -335,7 +332,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
             const uint32_t lo = v * SL, hi = min(P, lo + SL);
             for (uint32_t i = lo + tid; i < hi; i += SGS_SORT_THREADS) a.vals[0][i] = i;
         }
-        grid_barrier(&a.ctl->bar_depth, bar_target);
+        grid_barrier(bar, bar_target);
     }
 
     for (uint32_t p = 1; p <= npass; p++) {
@@ -369,9 +366,9 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
             publish_hist(sm.cnt, a.hist, v, nd);
         }
         prof_mark(a.prof, pslot);
-        grid_barrier(&a.ctl->bar_depth, bar_target);
+        grid_barrier(bar, bar_target);
         column_scans(a.hist, VB, nd);
-        grid_barrier(&a.ctl->bar_depth, bar_target);
+        grid_barrier(bar, bar_target);
         prof_mark(a.prof, pslot);
         for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
             const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
@@ -384,7 +381,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
             __syncthreads();
         }
         prof_mark(a.prof, pslot);
-        grid_barrier(&a.ctl->bar_depth, bar_target);
+        grid_barrier(bar, bar_target);
         prof_mark(a.prof, pslot);
     }
 
@@ -418,7 +415,7 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const D
         }
     }
     prof_mark(a.prof, pslot);
-    grid_barrier(&a.ctl->bar_depth, bar_target);
+    grid_barrier(bar, bar_target);
     prof_mark(a.prof, pslot);
     for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
         const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
@@ -565,9 +562,7 @@ __device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const CoarseArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+__device__ __forceinline__ void coarse_sort_phases(const CoarseArgs& a, SortSmem& sm, uint32_t* bar, uint32_t& bar_target) {
     const uint32_t tid = threadIdx.x;
     int pslot = 64;
     prof_mark(a.prof, pslot);
@@ -593,7 +588,6 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const 
     const bool resident = slices_per_block == 1u;
     const uint32_t dbits = ((uint32_t)a.super_bits + npass - 1u) / npass;
     const uint32_t nd = 1u << dbits;
-    uint32_t bar_target = 0;
 
     for (uint32_t p = 1; p <= npass; p++) {
         const uint32_t shift = (p - 1u) * dbits;
@@ -622,9 +616,9 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const 
             publish_hist(sm.cnt, a.hist, v, nd);
         }
         prof_mark(a.prof, pslot);
-        grid_barrier(&a.ctl->bar_tile, bar_target);
+        grid_barrier(bar, bar_target);
         column_scans(a.hist, VB, nd);
-        grid_barrier(&a.ctl->bar_tile, bar_target);
+        grid_barrier(bar, bar_target);
         prof_mark(a.prof, pslot);
         for (uint32_t v = blockIdx.x; v < VB; v += G) {
             const uint32_t lo = min(Rc, v * SL), hi = min(Rc, lo + SL), n = hi - lo;
@@ -644,9 +638,37 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const 
             __syncthreads();
         }
         prof_mark(a.prof, pslot);
-        if (p < npass) grid_barrier(&a.ctl->bar_tile, bar_target);
+        if (p < npass) grid_barrier(bar, bar_target);
     }
     prof_mark(a.prof, pslot);
+}
+
+__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const DepthArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    __shared__ Quad s_w[32];
+    uint32_t bar_target = 0;
+    depth_sort_phases(a, sm, s_w, &a.ctl->bar_depth, bar_target);
+}
+
+__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const CoarseArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    uint32_t bar_target = 0;
+    coarse_sort_phases(a, sm, &a.ctl->bar_tile, bar_target);
+}
+
+// Both persistent stages in ONE cooperative launch (the normal path: a launch boundary between two cooperative
+// kernels costs ~7 us on B200).  The host ticket is written at the end of the depth stage, i.e. in the middle of this
+// kernel; the stand-alone coarse kernel remains for the capacity re-launch and for per-stage profiling.
+__global__ void __launch_bounds__(SGS_SORT_THREADS, 1) binning_fused_kernel(const DepthArgs d, const CoarseArgs c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    __shared__ Quad s_w[32];
+    uint32_t bar_target = 0;
+    depth_sort_phases(d, sm, s_w, &d.ctl->bar_depth, bar_target);
+    grid_barrier(&d.ctl->bar_depth, bar_target);     // totals + coffs of every block visible to every block
+    coarse_sort_phases(c, sm, &d.ctl->bar_depth, bar_target);
 }
 
 // multi-pass sorts only (more than 512 supertiles): supertile buckets from the sorted keys, one thread per instance
@@ -842,6 +864,7 @@ int binning_grid_blocks() {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(coarse_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        cudaFuncSetAttribute(binning_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cached = sms;
         cached_dev = dev;
     }
@@ -859,9 +882,7 @@ static int vblocks_for(size_t n) {
 int binning_depth_vblocks(int P) { return vblocks_for((size_t)P); }
 size_t binning_hist_words(size_t n) { return ((size_t)vblocks_for(n) + 1) * SGS_SORT_ND; }
 
-cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s) {
-    const int G = binning_grid_blocks();
-    if (G <= 0) return cudaErrorInvalidDevice;
+static DepthArgs make_depth_args(int P, const GeomState& g, HostSlot* slot, unsigned long long ticket) {
     DepthArgs a;
     a.P = P;
     a.vblocks = g.depth_vblocks;
@@ -882,15 +903,11 @@ cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long 
     a.slot = slot;
     a.ticket = ticket;
     a.prof = g_prof_on ? g_prof_host : nullptr;
-    void* args[] = {&a};
-    return cudaLaunchCooperativeKernel((const void*)depth_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
-                                       sizeof(SortSmem), s);
+    return a;
 }
 
-cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
-                                cudaStream_t s) {
-    const int G = binning_grid_blocks();
-    if (G <= 0) return cudaErrorInvalidDevice;
+static CoarseArgs make_coarse_args(int P, const ViewParams& vp, const GeomState& g, const BinningState& b,
+                                   const ImageState& img, int keep) {
     CoarseArgs a;
     a.P = P;
     a.n_super = binning_supertiles(vp.tiles_x, vp.tiles_y, &a.super_x);
@@ -909,11 +926,14 @@ cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, Binnin
     a.header = b.header;
     a.ctl = g.ctl;
     a.prof = g_prof_on ? g_prof_host : nullptr;
+    return a;
+}
+
+// supertile buckets (multi-pass sorts) + expansion into the per-tile lists and ranges
+static cudaError_t launch_expand(const CoarseArgs& a, const ViewParams& vp, const GeomState& g, const BinningState& b,
+                                 const ImageState& img, cudaStream_t s) {
+    const int G = binning_grid_blocks();
     const int side = binning_coarse_list_side(a.n_super);
-    void* args[] = {&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)coarse_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
-                                                sizeof(SortSmem), s);
-    if (e != cudaSuccess) return e;
     if (coarse_passes(a.n_super) > 1)
         coarse_ranges_kernel<<<4 * G, 256, 0, s>>>(b.coarse_keys[side], g.ctl, a.cap, img.cranges);
     ExpandArgs x;
@@ -930,6 +950,41 @@ cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, Binnin
     tile_count_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
     tile_fill_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
     return cudaGetLastError();
+}
+
+cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s) {
+    const int G = binning_grid_blocks();
+    if (G <= 0) return cudaErrorInvalidDevice;
+    DepthArgs a = make_depth_args(P, g, slot, ticket);
+    void* args[] = {&a};
+    return cudaLaunchCooperativeKernel((const void*)depth_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
+                                       sizeof(SortSmem), s);
+}
+
+cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                                cudaStream_t s) {
+    const int G = binning_grid_blocks();
+    if (G <= 0) return cudaErrorInvalidDevice;
+    CoarseArgs a = make_coarse_args(P, vp, g, b, img, keep);
+    void* args[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)coarse_sort_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
+                                                sizeof(SortSmem), s);
+    if (e != cudaSuccess) return e;
+    return launch_expand(a, vp, g, b, img, s);
+}
+
+// depth sort + supertile bucketing in one cooperative launch, then the expansion kernels
+cudaError_t launch_binning_fused(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                                 HostSlot* slot, unsigned long long ticket, cudaStream_t s) {
+    const int G = binning_grid_blocks();
+    if (G <= 0) return cudaErrorInvalidDevice;
+    DepthArgs d = make_depth_args(P, g, slot, ticket);
+    CoarseArgs c = make_coarse_args(P, vp, g, b, img, keep);
+    void* args[] = {&d, &c};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)binning_fused_kernel, dim3(G), dim3(SGS_SORT_THREADS), args,
+                                                sizeof(SortSmem), s);
+    if (e != cudaSuccess) return e;
+    return launch_expand(c, vp, g, b, img, s);
 }
 
 }  // namespace sgs

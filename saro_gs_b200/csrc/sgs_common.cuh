@@ -265,6 +265,9 @@ int    binning_coarse_list_side(int n_super);
 cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s);
 cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
                                 cudaStream_t s);
+// the normal path: depth_sort + the persistent part of tile_binning in ONE cooperative launch, then the expansion
+cudaError_t launch_binning_fused(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
+                                 HostSlot* slot, unsigned long long ticket, cudaStream_t s);
 
 void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,
