@@ -44,3 +44,32 @@ for P in (700, 129):
     stats.commit(m)
     torch.cuda.synchronize()
     print("densify ok", P, float(m.denom.sum()))
+
+# scale-aware plane sampler (round 2): forward + backward on a small field with two resolution levels
+from saro_gs_b200.hexplane import ScaleAwareResField
+cfg = {"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 8, "resolution": [16, 16, 8, 6]}
+field = ScaleAwareResField(cfg, [1, 2]).to(dev)
+with torch.no_grad():
+    for level in field.grids:
+        for p in level:
+            p.normal_()
+field.set_aabb([1.0, 1.0, 1.0], [-1.0, -1.0, -1.0], 10)
+pts = torch.rand(777, 3, device=dev) * 2.4 - 1.2
+feats = field(pts, torch.rand(777, 1, device=dev) * 0.9, torch.exp(torch.randn(777, 3, device=dev) * 2 - 3))
+feats.sum().backward()
+torch.cuda.synchronize()
+print("plane ok", tuple(feats.shape), float(field.grids[0][0].grad.abs().sum()))
+
+# the capacity re-launch path of the binning (prediction forced to a few instances)
+from saro_gs_b200 import _lib
+_lib.load().sgs_debug_set_capacity(64)
+scene, cam = synthetic.small_scene(P=900, seed=5)
+rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                       cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+with torch.no_grad():
+    img = sgs.GaussianRasterizer(rs)(means3D=scene.means3D.to(dev), means2D=torch.zeros(900, 3, device=dev),
+                                     opacities=scene.opacities.to(dev), shs=scene.shs.to(dev), scales=scene.scales.to(dev),
+                                     rotations=scene.rotations.to(dev))[0]
+_lib.load().sgs_debug_set_capacity(-1)
+torch.cuda.synchronize()
+print("relaunch ok", float(img.sum()))
