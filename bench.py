@@ -419,10 +419,12 @@ def run_native_or_ref(args, impl):
                                     "count, tile fill, render | render bwd, preprocess bwd + one 14 MB memset); no " \
                                     "library (CUB / cuBLAS) kernels on this path since round 2"
         if rank == 0:
-            line["loss_path"] = loss_path_timing(dev, H, W)
-            line["deform_path"] = deform_path_timing(dev)
-            line["densify_path"] = densify_path_timing(dev)
-            line["plane_path"] = plane_path_timing(dev)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):     # stdout carries exactly one JSON line
+                line["loss_path"] = loss_path_timing(dev, H, W)
+                line["deform_path"] = deform_path_timing(dev)
+                line["densify_path"] = densify_path_timing(dev)
+                line["plane_path"] = plane_path_timing(dev)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
     if rank == 0:
