@@ -48,6 +48,8 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.depth_raw, P);
     g.n_blk_range = sgs::preprocess_blocks((int)P);
     sgs::carve(chunk, g.blk_range, (size_t)g.n_blk_range);
+    sgs::carve(chunk, g.blk_sums, (size_t)g.n_blk_range);
+    sgs::carve(chunk, g.rect_sorted, P);
     sgs::carve(chunk, g.depth_keys[0], P);
     sgs::carve(chunk, g.depth_keys[1], P);
     sgs::carve(chunk, g.depth_vals[0], P);
@@ -56,7 +58,7 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     sgs::carve(chunk, g.ctl, 1);
     g.depth_vblocks = sgs::binning_depth_vblocks((int)P);
     sgs::carve(chunk, g.hist, ((size_t)g.depth_vblocks + 1) * 512);
-    sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks * 4);
+    sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks);
     return g;
 }
 
@@ -81,6 +83,7 @@ sgs::BinningState carve_binning(char*& chunk, size_t cap, bool with_packed, bool
     b.point_list = nullptr;
     b.coarse_keys[0] = b.coarse_keys[1] = b.coarse_vals[0] = b.coarse_vals[1] = nullptr;
     b.hist = nullptr;
+    b.coarse_pairs = nullptr;
     b.cap = cap;
     if (header_and_packed_only) return b;
     sgs::carve(chunk, b.point_list, cap);
@@ -89,6 +92,7 @@ sgs::BinningState carve_binning(char*& chunk, size_t cap, bool with_packed, bool
     sgs::carve(chunk, b.coarse_vals[0], cap);
     sgs::carve(chunk, b.coarse_keys[1], cap);
     sgs::carve(chunk, b.coarse_vals[1], cap);
+    sgs::carve(chunk, b.coarse_pairs, cap);
     sgs::carve(chunk, b.hist, sgs::binning_hist_words(cap));
     return b;
 }
@@ -330,6 +334,8 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     sgs::GeomState g = carve_geom(gchunk, (size_t)P);
 
     const size_t supers = (size_t)sgs::binning_supertiles(vp.tiles_x, vp.tiles_y, nullptr);
+    if (supers > 65536)     // the coarse sort carries the supertile id in 16 bits (images up to 16384 x 16384 pixels)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_forward: image larger than 65536 supertiles of 64x64 pixels");
     const size_t img_bytes = required_bytes([&](char*& p) { carve_image(p, N, tiles, supers); });
     char* ichunk = image_buffer(image_user, img_bytes);
     if (!ichunk) return fail(SGS_ERR_ALLOC, "sgs_forward: image buffer allocation failed");

@@ -154,6 +154,17 @@ __device__ __forceinline__ void rank_slice(SortSmem& sm, uint32_t n, uint32_t sh
 }
 
 // hist layout: [vblocks + 1][nd]; row `vblocks` receives the digit totals
+__device__ __forceinline__ void scatter_slice_pairs(SortSmem& sm, uint32_t n, uint32_t shift, uint32_t nd,
+                                                    unsigned long long* __restrict__ out) {
+    const uint32_t per = keys_per_warp(n);
+    for (uint32_t i = threadIdx.x; i < n; i += SGS_SORT_THREADS) {
+        const uint32_t k = sm.key[i];
+        const uint32_t d = (k >> shift) & (nd - 1u);
+        const uint32_t dst = sm.base[d] + sm.whist[i / per][d] + sm.rank[i];
+        out[dst] = (unsigned long long)sm.val[i] | ((unsigned long long)k << 32);
+    }
+}
+
 __device__ __forceinline__ void publish_hist(const uint32_t* cnt, uint32_t* __restrict__ hist, uint32_t v, uint32_t nd) {
     for (uint32_t d = threadIdx.x; d < nd; d += SGS_SORT_THREADS) __stcg(hist + (size_t)v * nd + d, cnt[d]);
 }
@@ -230,6 +241,25 @@ __device__ __forceinline__ void scatter_slice(SortSmem& sm, uint32_t n, uint32_t
     }
 }
 
+// bit (4 ly + lx) set  <=>  the kept rect covers tile (tx0 + lx, ty0 + ly)
+__device__ __forceinline__ uint32_t tile_mask16(const ushort4 r, uint32_t tx0, uint32_t ty0) {
+    uint32_t xm = 0, ym = 0;
+#pragma unroll
+    for (uint32_t l = 0; l < SGS_ST; l++) {
+        xm |= ((tx0 + l >= r.x) && (tx0 + l < r.y)) ? (1u << l) : 0u;
+        ym |= ((ty0 + l >= r.z) && (ty0 + l < r.w)) ? (1u << l) : 0u;
+    }
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t l = 0; l < SGS_ST; l++) m |= ((ym >> l) & 1u) ? (xm << (4 * l)) : 0u;
+    return m;
+}
+
+__device__ __forceinline__ ushort4 as_rect(unsigned long long v) {
+    return make_ushort4((unsigned short)(v & 0xFFFF), (unsigned short)((v >> 16) & 0xFFFF), (unsigned short)((v >> 32) & 0xFFFF),
+                        (unsigned short)(v >> 48));
+}
+
 // supertiles a kept tile rect overlaps: [x0, x1) x [y0, y1) in supertile units
 __device__ __forceinline__ uint4 super_rect(const ushort4 r) {
     if (r.y <= r.x || r.w <= r.z) return make_uint4(0u, 0u, 0u, 0u);
@@ -246,50 +276,48 @@ struct DepthArgs {
     int slice;        // keys per slice
     const uint32_t* raw;
     const uint2* blk_range;   // per-preprocess-block (max key, max ~key) of the visible Gaussians
+    const uint4* blk_sums;    // per-preprocess-block (kept, touched, visible) sums
     int n_blk_range;
+    ushort4* rect_sorted;     // out: rect_kept in depth order
     uint32_t* keys[2];
     uint32_t* vals[2];
     const ushort4* rect_kept;
     const uint32_t* tiles_touched;
     uint32_t* coffs;
     uint32_t* hist;
-    unsigned long long* blocksum;
+    uint32_t* blocksum;
     BinCtl* ctl;
     HostSlot* slot;
     unsigned long long ticket;
     unsigned long long* prof;
 };
 
-struct Quad {
-    unsigned long long kept, touched;
-    uint32_t vis, coarse;
+// block-wide sum of three 64-bit counters (every thread gets the result)
+struct Tri {
+    unsigned long long kept, touched, vis;
 };
-__device__ __forceinline__ Quad quad_add(const Quad& a, const Quad& b) {
-    return {a.kept + b.kept, a.touched + b.touched, a.vis + b.vis, a.coarse + b.coarse};
-}
-__device__ __forceinline__ Quad quad_xor(const Quad& a, int o) {
-    Quad r;
-    r.kept = __shfl_xor_sync(0xFFFFFFFFu, a.kept, o);
-    r.touched = __shfl_xor_sync(0xFFFFFFFFu, a.touched, o);
-    r.vis = __shfl_xor_sync(0xFFFFFFFFu, a.vis, o);
-    r.coarse = __shfl_xor_sync(0xFFFFFFFFu, a.coarse, o);
-    return r;
-}
-// block-wide sum (every thread gets it)
-__device__ __forceinline__ Quad block_sum(Quad q, Quad* s_w) {
+__device__ __forceinline__ Tri block_sum3(Tri q, Tri* s_w) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q = quad_add(q, quad_xor(q, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        q.kept += __shfl_xor_sync(0xFFFFFFFFu, q.kept, o);
+        q.touched += __shfl_xor_sync(0xFFFFFFFFu, q.touched, o);
+        q.vis += __shfl_xor_sync(0xFFFFFFFFu, q.vis, o);
+    }
     __syncthreads();
     if (lane == 0) s_w[warp] = q;
     __syncthreads();
-    Quad t = s_w[lane];
+    Tri t = s_w[lane];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t = quad_add(t, quad_xor(t, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        t.kept += __shfl_xor_sync(0xFFFFFFFFu, t.kept, o);
+        t.touched += __shfl_xor_sync(0xFFFFFFFFu, t.touched, o);
+        t.vis += __shfl_xor_sync(0xFFFFFFFFu, t.vis, o);
+    }
     return t;
 }
 
-__device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& sm, Quad* s_w, uint32_t* bar,
+__device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& sm, Tri* s_w, uint32_t* bar,
                                                   uint32_t& bar_target) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t P = (uint32_t)a.P, VB = (uint32_t)a.vblocks, SL = (uint32_t)a.slice;
@@ -302,10 +330,35 @@ __device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& 
     uint32_t key_max, key_nmin;
     {
         uint32_t kmax = 0u, knmin = 0u;
+        Tri tot = {0ull, 0ull, 0ull};
         for (int i = tid; i < a.n_blk_range; i += SGS_SORT_THREADS) {
             const uint2 r = __ldcg(a.blk_range + i);
             kmax = max(kmax, r.x);
             knmin = max(knmin, r.y);
+            if (blockIdx.x == 0) {
+                const uint4 q = __ldcg(a.blk_sums + i);
+                tot.kept += q.x;
+                tot.touched += q.y;
+                tot.vis += q.z;
+            }
+        }
+        if (blockIdx.x == 0) {
+            // the instance totals do not depend on the order: block 0 reports them to the host right away, at the
+            // START of the binning, and leaves them in the control block for the later stages
+            tot = block_sum3(tot, s_w);
+            if (tid == 0) {
+                a.ctl->kept = tot.kept;
+                a.ctl->touched = tot.touched;
+                a.ctl->visible = (uint32_t)tot.vis;
+                if (a.slot) {
+                    volatile HostSlot* hs = a.slot;
+                    hs->kept = tot.kept;
+                    hs->touched = tot.touched;
+                    hs->visible = (uint32_t)tot.vis;
+                    __threadfence_system();
+                    hs->ticket = a.ticket;
+                }
+            }
         }
         kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
         knmin = __reduce_max_sync(0xFFFFFFFFu, knmin);
@@ -385,48 +438,50 @@ __device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& 
         prof_mark(a.prof, pslot);
     }
 
-    // ---- scan, in depth order, of the supertile counts; totals of (kept tiles, touched tiles, visible)
+    // ---- scan, in depth order, of the supertile counts (+ the kept rects in depth order for the next stage)
     const uint32_t* order = a.vals[0];
-    // gathers of one slice (all loads independent); supertile count of every item -> sm.key
-    auto gather = [&](uint32_t lo, uint32_t n) -> Quad {
-        Quad q = {0ull, 0ull, 0u, 0u};
-        for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) {
-            const uint32_t gid = __ldcg(order + lo + i);
-            const ushort4 r = a.rect_kept[gid];
-            const uint32_t tt = a.tiles_touched[gid];
-            const uint4 sr = super_rect(r);
-            const uint32_t cc = (sr.y - sr.x) * (sr.w - sr.z);
-            sm.key[i] = cc;
-            q.kept += (uint32_t)(r.y - r.x) * (uint32_t)(r.w - r.z);
-            q.touched += tt;
-            q.vis += tt ? 1u : 0u;
-            q.coarse += cc;
+    // one slice: supertile count of every item -> sm.key, its rect -> rect_sorted; two items per thread in flight
+    auto gather = [&](uint32_t lo, uint32_t n) -> uint32_t {
+        uint32_t sum = 0;
+        for (uint32_t i = tid; i < n; i += 2 * SGS_SORT_THREADS) {
+            const uint32_t i1 = i + SGS_SORT_THREADS;
+            const uint32_t g0 = __ldcg(order + lo + i);
+            const uint32_t g1 = i1 < n ? __ldcg(order + lo + i1) : g0;
+            const ushort4 r0 = a.rect_kept[g0];
+            const ushort4 r1 = a.rect_kept[g1];
+            const uint4 s0 = super_rect(r0), s1 = super_rect(r1);
+            const uint32_t c0 = (s0.y - s0.x) * (s0.w - s0.z), c1 = (s1.y - s1.x) * (s1.w - s1.z);
+            sm.key[i] = c0;
+            a.rect_sorted[lo + i] = r0;
+            sum += c0;
+            if (i1 < n) {
+                sm.key[i1] = c1;
+                a.rect_sorted[lo + i1] = r1;
+                sum += c1;
+            }
         }
-        return q;
+        return sum;
+    };
+    auto block_total = [&](uint32_t v) -> uint32_t {
+        v = __reduce_add_sync(0xFFFFFFFFu, v);
+        __syncthreads();
+        if (lane == 0) sm.wsum[warp] = v;
+        __syncthreads();
+        return __reduce_add_sync(0xFFFFFFFFu, sm.wsum[lane]);
     };
     for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
         const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
-        const Quad tot = block_sum(gather(lo, n), s_w);
-        if (tid == 0) {
-            __stcg(a.blocksum + 4 * (size_t)v, tot.kept);
-            __stcg(a.blocksum + 4 * (size_t)v + 1, tot.touched);
-            __stcg(a.blocksum + 4 * (size_t)v + 2, (unsigned long long)tot.vis);
-            __stcg(a.blocksum + 4 * (size_t)v + 3, (unsigned long long)tot.coarse);
-        }
+        const uint32_t tot = block_total(gather(lo, n));
+        if (tid == 0) __stcg(a.blocksum + v, tot);
     }
     prof_mark(a.prof, pslot);
     grid_barrier(bar, bar_target);
     prof_mark(a.prof, pslot);
     for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
         const uint32_t lo = v * SL, hi = min(P, lo + SL), n = hi > lo ? hi - lo : 0u;
-        Quad pre = {0ull, 0ull, 0u, 0u};     // slices before this one
-        for (uint32_t vv = tid; vv < v; vv += SGS_SORT_THREADS) {
-            pre.kept += __ldcg(a.blocksum + 4 * (size_t)vv);
-            pre.touched += __ldcg(a.blocksum + 4 * (size_t)vv + 1);
-            pre.vis += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)vv + 2);
-            pre.coarse += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)vv + 3);
-        }
-        pre = block_sum(pre, s_w);
+        uint32_t pre = 0;     // slices before this one
+        for (uint32_t vv = tid; vv < v; vv += SGS_SORT_THREADS) pre += __ldcg(a.blocksum + vv);
+        pre = block_total(pre);
         if (!resident) (void)gather(lo, n);
         __syncthreads();
         // block-wide inclusive scan of sm.key[0..n): contiguous segment per thread
@@ -440,36 +495,19 @@ __device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& 
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= (uint32_t)o) inc += y;
         }
+        __syncthreads();
         if (lane == 31) sm.wsum[warp] = inc;
         __syncthreads();
         uint32_t woff = 0;
         for (uint32_t w = 0; w < warp; w++) woff += sm.wsum[w];
-        uint32_t run = pre.coarse + woff + inc - mine;
+        uint32_t run = pre + woff + inc - mine;
         for (uint32_t i = b; i < e; i++) {
             run += sm.key[i];
             sm.val[i] = run;
         }
         __syncthreads();
         for (uint32_t i = tid; i < n; i += SGS_SORT_THREADS) a.coffs[lo + i] = sm.val[i];
-        if (v == VB - 1u && tid == 0) {
-            Quad all = pre;
-            all.kept += __ldcg(a.blocksum + 4 * (size_t)v);
-            all.touched += __ldcg(a.blocksum + 4 * (size_t)v + 1);
-            all.vis += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)v + 2);
-            all.coarse += (uint32_t)__ldcg(a.blocksum + 4 * (size_t)v + 3);
-            a.ctl->kept = all.kept;
-            a.ctl->touched = all.touched;
-            a.ctl->visible = all.vis;
-            a.ctl->coarse = all.coarse;
-            if (a.slot) {
-                volatile HostSlot* hs = a.slot;
-                hs->kept = all.kept;
-                hs->touched = all.touched;
-                hs->visible = all.vis;
-                __threadfence_system();
-                hs->ticket = a.ticket;
-            }
-        }
+        if (v == VB - 1u && tid == 0) a.ctl->coarse = pre + __ldcg(a.blocksum + v);
         __syncthreads();
     }
     prof_mark(a.prof, pslot);
@@ -487,9 +525,10 @@ struct CoarseArgs {
     unsigned long long cap;
     const uint32_t* order;      // Gaussians in depth order
     const uint32_t* coffs;      // inclusive scan of the supertile counts, in depth order
-    const ushort4* rect_kept;
-    uint32_t* keys[2];
+    const ushort4* rect_sorted; // kept rects in depth order
+    uint32_t* keys[2];          // key = supertile id | (mask of the supertile's 16 tiles the rect covers) << 16
     uint32_t* vals[2];
+    unsigned long long* pairs;  // final list: Gaussian index | key << 32, supertile-major, depth order inside
     uint32_t* hist;
     uint2* cranges;             // [n_super] bucket of every supertile in the coarse list
     uint32_t* header;
@@ -519,12 +558,14 @@ __device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a
     for (uint32_t kb = lo;; kb += SGS_SORT_THREADS) {
         const uint32_t k = kb + tid;
         uint32_t n = 0, start = 0, gid = 0;
+        unsigned long long rk = 0ull;
         uint4 sr = make_uint4(0u, 0u, 0u, 0u);
         bool beyond = true;    // this Gaussian's instances end at or after e (nothing more to do past it)
         if (k < P) {
             const uint32_t incl = __ldcg(a.coffs + k);
             gid = __ldcg(a.order + k);
-            sr = super_rect(a.rect_kept[gid]);
+            rk = __ldcg(reinterpret_cast<const unsigned long long*>(a.rect_sorted) + k);
+            sr = super_rect(as_rect(rk));
             n = (sr.y - sr.x) * (sr.w - sr.z);
             start = incl - n;
             beyond = incl >= e;
@@ -536,7 +577,7 @@ __device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a
             for (uint32_t y = sr.z; y < sr.w; y++)
                 for (uint32_t x = sr.x; x < sr.y; x++, j++)
                     if (j >= s && j < e) {
-                        sm.key[j - s] = y * (uint32_t)a.super_x + x;
+                        sm.key[j - s] = (y * (uint32_t)a.super_x + x) | (tile_mask16(as_rect(rk), x * SGS_ST, y * SGS_ST) << 16);
                         sm.val[j - s] = gid;
                     }
         }
@@ -550,10 +591,12 @@ __device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a
             const uint32_t sx0 = __shfl_sync(0xFFFFFFFFu, sr.x, src);
             const uint32_t sy0 = __shfl_sync(0xFFFFFFFFu, sr.z, src);
             const uint32_t sw = __shfl_sync(0xFFFFFFFFu, w, src);
+            const unsigned long long srk = __shfl_sync(0xFFFFFFFFu, rk, src);
             const uint32_t j0 = max(sstart, s) - sstart, j1 = min(sstart + sn, e) - sstart;
             for (uint32_t i = j0 + lane; i < j1; i += 32) {
                 const uint32_t yy = i / sw, xx = i - yy * sw;
-                sm.key[sstart + i - s] = (sy0 + yy) * (uint32_t)a.super_x + (sx0 + xx);
+                const uint32_t sx = sx0 + xx, sy = sy0 + yy;
+                sm.key[sstart + i - s] = (sy * (uint32_t)a.super_x + sx) | (tile_mask16(as_rect(srk), sx * SGS_ST, sy * SGS_ST) << 16);
                 sm.val[sstart + i - s] = sgid;
             }
         }
@@ -594,9 +637,7 @@ __device__ __forceinline__ void coarse_sort_phases(const CoarseArgs& a, SortSmem
         const uint32_t out = (p - 1u) & 1u;
         const uint32_t* in_key = a.keys[out ^ 1u];
         const uint32_t* in_val = a.vals[out ^ 1u];
-        // single-pass sort (digit = supertile id): the keys are dead, the buckets come from the digit totals;
-        // multi-pass: the last pass keeps its keys for coarse_ranges_kernel
-        uint32_t* out_key = (npass == 1u) ? nullptr : a.keys[out];
+        const bool last = p == npass;       // the last pass writes (Gaussian, key) pairs, 8 bytes per store
         auto load = [&](uint32_t lo, uint32_t n) {
             if (p == 1u) {
                 generate_slice(sm, a, lo, lo + n);
@@ -634,7 +675,8 @@ __device__ __forceinline__ void coarse_sort_phases(const CoarseArgs& a, SortSmem
                     a.cranges[d] = tot ? make_uint2(st, st + tot) : make_uint2(0u, 0u);
                 }
             }
-            scatter_slice(sm, n, shift, nd, out_key, a.vals[out]);
+            if (last) scatter_slice_pairs(sm, n, shift, nd, a.pairs);
+            else scatter_slice(sm, n, shift, nd, a.keys[out], a.vals[out]);
             __syncthreads();
         }
         prof_mark(a.prof, pslot);
@@ -646,7 +688,7 @@ __device__ __forceinline__ void coarse_sort_phases(const CoarseArgs& a, SortSmem
 __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) depth_sort_kernel(const DepthArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
-    __shared__ Quad s_w[32];
+    __shared__ Tri s_w[32];
     uint32_t bar_target = 0;
     depth_sort_phases(a, sm, s_w, &a.ctl->bar_depth, bar_target);
 }
@@ -664,21 +706,21 @@ __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) coarse_sort_kernel(const 
 __global__ void __launch_bounds__(SGS_SORT_THREADS, 1) binning_fused_kernel(const DepthArgs d, const CoarseArgs c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
-    __shared__ Quad s_w[32];
+    __shared__ Tri s_w[32];
     uint32_t bar_target = 0;
     depth_sort_phases(d, sm, s_w, &d.ctl->bar_depth, bar_target);
     grid_barrier(&d.ctl->bar_depth, bar_target);     // totals + coffs of every block visible to every block
     coarse_sort_phases(c, sm, &d.ctl->bar_depth, bar_target);
 }
 
-// multi-pass sorts only (more than 512 supertiles): supertile buckets from the sorted keys, one thread per instance
-__global__ void __launch_bounds__(256) coarse_ranges_kernel(const uint32_t* __restrict__ sorted, const BinCtl* ctl,
+// multi-pass sorts only (more than 512 supertiles): supertile buckets from the sorted pairs, one thread per instance
+__global__ void __launch_bounds__(256) coarse_ranges_kernel(const unsigned long long* __restrict__ pairs, const BinCtl* ctl,
                                                             unsigned long long cap, uint2* __restrict__ cranges) {
     if (__ldcg(&ctl->kept) > cap) return;
     const uint32_t Rc = __ldcg(&ctl->coarse);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Rc; i += gridDim.x * blockDim.x) {
-        const uint32_t cur = sorted[i];
-        const uint32_t prev = i ? sorted[i - 1] : 0xFFFFFFFFu;
+        const uint32_t cur = (uint32_t)(pairs[i] >> 32) & 0xFFFFu;
+        const uint32_t prev = i ? ((uint32_t)(pairs[i - 1] >> 32) & 0xFFFFu) : 0xFFFFFFFFu;
         if (cur != prev) {
             cranges[cur].x = i;
             if (i) cranges[prev].y = i;
@@ -692,27 +734,12 @@ __global__ void __launch_bounds__(256) coarse_ranges_kernel(const uint32_t* __re
 // ------------------------------------------------------------------------------------------------
 struct ExpandArgs {
     int tiles_x, tiles_y, super_x, n_tiles;
-    const uint32_t* coarse_list;
+    const unsigned long long* pairs;   // supertile-major coarse list: Gaussian index | (supertile | tile mask << 16) << 32
     const uint2* cranges;
-    const ushort4* rect_kept;
     uint2* ranges;          // [n_tiles]: the count kernel writes .y = count, its last block turns that into [start, end)
     uint32_t* point_list;
     uint32_t* done;         // last-block ticket (zero before and after the kernel)
 };
-
-// bit (4 ly + lx) set  <=>  the kept rect covers tile (tx0 + lx, ty0 + ly)
-__device__ __forceinline__ uint32_t tile_mask16(const ushort4 r, uint32_t tx0, uint32_t ty0) {
-    uint32_t xm = 0, ym = 0;
-#pragma unroll
-    for (uint32_t l = 0; l < SGS_ST; l++) {
-        xm |= ((tx0 + l >= r.x) && (tx0 + l < r.y)) ? (1u << l) : 0u;
-        ym |= ((ty0 + l >= r.z) && (ty0 + l < r.w)) ? (1u << l) : 0u;
-    }
-    uint32_t m = 0;
-#pragma unroll
-    for (uint32_t l = 0; l < SGS_ST; l++) m |= ((ym >> l) & 1u) ? (xm << (4 * l)) : 0u;
-    return m;
-}
 
 __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const ExpandArgs a) {
     __shared__ uint32_t s_cnt[16];
@@ -725,10 +752,12 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const Expan
     if (tid < 16) s_cnt[tid] = 0;
     __syncthreads();
     uint32_t mine = 0;   // lane t < 16 of every warp accumulates tile t
+    (void)tx0;
+    unsigned long long nxt = (cr.x + tid < cr.y) ? __ldcg(a.pairs + cr.x + tid) : 0ull;
     for (uint32_t i0 = cr.x + (tid & ~31u); i0 < cr.y; i0 += SGS_EXP_THREADS) {
         const uint32_t i = i0 + lane;
-        uint32_t m = 0;
-        if (i < cr.y) m = tile_mask16(a.rect_kept[__ldcg(a.coarse_list + i)], tx0, ty0);
+        const uint32_t m = (i < cr.y) ? (uint32_t)(nxt >> 48) : 0u;
+        nxt = (i + SGS_EXP_THREADS < cr.y) ? __ldcg(a.pairs + i + SGS_EXP_THREADS) : 0ull;   // next chunk in flight
 #pragma unroll
         for (uint32_t t = 0; t < 16; t++) {
             const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, (m >> t) & 1u));
@@ -786,13 +815,12 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const Expand
         s_run[tid] = (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) ? a.ranges[ty * a.tiles_x + tx].x : 0u;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long nxt = (cr.x + tid < cr.y) ? __ldcg(a.pairs + cr.x + tid) : 0ull;
     for (uint32_t i0 = cr.x; i0 < cr.y; i0 += SGS_EXP_THREADS) {
         const uint32_t i = i0 + tid;
-        uint32_t m = 0, gid = 0;
-        if (i < cr.y) {
-            gid = __ldcg(a.coarse_list + i);
-            m = tile_mask16(a.rect_kept[gid], tx0, ty0);
-        }
+        const uint32_t gid = (uint32_t)nxt;
+        const uint32_t m = (i < cr.y) ? (uint32_t)(nxt >> 48) : 0u;
+        nxt = (i + SGS_EXP_THREADS < cr.y) ? __ldcg(a.pairs + i + SGS_EXP_THREADS) : 0ull;       // next chunk in flight
         uint32_t before[16];
 #pragma unroll
         for (uint32_t t = 0; t < 16; t++) {
@@ -889,7 +917,9 @@ static DepthArgs make_depth_args(int P, const GeomState& g, HostSlot* slot, unsi
     a.slice = (P + a.vblocks - 1) / a.vblocks;
     a.raw = g.depth_raw;
     a.blk_range = g.blk_range;
+    a.blk_sums = g.blk_sums;
     a.n_blk_range = g.n_blk_range;
+    a.rect_sorted = g.rect_sorted;
     a.keys[0] = g.depth_keys[0];
     a.keys[1] = g.depth_keys[1];
     a.vals[0] = g.depth_vals[0];
@@ -916,7 +946,8 @@ static CoarseArgs make_coarse_args(int P, const ViewParams& vp, const GeomState&
     a.cap = (unsigned long long)b.cap;
     a.order = g.depth_vals[0];
     a.coffs = g.coffs;
-    a.rect_kept = g.rect_kept;
+    a.rect_sorted = g.rect_sorted;
+    a.pairs = b.coarse_pairs;
     a.keys[0] = b.coarse_keys[0];
     a.keys[1] = b.coarse_keys[1];
     a.vals[0] = b.coarse_vals[0];
@@ -933,17 +964,15 @@ static CoarseArgs make_coarse_args(int P, const ViewParams& vp, const GeomState&
 static cudaError_t launch_expand(const CoarseArgs& a, const ViewParams& vp, const GeomState& g, const BinningState& b,
                                  const ImageState& img, cudaStream_t s) {
     const int G = binning_grid_blocks();
-    const int side = binning_coarse_list_side(a.n_super);
     if (coarse_passes(a.n_super) > 1)
-        coarse_ranges_kernel<<<4 * G, 256, 0, s>>>(b.coarse_keys[side], g.ctl, a.cap, img.cranges);
+        coarse_ranges_kernel<<<4 * G, 256, 0, s>>>(b.coarse_pairs, g.ctl, a.cap, img.cranges);
     ExpandArgs x;
     x.tiles_x = vp.tiles_x;
     x.tiles_y = vp.tiles_y;
     x.super_x = a.super_x;
     x.n_tiles = vp.tiles_x * vp.tiles_y;
-    x.coarse_list = b.coarse_vals[side];
+    x.pairs = b.coarse_pairs;
     x.cranges = img.cranges;
-    x.rect_kept = g.rect_kept;
     x.ranges = img.ranges;
     x.point_list = b.point_list;
     x.done = &g.ctl->expand_done;

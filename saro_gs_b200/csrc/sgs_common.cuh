@@ -115,13 +115,15 @@ struct GeomState {
                               //       clipped to the exact bounding box of the alpha >= 1/255 ellipse
     uint32_t* depth_raw;      // [P]   float bits of depth (0xFFFFFFFF when culled), written by preprocess
     uint2*    blk_range;      // [preprocess blocks] (max key, max ~key) over the block's visible Gaussians
+    uint4*    blk_sums;       // [preprocess blocks] (kept tiles, touched tiles, visible Gaussians, -) of the block
+    ushort4*  rect_sorted;    // [P]   rect_kept in depth order (written by the depth-sort kernel's scan)
     int       n_blk_range;
     uint32_t* depth_keys[2];  // [P]   radix-sort ping-pong: normalised keys
     uint32_t* depth_vals[2];  // [P]   radix-sort ping-pong: Gaussian index; [0] ends up holding the depth order
     uint32_t* coffs;          // [P]   inclusive scan, in depth order, of the supertiles each kept rect overlaps
     BinCtl*   ctl;            // control block (see above)
     uint32_t* hist;           // [depth_vblocks + 1][512] per-block digit histograms of the current radix pass
-    unsigned long long* blocksum;  // [depth_vblocks][4] per-block (kept, touched, visible, coarse) of the scan
+    uint32_t* blocksum;       // [depth_vblocks] per-slice supertile count of the scan
     int       depth_vblocks;  // virtual blocks of the depth sort (multiple of the grid size)
 };
 
@@ -151,8 +153,9 @@ struct BinningState {
     uint32_t*   header;         // [32] word 1: kept instances; 2: packed records present; 3: cap
     PackedInst* packed;         // [cap] tile-ordered packed records (tile t uses [ranges[t].x, +tile_count[t]))
     uint32_t*   point_list;     // [cap] Gaussian index of every kept instance, tile-major, depth order inside a tile
-    uint32_t*   coarse_keys[2]; // [cap] supertile id; radix-sort ping-pong (only touched when > 512 supertiles)
-    uint32_t*   coarse_vals[2]; // [cap] Gaussian index; one side ends up holding the supertile-major coarse list
+    uint32_t*   coarse_keys[2]; // [cap] supertile id | tile mask << 16; radix-sort ping-pong (only when > 512 supertiles)
+    uint32_t*   coarse_vals[2]; // [cap] Gaussian index; ping-pong (only when > 512 supertiles)
+    unsigned long long* coarse_pairs;  // [cap] the supertile-major coarse list: Gaussian index | key << 32
     uint32_t*   hist;           // per-block digit histograms of the coarse radix pass
     size_t      cap;
 };

@@ -321,21 +321,34 @@ preprocess_fwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     // [min, max] (fewer radix passes) and gets that range from these partials without a pass over the keys
     {
         __shared__ uint32_t s_kmax[SGS_PRE_THREADS / 32], s_knmin[SGS_PRE_THREADS / 32];
+        __shared__ uint32_t s_kept[SGS_PRE_THREADS / 32], s_touched[SGS_PRE_THREADS / 32], s_vis[SGS_PRE_THREADS / 32];
         const uint32_t kx = __reduce_max_sync(0xFFFFFFFFu, visible ? out_key : 0u);
         const uint32_t kn = __reduce_max_sync(0xFFFFFFFFu, visible ? ~out_key : 0u);
+        // the instance totals do not depend on the depth order: block partials here, reduced by the binning kernel
+        const uint32_t area = (uint32_t)(out_rect.y - out_rect.x) * (uint32_t)(out_rect.w - out_rect.z);
+        const uint32_t sk = __reduce_add_sync(0xFFFFFFFFu, area);
+        const uint32_t st = __reduce_add_sync(0xFFFFFFFFu, out_tiles);
+        const uint32_t sv = __reduce_add_sync(0xFFFFFFFFu, visible ? 1u : 0u);
         if ((threadIdx.x & 31) == 0) {
             s_kmax[threadIdx.x >> 5] = kx;
             s_knmin[threadIdx.x >> 5] = kn;
+            s_kept[threadIdx.x >> 5] = sk;
+            s_touched[threadIdx.x >> 5] = st;
+            s_vis[threadIdx.x >> 5] = sv;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t a = 0u, b = 0u;
+            uint32_t a = 0u, b = 0u, c = 0u, d = 0u, e = 0u;
 #pragma unroll
             for (int w = 0; w < SGS_PRE_THREADS / 32; w++) {
                 a = max(a, s_kmax[w]);
                 b = max(b, s_knmin[w]);
+                c += s_kept[w];
+                d += s_touched[w];
+                e += s_vis[w];
             }
             g.blk_range[blockIdx.x] = make_uint2(a, b);
+            g.blk_sums[blockIdx.x] = make_uint4(c, d, e, 0u);
         }
     }
     if (!valid) return;
