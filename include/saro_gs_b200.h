@@ -219,6 +219,14 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
  * radii_max (MAX), then commits on every rank.  Both return 0 or a negative error code. */
 int sgs_densify_add_view(int P, const float* dL_dmeans2D, const int* radii, float* grad_sum, int* vis_count, int* radii_max,
                          void* stream);
+/* Fused form of sgs_densify_add_view: arms the calling thread's NEXT sgs_backward call (of P Gaussians) to apply the
+ * same update to the three running buffers in the epilogue of its last kernel, where dL_dmeans2D and radii are in
+ * registers — no extra launch and no re-read (the reference appends to its lists right after loss.backward(),
+ * train.py:211-215).  One-shot: the sink is cleared by that sgs_backward call whether it succeeds or not; all three
+ * pointers NULL disarms it.  Call it from the thread that calls sgs_backward (in PyTorch: inside the autograd
+ * function's backward — saro_gs_b200.densify.BatchDensifyStats.attach_next_backward does that).  Returns 0 or a
+ * negative error code. */
+int sgs_densify_attach(int P, float* grad_sum, int* vis_count, int* radii_max);
 int sgs_densify_commit(int P, const float* grad_sum, const int* vis_count, const int* radii_max, float* max_radii2D,
                        float* xyz_gradient_accum, float* denom, void* stream);
 

@@ -49,6 +49,7 @@ ABI = {
     "sgs_deform_pack_mlp": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_deform_eval": (_i64, [_i, _i, _f] + [_vp] * 10 + [_vp, ctypes.c_size_t] + [_vp] * 5 + [_vp]),
     "sgs_densify_add_view": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_densify_attach": (_i, [_i, _vp, _vp, _vp]),
     "sgs_densify_commit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_plane_levels": (_i, [_i, _i, _i]),
     "sgs_plane_pyramid_floats": (ctypes.c_size_t, [_i, _i, _i, _i]),

@@ -146,6 +146,25 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     return int(rendered), out_color, radii, bufs[_GEOM], bufs[_BINNING], bufs[_IMAGE], out_depth
 
 
+# Densification statistics armed for the next backward call (densify.BatchDensifyStats.attach_next_backward).  A plain
+# module slot, not a thread-local: autograd runs backward on its own thread, the arming call comes from the caller's.
+_pending_densify = None
+_pending_lock = threading.Lock()
+
+
+def arm_densify_sink(stats):
+    global _pending_densify
+    with _pending_lock:
+        _pending_densify = stats
+
+
+def _take_densify_sink():
+    global _pending_densify
+    with _pending_lock:
+        stats, _pending_densify = _pending_densify, None
+    return stats
+
+
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
                                  degree, campos, geomBuffer, R, binningBuffer, imageBuffer):
@@ -190,8 +209,15 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     dL_drotations = torch.empty((P, 4), **opts)
     dL_dacc = torch.empty((P, 12), **opts)
 
+    sink = _take_densify_sink()
+    if sink is not None and (sink.P != P or sink.device != dev):
+        raise RuntimeError(f"densification statistics armed for {sink.P} Gaussians on {sink.device}, backward runs "
+                           f"{P} on {dev}")
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if sink is not None:    # same thread as sgs_backward below: the C side keeps the sink per thread, one-shot
+            _check(lib.sgs_densify_attach(P, sink.grad_sum.data_ptr(), sink.vis_count.data_ptr(),
+                                          sink.radii_max.data_ptr()), "sgs_densify_attach")
         rc = lib.sgs_backward(
             P, int(degree), M, int(R), _ptr(background), W, H,
             _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
@@ -201,6 +227,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations),
             ctypes.c_void_p(stream))
     _check(rc, "sgs_backward")
+    if sink is not None:
+        sink.views += 1
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

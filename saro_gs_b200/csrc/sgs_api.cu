@@ -433,6 +433,29 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     return (int64_t)R;
 }
 
+// one-shot sink of the calling thread, armed by sgs_densify_attach and consumed by its next sgs_backward
+struct PendingSink {
+    int P = -1;
+    sgs::DensifySink sink{nullptr, nullptr, nullptr};
+};
+static PendingSink& pending_sink() {
+    thread_local PendingSink p;
+    return p;
+}
+
+int sgs_densify_attach(int P, float* grad_sum, int* vis_count, int* radii_max) {
+    PendingSink& p = pending_sink();
+    if (!grad_sum && !vis_count && !radii_max) {   // detach
+        p = PendingSink();
+        return 0;
+    }
+    if (P < 0 || !grad_sum || !vis_count || !radii_max)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_densify_attach: bad size or null running buffer");
+    p.P = P;
+    p.sink = sgs::DensifySink{grad_sum, vis_count, radii_max};
+    return 0;
+}
+
 int sgs_backward(int P, int D, int M, int64_t R, const float* background, int width, int height,
                  const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                  float scale_modifier, const float* rotations, const float* cov3D_precomp,
@@ -442,6 +465,12 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                  void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    // the densification sink is consumed by this call whatever its outcome (it must never leak into a later view)
+    const PendingSink armed = pending_sink();
+    pending_sink() = PendingSink();
+    const sgs::DensifySink sink = armed.sink;
+    if (sink.grad_sum && armed.P != P)
+        return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: sgs_densify_attach was armed for a different number of Gaussians");
     if (P < 0 || R < 0 || width <= 0 || height <= 0) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: bad sizes");
     if (P == 0) return 0;
     if (!geom_buffer || !binning_buffer || !image_buffer)
@@ -473,7 +502,7 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
         StageScope sc(SGS_STAGE_PREPROCESS_BWD, s, 1);
         sgs::launch_preprocess_bwd(P, vp, means3D, radii, shs, cov3D_precomp ? nullptr : scales,
                                    cov3D_precomp ? nullptr : rotations, cov3D, g, dL_dacc, dL_dmean2D, dL_dopacity,
-                                   dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, s);
+                                   dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, sink, s);
     }
     (void)colors_precomp;
     SGS_CUDA_OK(cudaGetLastError());

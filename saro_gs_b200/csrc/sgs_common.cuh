@@ -279,10 +279,17 @@ void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageS
 void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, const float* dL_dpix,
                        float* acc /*[P][12]*/, cudaStream_t s);
 
+// running buffers of the densification statistics (sgs_densify_attach): all NULL = not attached
+struct DensifySink {
+    float* grad_sum;
+    int* vis_count;
+    int* radii_max;
+};
+
 void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, const int* radii, const float* shs,
                            const float* scales, const float* rotations, const float* cov3D, GeomState g,
                            const float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                           cudaStream_t s);
+                           DensifySink sink, cudaStream_t s);
 
 }  // namespace sgs

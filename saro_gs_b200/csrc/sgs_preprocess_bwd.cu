@@ -49,7 +49,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       const float4* __restrict__ conic_opacity, const float* __restrict__ acc, float* __restrict__ dL_dmean2D,
                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
-                      float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int rot_vec) {
+                      float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int rot_vec, const DensifySink sink) {
     __shared__ ViewSmem cam;
     // SH rows travel through shared memory so that both the 192-B reads and the 192-B gradient writes of a
     // warp are fully coalesced (32 consecutive rows = 6 KB contiguous)
@@ -352,6 +352,14 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
             dL_dscale[3 * idx + i] = o_scale[i];
         }
         dL_dopacity[idx] = o_opacity;
+        // densification statistics of this view (train.py:211-215 of the reference) as an epilogue: the means2D gradient
+        // and the radius are in registers, so sgs_densify_add_view costs no launch and no re-read (csrc/sgs_densify.cu
+        // holds the stand-alone kernel with the same arithmetic).  Culled Gaussians would add 0 / 0 / max(., 0).
+        if (sink.grad_sum && pre_radius > 0) {
+            sink.grad_sum[idx] += sqrtf(o_mean2D[0] * o_mean2D[0] + o_mean2D[1] * o_mean2D[1]);
+            sink.vis_count[idx] += 1;
+            sink.radii_max[idx] = max(sink.radii_max[idx], pre_radius);
+        }
 #pragma unroll
         for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = o_cov[i];
         if (rot_vec) {
@@ -405,7 +413,7 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
                            const float* scales, const float* rotations, const float* cov3D, GeomState g,
                            const float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                           cudaStream_t s) {
+                           DensifySink sink, cudaStream_t s) {
     if (P <= 0) return;
     const int block = SGS_PRE_THREADS, grid = (P + block - 1) / block;
     const bool vec = (shs != nullptr) && vp.sh_coeffs == 16 && ((reinterpret_cast<size_t>(shs) & 15) == 0) &&
@@ -415,11 +423,11 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
     if (vec)
         preprocess_bwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
                                                           g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec);
+                                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
     else
         preprocess_bwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
                                                            g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec);
+                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
 }
 
 }  // namespace sgs

@@ -24,9 +24,16 @@
 //     Gaussian in the fused backward-preprocess kernel;
 //   * the accum_rec recursion is carried as ONE scalar  a = sum_c accum_rec[c] dL/dpix[c]  (the
 //     reference carries 3 colours and re-dots them with dL/dpix for every pair);
-//   * the 9 sums are reduced across the warp's 64 pixels with a 12-shuffle "transposing" butterfly,
-//     then one RED.ADD.F32 per value per (warp, instance) into a [P][12] accumulator
-//     => 64x fewer L2 atomics than the reference.
+//   * reduction across the warp's 64 pixels (G = SGS_B_STASH visits at a time): every lane parks its SIX
+//     dx-independent partial sums (sum g, sum g dy, sum g dy^2, sum w dL/dpix[c]) of a visit in a per-warp
+//     shared-memory stash; after G visits lane l owns (visit l / 6, value l % 6): it reads the 32 partials as
+//     8 x LDS.128, adds the four lane rows, and only then forms the dx moments from the 8 COLUMN sums
+//     (all lanes of a column share dx) — sum g dx, sum g dx^2, sum g dx dy cost nothing per visit.  One
+//     RED.ADD.F32 per value per (warp, instance) into a [P][12] accumulator => 64x fewer L2 atomics than the
+//     reference, and ~25 instead of ~55 instructions per visit for the reduction compared with the 12-shuffle
+//     transposing butterfly of round 1 (kept as the G = 0 variant for A/B measurements).
+#include <cstdlib>
+
 #include "sgs_render_common.cuh"
 
 namespace sgs {
@@ -117,16 +124,37 @@ __forceinline__ __device__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-#define SGS_B_STAGES 3
-#define SGS_B_STAGE_BYTES (SGS_R_BATCH * 48)
+template <int OFF>
+__forceinline__ __device__ void sts32_off(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(addr), "f"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__forceinline__ __device__ float4 lds128_off(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr), "n"(OFF));
+    return v;
+}
+__forceinline__ __device__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__forceinline__ __device__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__forceinline__ __device__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
 
-__global__ void __launch_bounds__(SGS_R_THREADS)
+#define SGS_B_STAGES 3
+#define SGS_B_PAIR_STRIDE 144   // bytes per stashed (visit, value) row: 32 lanes x 4 B + 16 B pad (conflict-free LDS.128)
+
+// BATCH: records per TMA batch.  G: visits per stash flush (0 = round-1 butterfly reduction).
+template <int BATCH, int G, int MINB>
+__global__ void __launch_bounds__(SGS_R_THREADS, MINB)
 render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
                   const uint32_t* __restrict__ tile_count, const PackedInst* __restrict__ packed,
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dpix, float* __restrict__ acc) {
     // ring of record batches filled by TMA bulk copies; no block-wide barrier in the main loop
+    constexpr int SGS_B_STAGE_BYTES = BATCH * 48;
+    constexpr int STASH_WARP_BYTES = G > 0 ? (G * 6 * SGS_B_PAIR_STRIDE + 16 * ((G * 8 + 15) / 16)) : 16;
     __shared__ __align__(128) unsigned char s_rec[SGS_B_STAGES * SGS_B_STAGE_BYTES];
+    __shared__ __align__(16) unsigned char s_stash[(SGS_R_THREADS / 32) * STASH_WARP_BYTES];
     __shared__ __align__(8) uint64_t s_full[SGS_B_STAGES];   // mbarriers: "batch has landed"
     __shared__ uint32_t s_done[SGS_B_STAGES];                // warps that finished the batch in this stage
 
@@ -146,15 +174,15 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const uint32_t start = ranges[tile].x;
     const int count = (int)tile_count[tile];
     if (count == 0) return;
-    const int nb = (count + SGS_R_BATCH - 1) / SGS_R_BATCH;      // batches, walked from the back of the list
+    const int nb = (count + BATCH - 1) / BATCH;      // batches, walked from the back of the list
     const unsigned char* src = reinterpret_cast<const unsigned char*>(packed + start);
     uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
     const uint32_t full_base = (uint32_t)__cvta_generic_to_shared(s_full);
     asm volatile("" : "+r"(rec_base));
 
-    // batch j covers records [lo, hi) with hi = count - 128 j
+    // batch j covers records [lo, hi) with hi = count - BATCH j
     auto issue = [&](int j) {
-        const int hi = count - j * SGS_R_BATCH, lo = max(0, hi - SGS_R_BATCH);
+        const int hi = count - j * BATCH, lo = max(0, hi - BATCH);
         const uint32_t bytes = (uint32_t)(hi - lo) * 48u;
         const int stage = j % SGS_B_STAGES;
         mbar_expect_tx(full_base + stage * 8, bytes);
@@ -190,18 +218,63 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     // warp-uniform bound: records at list positions >= this were blended by no pixel of the warp
     const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(st.lc0, st.lc1));
 
-    // which accumulator slot this lane owns after the butterfly (see the reduction below)
+    // G == 0: which accumulator slot this lane owns after the butterfly (see the reduction below)
     //   bit1 set -> value 4 ; else value = (bit4 ? 5 : 0) + (bit2 ? 2 : 0) + (bit3 ? 1 : 0)
     const int my_slot = (lane & 2) ? 4 : (((lane & 16) ? 5 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 8) ? 1 : 0));
     const bool writer = (lane & 1) == 0 && ((lane & 2) == 0 || lane == 2);
     const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
     float* const acc_lane = acc + my_slot;
 
+    // G > 0: the warp's stash = G x 6 rows of 32 lane partials (+ pad), then G x (Gaussian x, Gaussian id).
+    // At a flush lane l reduces row l = (visit l / 6, value l % 6); values: 0 sum g, 1 sum g dy, 2 sum g dy^2,
+    // 3..5 sum w dL/dpix[c].  Accumulator slots (consumed by preprocess_bwd_kernel): 0 g dx, 1 g dy, 2 g dx^2,
+    // 3 g dx dy, 4 g dy^2, 5 g, 6..8 colour.
+    const uint32_t stash_base = (uint32_t)__cvta_generic_to_shared(s_stash) + warp * STASH_WARP_BYTES;
+    const uint32_t meta_base = stash_base + G * 6 * SGS_B_PAIR_STRIDE;
+    const int fl_v = lane / 6, fl_k = lane - 6 * fl_v;
+    const int fl_slot = fl_k == 0 ? 5 : (fl_k == 1 ? 1 : (fl_k == 2 ? 4 : fl_k + 3));
+    const float pxb = (float)(tx0 + (warp & 1) * SGS_Q);   // x of the quadrant's first pixel column
+    uint32_t stash_wr = stash_base + lane * 4u;
+    int nst = 0;                                            // visits in the stash (warp-uniform)
+    auto flush = [&](int nv) {
+        __syncwarp();
+        if (lane < nv * 6) {
+            const uint32_t row = stash_base + lane * SGS_B_PAIR_STRIDE;
+            // partial i came from lane i = 8 r + c (r: pixel-row pair, c: pixel column): add the four r
+            const float4 q0 = lds128_off<0>(row), q1 = lds128_off<16>(row), q2 = lds128_off<32>(row),
+                         q3 = lds128_off<48>(row), q4 = lds128_off<64>(row), q5 = lds128_off<80>(row),
+                         q6 = lds128_off<96>(row), q7 = lds128_off<112>(row);
+            const float2 c01 = add2(add2(lo2(q0), lo2(q2)), add2(lo2(q4), lo2(q6)));
+            const float2 c23 = add2(add2(hi2(q0), hi2(q2)), add2(hi2(q4), hi2(q6)));
+            const float2 c45 = add2(add2(lo2(q1), lo2(q3)), add2(lo2(q5), lo2(q7)));
+            const float2 c67 = add2(add2(hi2(q1), hi2(q3)), add2(hi2(q5), hi2(q7)));
+            float gx;
+            uint32_t gid;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(gx), "=r"(gid) : "r"(meta_base + fl_v * 8u));
+            // dx of column c exactly as the visit computed it: x - (float)px
+            const float2 gx2 = make_float2(gx, gx);
+            const float2 d01 = add2(gx2, make_float2(-pxb, -(pxb + 1.f)));
+            const float2 d23 = add2(gx2, make_float2(-(pxb + 2.f), -(pxb + 3.f)));
+            const float2 d45 = add2(gx2, make_float2(-(pxb + 4.f), -(pxb + 5.f)));
+            const float2 d67 = add2(gx2, make_float2(-(pxb + 6.f), -(pxb + 7.f)));
+            const float2 t01 = __fmul2_rn(c01, d01), t23 = __fmul2_rn(c23, d23), t45 = __fmul2_rn(c45, d45),
+                         t67 = __fmul2_rn(c67, d67);
+            const float2 s0 = add2(add2(c01, c23), add2(c45, c67));
+            const float2 s1 = add2(add2(t01, t23), add2(t45, t67));
+            const float2 s2 = __ffma2_rn(t01, d01, __ffma2_rn(t23, d23, __ffma2_rn(t45, d45, __fmul2_rn(t67, d67))));
+            float* const dst = acc + (size_t)(gid & 0x0FFFFFFFu) * 12;
+            atomicAdd(dst + fl_slot, s0.x + s0.y);
+            if (fl_k < 2) atomicAdd(dst + (fl_k == 0 ? 0 : 3), s1.x + s1.y);
+            if (fl_k == 0) atomicAdd(dst + 2, s2.x + s2.y);
+        }
+        __syncwarp();
+    };
+
     __syncthreads();   // mbarrier initialisation visible to every warp (the only block-wide barrier)
 
     for (int j = 0; j < nb; j++) {
         const int stage = j % SGS_B_STAGES;
-        const int hi = count - j * SGS_R_BATCH, lo = max(0, hi - SGS_R_BATCH);
+        const int hi = count - j * BATCH, lo = max(0, hi - BATCH);
         const int nrec = hi - lo;
         const uint32_t sbase = rec_base + stage * SGS_B_STAGE_BYTES;
         mbar_wait(full_base + stage * 8, (uint32_t)((j / SGS_B_STAGES) & 1));
@@ -210,7 +283,7 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
         // warp's last contributor
         uint32_t mywords = 0;
 #pragma unroll
-        for (int k = 0; k < SGS_R_BATCH / 32; k++) {
+        for (int k = 0; k < BATCH / 32; k++) {
             const int slot = k * 32 + lane;
             bool v = false;
             if (slot < nrec) {
@@ -222,7 +295,7 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
             if (lane == k) mywords = b;
         }
 
-        for (int k = SGS_R_BATCH / 32 - 1; k >= 0; k--) {
+        for (int k = BATCH / 32 - 1; k >= 0; k--) {
             uint32_t word = __shfl_sync(0xFFFFFFFFu, mywords, k);
             while (word) {
                 const uint32_t bit = 31u - __clz(word);
@@ -248,14 +321,34 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 // moments of g over this thread's two pixels (dx shared)
                 const float2 gy = __fmul2_rn(g, dy);
                 float v5 = g.x + g.y;                       // sum g            -> dL/dopacity
-                float v0 = v5 * dx;                         // sum g dx
                 float v1 = gy.x + gy.y;                     // sum g dy
-                float v2 = v0 * dx;                         // sum g dx^2
-                float v3 = v1 * dx;                         // sum g dx dy
                 float v4 = fmaf(gy.y, dy.y, gy.x * dy.x);   // sum g dy^2
                 float v6 = fmaf(w.y, st.d0.y, w.x * st.d0.x);   // sum alpha T dL/dpix[c]  -> dL/dcolour
                 float v7 = fmaf(w.y, st.d1.y, w.x * st.d1.x);
                 float v8 = fmaf(w.y, st.d2.y, w.x * st.d2.x);
+
+                if (G > 0) {
+                    // park the six dx-independent partials; the dx moments are formed per column at the flush
+                    sts32_off<0 * SGS_B_PAIR_STRIDE>(stash_wr, v5);
+                    sts32_off<1 * SGS_B_PAIR_STRIDE>(stash_wr, v1);
+                    sts32_off<2 * SGS_B_PAIR_STRIDE>(stash_wr, v4);
+                    sts32_off<3 * SGS_B_PAIR_STRIDE>(stash_wr, v6);
+                    sts32_off<4 * SGS_B_PAIR_STRIDE>(stash_wr, v7);
+                    sts32_off<5 * SGS_B_PAIR_STRIDE>(stash_wr, v8);
+                    if (lane == 0)
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(meta_base + nst * 8u), "f"(ra.x),
+                                     "r"(__float_as_uint(c.w)) : "memory");
+                    stash_wr += 6 * SGS_B_PAIR_STRIDE;
+                    if (++nst == G) {
+                        flush(G);
+                        nst = 0;
+                        stash_wr = stash_base + lane * 4u;
+                    }
+                    continue;
+                }
+                float v0 = v5 * dx;                         // sum g dx
+                float v2 = v0 * dx;                         // sum g dx^2
+                float v3 = v1 * dx;                         // sum g dx dy
 
                 // transposing butterfly: 9 values x 32 lanes -> one value per writer lane
                 // step 1 (xor 16): pairs (v0,v5) (v1,v6) (v2,v7) (v3,v8); v4 reduced plainly
@@ -291,13 +384,26 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
             }
         }
     }
+    if (G > 0 && nst) flush(nst);
 }
 
 void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, const float* dL_dpix, float* acc,
                        cudaStream_t s) {
     dim3 grid(vp.tiles_x, vp.tiles_y, 1);
-    render_bwd_kernel<<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, img.final_T,
-                                                    img.n_contrib, dL_dpix, acc);
+    // developer switch for A/B measurements (tools/bwd_variants.py): SGS_BWD_VARIANT = 0 butterfly reduction,
+    // 1 stash reduction (default), 2 stash reduction with 64-record batches capped at 64 registers (8 CTAs per SM), 3 the same without the cap
+    static const int variant = [] {
+        const char* e = getenv("SGS_BWD_VARIANT");
+        return e ? atoi(e) : 1;
+    }();
+#define SGS_LAUNCH_RB(BATCH, G, MINB)                                                                        \
+    render_bwd_kernel<BATCH, G, MINB><<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, \
+                                                                     img.final_T, img.n_contrib, dL_dpix, acc)
+    if (variant == 0) SGS_LAUNCH_RB(128, 0, 10);
+    else if (variant == 2) SGS_LAUNCH_RB(64, 5, 8);
+    else if (variant == 3) SGS_LAUNCH_RB(64, 5, 7);
+    else SGS_LAUNCH_RB(128, 5, 6);
+#undef SGS_LAUNCH_RB
 }
 
 }  // namespace sgs

@@ -11,6 +11,7 @@ buffers are all-reduced between the two.  No CPU / PyTorch fallback: CPU tensors
     for cam in batch:
         ... render, loss.backward() ...
         stats.add_view(viewspace_point_tensor.grad, radii)    # replaces train.py:211-215
+        # (or, fused: stats.attach_next_backward() BEFORE loss.backward() — the rasterizer's backward does it)
     stats.all_reduce()                                        # data parallel only
     stats.commit(gaussians)                                   # replaces train.py:281-292
 """
@@ -57,6 +58,13 @@ class BatchDensifyStats:
         if rc != 0:
             raise RuntimeError(f"sgs_densify_add_view failed ({rc}): {_lib.last_error()}")
         self.views += 1
+
+    def attach_next_backward(self):
+        """Fused form of add_view: the NEXT rasterizer backward (of self.P Gaussians on self.device) applies this view's
+        update in the epilogue of its last kernel — no extra launch, the gradient and the radii are still in registers.
+        Call it before loss.backward(); do not also call add_view for that view."""
+        from . import backend
+        backend.arm_densify_sink(self)
 
     def all_reduce(self, group=None):
         """Data-parallel training: combine the views of all ranks (NCCL over NVLink; three small collectives)."""
