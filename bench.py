@@ -662,7 +662,51 @@ def densify_path_timing(dev, P=300_000, V=4, iters=20):
     agree = torch.equal(ma.max_radii2D, mb.max_radii2D) and torch.equal(ma.denom, mb.denom) and \
         torch.allclose(ma.xyz_gradient_accum, mb.xyz_gradient_accum, rtol=1e-5)
     return {"what": "densification statistics, %d views x %d Gaussians (6 launches: launch-latency bound)" % (V, P),
-            "fused_ms": a, "pytorch_ops_ms": b, "speedup": b / a, "agree": bool(agree)}
+            "fused_ms": a, "pytorch_ops_ms": b, "speedup": b / a, "agree": bool(agree),
+            "in_backward": densify_in_backward_timing(dev)}
+
+
+def densify_in_backward_timing(dev, iters=20):
+    """The per-view statistics update as an epilogue of the rasterizer's backward (BatchDensifyStats.attach_next_backward
+    -> sgs_densify_attach): rasterizer forward + backward of the configs[1] view with the sink armed, without it, and
+    without it but followed by the stand-alone add_view kernel."""
+    import saro_gs_b200 as sgs
+    from saro_gs_b200.densify import BatchDensifyStats
+    scene, cams, params, cot = make_inputs(dev, 0)
+    c = cams[0]
+    rs = sgs.GaussianRasterizationSettings(c.height, c.width, c.tanfovx, c.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                           c.viewmatrix.to(dev), c.projmatrix.to(dev), scene.sh_degree, c.campos.to(dev), False)
+    cot = cot.to(dev)
+    P = params["means3D"].shape[0]
+    stats = BatchDensifyStats(P, dev)
+
+    def step(mode):
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii, _ = sgs.GaussianRasterizer(rs)(means3D=params["means3D"], means2D=m2d, opacities=params["opacities"],
+                                                     shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        if mode == "armed":
+            stats.attach_next_backward()
+        color.backward(cot)
+        if mode == "separate":
+            stats.add_view(m2d.grad, radii)
+        for p in params.values():
+            p.grad = None
+
+    out = {}
+    for mode in ("plain", "armed", "separate"):
+        for _ in range(5):
+            step(mode)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step(mode)
+        e1.record()
+        torch.cuda.synchronize()
+        out[mode + "_ms_per_view"] = e0.elapsed_time(e1) / iters
+    out["what"] = "rasterizer forward + backward of the configs[1] view: no statistics / statistics in the backward's " \
+                  "epilogue / stand-alone add_view kernel after backward"
+    return out
 
 
 def cpu_baseline(precision="f32"):

@@ -49,10 +49,7 @@ __forceinline__ __device__ float xsplit(float lo, float hi, bool upper, int xorm
 // packed FMUL2 / FFMA2 / FADD2 instructions (one issue slot for both pixels).
 struct BwdPix2 {
     float2 T;           // transmittance in front of the instance being visited
-    float2 a_rec;       // sum_c accum_rec[c] * dL/dpix[c]
-    float2 last_alpha;  // alpha of the previously visited (= next deeper) blended instance
-    float2 last_cd;     // its colour . dL/dpix
-    float2 last_om;     // 1 - last_alpha
+    float2 a_rec;       // sum_c accum_rec[c] * dL/dpix[c] over the instances behind the one being visited
     float2 d0, d1, d2;  // dL/dpix
     float2 bgT;         // -T_final * (bg . dL/dpix)
     uint32_t lc0, lc1;  // n_contrib of the two pixels
@@ -63,35 +60,36 @@ __forceinline__ __device__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y
 
 // two pixels x one instance: g = G * dL/dalpha and w = alpha * T per pixel (0 when the pair did not blend).
 // A pixel that does not blend runs through the same packed code with alpha = G = 0: then 1 - alpha = 1, its
-// reciprocal is exactly 1, T is unchanged, g = w = 0, and the pending accum_rec fold  a <- la*lcd + lom*a  is
-// merely applied one step early (afterwards la = 0, lom = 1, so the next fold returns a bit for bit).
+// reciprocal is exactly 1, T is unchanged, g = w = 0, and the accum_rec fold  a <- alpha*cd + (1 - alpha)*a  returns a
+// bit for bit.  The reference folds the PREVIOUS blended instance at the start of the next one
+// ($R/cuda_rasterizer/backward.cu:515-519); folding the current one at the end of its own visit is the same
+// sequence of operations on the same values without three carried register pairs.
 __forceinline__ __device__ void grad_pixels2(BwdPix2& s, float2 pw, bool act0, bool act1, float o, const float4 c,
                                              float2& g, float2& w) {
     // accurate expf() and a < 1 ulp reciprocal, like forward / the reference: alpha must equal forward's bit for
     // bit and T is recovered by a long product of 1/(1-alpha) factors — a bare ex2.approx / rcp.approx (~1e-7
     // each, but biased) drifts T by ~n * 1e-7 over n blended instances (measured: 2.5x the error on dL/dmeans3D).
     float2 G = expf2_exact(pw);        // both pixels, branch-free, bit-identical to expf (sgs_render_common.cuh)
-    if (!act0) G.x = 0.f;
-    if (!act1) G.y = 0.f;
     float2 alpha = __fmul2_rn(bcast2(o), G);
-    alpha.x = min(0.99f, alpha.x);
-    alpha.y = min(0.99f, alpha.y);
-    if (alpha.x < 1.0f / 255.0f) { alpha.x = 0.f; G.x = 0.f; }
-    if (alpha.y < 1.0f / 255.0f) { alpha.y = 0.f; G.y = 0.f; }
+    // one predicate per pixel: passed the power tests AND alpha >= 1/255 (an inactive lane's G may be anything,
+    // NaN included: the comparison is then false or irrelevant, the selects below drop the value)
+    const bool go0 = act0 && !(alpha.x < 1.0f / 255.0f);
+    const bool go1 = act1 && !(alpha.y < 1.0f / 255.0f);
+    alpha.x = go0 ? min(0.99f, alpha.x) : 0.f;
+    alpha.y = go1 ? min(0.99f, alpha.y) : 0.f;
+    G.x = go0 ? G.x : 0.f;
+    G.y = go1 ? G.y : 0.f;
     const float2 om = __fadd2_rn(bcast2(1.f), neg2(alpha));   // in [0.01, 1]
     float2 inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(om.x));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(om.y));
     inv = __ffma2_rn(inv, __ffma2_rn(neg2(om), inv, bcast2(1.f)), inv);   // one Newton step: < 1 ulp
     s.T = __fmul2_rn(s.T, inv);                                            // $R/.../backward.cu:503
-    s.a_rec = __ffma2_rn(s.last_alpha, s.last_cd, __fmul2_rn(s.last_om, s.a_rec));   // :515-519, dotted with dL/dpix
     const float2 cd = __ffma2_rn(bcast2(c.z), s.d2, __ffma2_rn(bcast2(c.y), s.d1, __fmul2_rn(bcast2(c.x), s.d0)));
     const float2 dL_dalpha = __ffma2_rn(__fadd2_rn(cd, neg2(s.a_rec)), s.T, __fmul2_rn(s.bgT, inv));   // :519-534
     g = __fmul2_rn(G, dL_dalpha);
     w = __fmul2_rn(alpha, s.T);
-    s.last_alpha = alpha;
-    s.last_cd = cd;
-    s.last_om = om;
+    s.a_rec = __ffma2_rn(alpha, cd, __fmul2_rn(om, s.a_rec));              // :515-519, dotted with dL/dpix
 }
 
 // ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UBLKCP + SYNCS) ---------------------------------------
@@ -144,6 +142,8 @@ __forceinline__ __device__ float2 hi2(float4 v) { return make_float2(v.z, v.w); 
 #define SGS_B_PAIR_STRIDE 144   // bytes per stashed (visit, value) row: 32 lanes x 4 B + 16 B pad (conflict-free LDS.128)
 
 // BATCH: records per TMA batch.  G: visits per stash flush (0 = round-1 butterfly reduction).
+// (Measured and dropped: one single-warp CTA per 8x8 quadrant with its own record ring — no warp waits for a slower
+// quadrant of its tile, but 4x the L2 reads and 24 instead of 32 resident warps: 348 us against 326 us.)
 template <int BATCH, int G, int MINB>
 __global__ void __launch_bounds__(SGS_R_THREADS, MINB)
 render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict__ ranges,
@@ -152,7 +152,7 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                   const float* __restrict__ dL_dpix, float* __restrict__ acc) {
     // ring of record batches filled by TMA bulk copies; no block-wide barrier in the main loop
     constexpr int SGS_B_STAGE_BYTES = BATCH * 48;
-    constexpr int STASH_WARP_BYTES = G > 0 ? (G * 6 * SGS_B_PAIR_STRIDE + 16 * ((G * 8 + 15) / 16)) : 16;
+    constexpr int STASH_WARP_BYTES = G > 0 ? G * 8 * SGS_B_PAIR_STRIDE : 16;
     __shared__ __align__(128) unsigned char s_rec[SGS_B_STAGES * SGS_B_STAGE_BYTES];
     __shared__ __align__(16) unsigned char s_stash[(SGS_R_THREADS / 32) * STASH_WARP_BYTES];
     __shared__ __align__(8) uint64_t s_full[SGS_B_STAGES];   // mbarriers: "batch has landed"
@@ -212,8 +212,7 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
         const float b0 = vp.bg[0], b1 = vp.bg[1], b2 = vp.bg[2];
         st.bgT = make_float2(-Tf0 * (b0 * st.d0.x + b1 * st.d1.x + b2 * st.d2.x),     // :531-534
                              -Tf1 * (b0 * st.d0.y + b1 * st.d1.y + b2 * st.d2.y));
-        st.a_rec = st.last_alpha = st.last_cd = make_float2(0.f, 0.f);
-        st.last_om = make_float2(1.f, 1.f);
+        st.a_rec = make_float2(0.f, 0.f);
     }
     // warp-uniform bound: records at list positions >= this were blended by no pixel of the warp
     const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(st.lc0, st.lc1));
@@ -225,38 +224,33 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
     float* const acc_lane = acc + my_slot;
 
-    // G > 0: the warp's stash = G x 6 rows of 32 lane partials (+ pad), then G x (Gaussian x, Gaussian id).
-    // At a flush lane l reduces row l = (visit l / 6, value l % 6); values: 0 sum g, 1 sum g dy, 2 sum g dy^2,
-    // 3..5 sum w dL/dpix[c].  Accumulator slots (consumed by preprocess_bwd_kernel): 0 g dx, 1 g dy, 2 g dx^2,
-    // 3 g dx dy, 4 g dy^2, 5 g, 6..8 colour.
+    // G > 0: the warp's stash = G visits x 8 rows of 32 lane values (+ pad): rows 0..5 the partial sums
+    // (0 sum g, 1 sum g dy, 2 sum g dy^2, 3..5 sum w dL/dpix[c]), row 6 the lanes' dx, row 7 the Gaussian id (32
+    // copies: unconditional full-warp stores need neither a predicate nor an address of their own).
+    // At a flush lane l reduces row (visit l / 6, value l % 6).  Accumulator slots (consumed by
+    // preprocess_bwd_kernel): 0 g dx, 1 g dy, 2 g dx^2, 3 g dx dy, 4 g dy^2, 5 g, 6..8 colour.
     const uint32_t stash_base = (uint32_t)__cvta_generic_to_shared(s_stash) + warp * STASH_WARP_BYTES;
-    const uint32_t meta_base = stash_base + G * 6 * SGS_B_PAIR_STRIDE;
     const int fl_v = lane / 6, fl_k = lane - 6 * fl_v;
     const int fl_slot = fl_k == 0 ? 5 : (fl_k == 1 ? 1 : (fl_k == 2 ? 4 : fl_k + 3));
-    const float pxb = (float)(tx0 + (warp & 1) * SGS_Q);   // x of the quadrant's first pixel column
     uint32_t stash_wr = stash_base + lane * 4u;
     int nst = 0;                                            // visits in the stash (warp-uniform)
     auto flush = [&](int nv) {
         __syncwarp();
         if (lane < nv * 6) {
-            const uint32_t row = stash_base + lane * SGS_B_PAIR_STRIDE;
+            const uint32_t vis = stash_base + fl_v * (8 * SGS_B_PAIR_STRIDE);
+            const uint32_t row = vis + fl_k * SGS_B_PAIR_STRIDE;
             // partial i came from lane i = 8 r + c (r: pixel-row pair, c: pixel column): add the four r
             const float4 q0 = lds128_off<0>(row), q1 = lds128_off<16>(row), q2 = lds128_off<32>(row),
                          q3 = lds128_off<48>(row), q4 = lds128_off<64>(row), q5 = lds128_off<80>(row),
                          q6 = lds128_off<96>(row), q7 = lds128_off<112>(row);
+            // dx of the 8 pixel columns (as the visit computed them) and the Gaussian id
+            const float4 dA = lds128_off<6 * SGS_B_PAIR_STRIDE>(vis), dB = lds128_off<6 * SGS_B_PAIR_STRIDE + 16>(vis);
+            const uint32_t gid = lds32(vis + 7 * SGS_B_PAIR_STRIDE);
             const float2 c01 = add2(add2(lo2(q0), lo2(q2)), add2(lo2(q4), lo2(q6)));
             const float2 c23 = add2(add2(hi2(q0), hi2(q2)), add2(hi2(q4), hi2(q6)));
             const float2 c45 = add2(add2(lo2(q1), lo2(q3)), add2(lo2(q5), lo2(q7)));
             const float2 c67 = add2(add2(hi2(q1), hi2(q3)), add2(hi2(q5), hi2(q7)));
-            float gx;
-            uint32_t gid;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(gx), "=r"(gid) : "r"(meta_base + fl_v * 8u));
-            // dx of column c exactly as the visit computed it: x - (float)px
-            const float2 gx2 = make_float2(gx, gx);
-            const float2 d01 = add2(gx2, make_float2(-pxb, -(pxb + 1.f)));
-            const float2 d23 = add2(gx2, make_float2(-(pxb + 2.f), -(pxb + 3.f)));
-            const float2 d45 = add2(gx2, make_float2(-(pxb + 4.f), -(pxb + 5.f)));
-            const float2 d67 = add2(gx2, make_float2(-(pxb + 6.f), -(pxb + 7.f)));
+            const float2 d01 = lo2(dA), d23 = hi2(dA), d45 = lo2(dB), d67 = hi2(dB);
             const float2 t01 = __fmul2_rn(c01, d01), t23 = __fmul2_rn(c23, d23), t45 = __fmul2_rn(c45, d45),
                          t67 = __fmul2_rn(c67, d67);
             const float2 s0 = add2(add2(c01, c23), add2(c45, c67));
@@ -335,10 +329,9 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                     sts32_off<3 * SGS_B_PAIR_STRIDE>(stash_wr, v6);
                     sts32_off<4 * SGS_B_PAIR_STRIDE>(stash_wr, v7);
                     sts32_off<5 * SGS_B_PAIR_STRIDE>(stash_wr, v8);
-                    if (lane == 0)
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(meta_base + nst * 8u), "f"(ra.x),
-                                     "r"(__float_as_uint(c.w)) : "memory");
-                    stash_wr += 6 * SGS_B_PAIR_STRIDE;
+                    sts32_off<6 * SGS_B_PAIR_STRIDE>(stash_wr, dx);
+                    sts32_off<7 * SGS_B_PAIR_STRIDE>(stash_wr, c.w);
+                    stash_wr += 8 * SGS_B_PAIR_STRIDE;
                     if (++nst == G) {
                         flush(G);
                         nst = 0;
@@ -390,8 +383,10 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
 void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, const float* dL_dpix, float* acc,
                        cudaStream_t s) {
     dim3 grid(vp.tiles_x, vp.tiles_y, 1);
-    // developer switch for A/B measurements (tools/bwd_variants.py): SGS_BWD_VARIANT = 0 butterfly reduction,
-    // 1 stash reduction (default), 2 stash reduction with 64-record batches capped at 64 registers (8 CTAs per SM), 3 the same without the cap
+    // developer switch for A/B measurements (tools/gpu_ab_bwd.sh): SGS_BWD_VARIANT = 0 round-1 butterfly reduction
+    // (369 us at configs[1]); stash reduction: 1 (default) 32-record batches, 5 visits per flush, 8 CTAs per SM
+    // (326 us); 2 64-record batches (334 us); 3 64-record batches, 4 visits per flush (330 us); 4 128-record batches,
+    // 5 CTAs per SM (352 us)
     static const int variant = [] {
         const char* e = getenv("SGS_BWD_VARIANT");
         return e ? atoi(e) : 1;
@@ -400,9 +395,10 @@ void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, con
     render_bwd_kernel<BATCH, G, MINB><<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, \
                                                                      img.final_T, img.n_contrib, dL_dpix, acc)
     if (variant == 0) SGS_LAUNCH_RB(128, 0, 10);
-    else if (variant == 2) SGS_LAUNCH_RB(64, 5, 8);
-    else if (variant == 3) SGS_LAUNCH_RB(64, 5, 7);
-    else SGS_LAUNCH_RB(128, 5, 6);
+    else if (variant == 2) SGS_LAUNCH_RB(64, 5, 7);
+    else if (variant == 3) SGS_LAUNCH_RB(64, 4, 8);
+    else if (variant == 4) SGS_LAUNCH_RB(128, 5, 6);
+    else SGS_LAUNCH_RB(32, 5, 8);
 #undef SGS_LAUNCH_RB
 }
 

@@ -92,6 +92,44 @@ def test_on_rasterizer_outputs():
     assert torch.allclose(g.xyz_gradient_accum.reshape(-1), want_acc, rtol=1e-5, atol=0)
 
 
+def test_fused_sink_in_rasterizer_backward_equals_add_view():
+    """stats.attach_next_backward(): the rasterizer's backward applies the view's update in the epilogue of its last
+    kernel (sgs_densify_attach) — bit-identical running buffers to the stand-alone add_view kernel, one-shot."""
+    import saro_gs_b200 as sgs
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=30_000, width=320, height=240, fx=250.0)
+    P = scene.means3D.shape[0]
+    params = {k: getattr(scene, k).to(DEV).requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    fused, plain = BatchDensifyStats(P, DEV), BatchDensifyStats(P, DEV)
+    for view in range(3):
+        c = cam if view == 0 else synthetic.yaw_camera(cam.width, cam.height, 250.0, 0.2 * view)
+        rs = sgs.GaussianRasterizationSettings(c.height, c.width, c.tanfovx, c.tanfovy, torch.zeros(3, device=DEV), 1.0,
+                                               c.viewmatrix.to(DEV), c.projmatrix.to(DEV), 3, c.campos.to(DEV), False)
+        m2d = torch.zeros(P, 3, device=DEV, requires_grad=True)
+        color, radii, _ = sgs.GaussianRasterizer(rs)(means3D=params["means3D"], means2D=m2d, opacities=params["opacities"],
+                                                     shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        if view < 2:
+            fused.attach_next_backward()
+        color.square().mean().backward()
+        if view < 2:
+            plain.add_view(m2d.grad, radii)
+    torch.cuda.synchronize()
+    assert fused.views == 2                                   # the third backward found no armed sink (one-shot)
+    assert (plain.vis_count > 0).any() and (plain.vis_count == 0).any()
+    assert torch.equal(fused.vis_count, plain.vis_count)
+    assert torch.equal(fused.radii_max, plain.radii_max)
+    assert torch.equal(fused.grad_sum, plain.grad_sum)
+    # a sink armed for another cloud size is refused and disarmed
+    other = BatchDensifyStats(P + 1, DEV)
+    m2d = torch.zeros(P, 3, device=DEV, requires_grad=True)
+    color, radii, _ = sgs.GaussianRasterizer(rs)(means3D=params["means3D"], means2D=m2d, opacities=params["opacities"],
+                                                 shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+    other.attach_next_backward()
+    with pytest.raises(RuntimeError):
+        color.square().mean().backward()
+    assert other.views == 0
+
+
 def test_rejects_bad_inputs():
     stats = BatchDensifyStats(10, DEV)
     with pytest.raises(RuntimeError):

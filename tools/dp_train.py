@@ -95,8 +95,8 @@ def main():
         for k in mine:
             color, radii, m2d = render(k)
             loss = loss_utils.l1_dssim_loss(color, targets[k], 0.2)
+            stats.attach_next_backward()                      # the view's statistics ride in the backward's last kernel
             loss.backward()                                   # gradients of the local views accumulate in .grad
-            stats.add_view(m2d.grad, radii)
         e[1].record()
         flats = []
         for b in buckets:
