@@ -30,6 +30,7 @@
 // matrix, grid-wide barrier, every block scatters.  All counts are read on the device: the host never waits between
 // the stages (see sgs_api.cu).  Round 1 used CUB here: 10 launches and 34-CTA decoupled look-back chains, 205 us.
 #include "sgs_common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace sgs {
@@ -272,6 +273,8 @@ __device__ __forceinline__ uint4 super_rect(const ushort4 r) {
 // ------------------------------------------------------------------------------------------------
 struct DepthArgs {
     int P;
+    int sort;         // 1: depth-sort the Gaussians first (round-2a design); 0: index order, the depth sort happens inside
+                      //    every supertile (tile_fill_sorted_kernel)
     int vblocks;      // virtual blocks (slices); multiple of gridDim.x; == gridDim.x  <=>  slices stay resident
     int slice;        // keys per slice
     const uint32_t* raw;
@@ -370,17 +373,21 @@ __device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& 
         key_max = __reduce_max_sync(0xFFFFFFFFu, sm.base[lane]);
         key_nmin = __reduce_max_sync(0xFFFFFFFFu, sm.cnt[lane]);
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) {   // the frame's key range, for the per-supertile depth sort
+            a.ctl->key_max = key_max;
+            a.ctl->key_nmin = key_nmin;
+        }
         prof_mark(a.prof, pslot);
     }
     const uint32_t key_min = ~key_nmin;
     // normalised key: visible -> raw - min in [0, span) ; culled -> span (sorted behind everything, stable)
     const uint32_t span = (key_nmin != 0u && key_max >= key_min) ? key_max - key_min + 1u : 0u;
     const uint32_t nbits = span ? 32u - (uint32_t)__clz(span) : 0u;
-    const uint32_t npass = (nbits + 8u) / 9u;
+    const uint32_t npass = a.sort ? (nbits + 8u) / 9u : 0u;
     const uint32_t dbits = npass ? (nbits + npass - 1u) / npass : 0u;
     const uint32_t nd = 1u << dbits;
 
-    if (npass == 0u) {   // nothing visible: identity order
+    if (npass == 0u && a.sort) {   // nothing visible: identity order
         for (uint32_t v = blockIdx.x; v < VB; v += gridDim.x) {
             const uint32_t lo = v * SL, hi = min(P, lo + SL);
             for (uint32_t i = lo + tid; i < hi; i += SGS_SORT_THREADS) a.vals[0][i] = i;
@@ -438,25 +445,27 @@ __device__ __forceinline__ void depth_sort_phases(const DepthArgs& a, SortSmem& 
         prof_mark(a.prof, pslot);
     }
 
-    // ---- scan, in depth order, of the supertile counts (+ the kept rects in depth order for the next stage)
+    // ---- scan, in depth order (sort = 0: in index order), of the supertile counts (+ the kept rects in depth order
+    // for the next stage)
     const uint32_t* order = a.vals[0];
+    const bool sorted = a.sort != 0;
     // one slice: supertile count of every item -> sm.key, its rect -> rect_sorted; two items per thread in flight
     auto gather = [&](uint32_t lo, uint32_t n) -> uint32_t {
         uint32_t sum = 0;
         for (uint32_t i = tid; i < n; i += 2 * SGS_SORT_THREADS) {
             const uint32_t i1 = i + SGS_SORT_THREADS;
-            const uint32_t g0 = __ldcg(order + lo + i);
-            const uint32_t g1 = i1 < n ? __ldcg(order + lo + i1) : g0;
+            const uint32_t g0 = sorted ? __ldcg(order + lo + i) : lo + i;
+            const uint32_t g1 = i1 < n ? (sorted ? __ldcg(order + lo + i1) : lo + i1) : g0;
             const ushort4 r0 = a.rect_kept[g0];
             const ushort4 r1 = a.rect_kept[g1];
             const uint4 s0 = super_rect(r0), s1 = super_rect(r1);
             const uint32_t c0 = (s0.y - s0.x) * (s0.w - s0.z), c1 = (s1.y - s1.x) * (s1.w - s1.z);
             sm.key[i] = c0;
-            a.rect_sorted[lo + i] = r0;
+            if (sorted) a.rect_sorted[lo + i] = r0;
             sum += c0;
             if (i1 < n) {
                 sm.key[i1] = c1;
-                a.rect_sorted[lo + i1] = r1;
+                if (sorted) a.rect_sorted[lo + i1] = r1;
                 sum += c1;
             }
         }
@@ -523,9 +532,9 @@ struct CoarseArgs {
     int super_bits;
     int keep;
     unsigned long long cap;
-    const uint32_t* order;      // Gaussians in depth order
-    const uint32_t* coffs;      // inclusive scan of the supertile counts, in depth order
-    const ushort4* rect_sorted; // kept rects in depth order
+    const uint32_t* order;      // Gaussians in depth order, or NULL: index order (the supertiles sort themselves)
+    const uint32_t* coffs;      // inclusive scan of the supertile counts, in that order
+    const ushort4* rect_sorted; // kept rects in that order
     uint32_t* keys[2];          // key = supertile id | (mask of the supertile's 16 tiles the rect covers) << 16
     uint32_t* vals[2];
     unsigned long long* pairs;  // final list: Gaussian index | key << 32, supertile-major, depth order inside
@@ -563,7 +572,7 @@ __device__ __forceinline__ void generate_slice(SortSmem& sm, const CoarseArgs& a
         bool beyond = true;    // this Gaussian's instances end at or after e (nothing more to do past it)
         if (k < P) {
             const uint32_t incl = __ldcg(a.coffs + k);
-            gid = __ldcg(a.order + k);
+            gid = a.order ? __ldcg(a.order + k) : k;
             rk = __ldcg(reinterpret_cast<const unsigned long long*>(a.rect_sorted) + k);
             sr = super_rect(as_rect(rk));
             n = (sr.y - sr.x) * (sr.w - sr.z);
@@ -739,6 +748,12 @@ struct ExpandArgs {
     uint2* ranges;          // [n_tiles]: the count kernel writes .y = count, its last block turns that into [start, end)
     uint32_t* point_list;
     uint32_t* done;         // last-block ticket (zero before and after the kernel)
+    // tile_fill_sorted_kernel only
+    const uint32_t* depth_raw;   // [P] float bits of the view-space depth
+    const BinCtl* ctl;           // key range of the frame, kept count
+    unsigned long long cap;
+    uint32_t* scratch_key[2];    // [cap] per-bucket scratch (the coarse sort's ping-pong buffers, free by now): only
+    uint32_t* scratch_val[2];    //       buckets longer than SGS_FS_CAP use them
 };
 
 __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const ExpandArgs a) {
@@ -850,6 +865,241 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const Expand
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3b': depth sort INSIDE the supertile + expansion (round 2b).  The coarse list arrives in Gaussian-index
+// order inside every supertile bucket (stage A no longer sorts the P Gaussians: three radix passes with six grid-wide
+// barriers, 58 us at configs[1]); one block per supertile sorts its bucket — a few thousand entries — by the depth
+// bits in shared memory with the same stable LSD passes (9-bit digits over the frame's key range), no grid barrier,
+// and then expands it into the 16 tile lists exactly like tile_fill_kernel.  Stable passes over an index-ordered
+// bucket give the order (depth bits, Gaussian index): the reference's order restricted to the supertile.
+// Buckets longer than SGS_FS_CAP run the same passes chunk by chunk through global scratch (slow but exact).
+// ------------------------------------------------------------------------------------------------
+#define SGS_FS_CAP 4096
+#define SGS_FS_IPT (SGS_FS_CAP / SGS_EXP_THREADS)
+struct FillSmem {
+    uint16_t whist[SGS_EXP_THREADS / 32][SGS_SORT_ND];   // per-warp digit counts -> exclusive prefix over the warps
+    uint32_t cnt[SGS_SORT_ND];                            // exclusive scan of the digit totals (bucket starts)
+    uint32_t key[2][SGS_FS_CAP];
+    uint16_t idx[2][SGS_FS_CAP];                          // position in the index-ordered bucket; the side being
+                                                          // written doubles as the rank array of the pass
+    uint32_t wsum[SGS_EXP_THREADS / 32];
+    uint32_t wc[16][SGS_EXP_THREADS / 32];
+    uint32_t run[16];
+};
+
+// Stable ranks of key[0..n) on digit (key >> shift) & (nd - 1): rank[i] = position among the keys of the same digit
+// within the owning warp's contiguous range; whist[w][d] = keys of digit d in the warps before w.  Returns, in the
+// thread d < nd, the total of digit d.
+__device__ __forceinline__ uint32_t fs_rank(FillSmem& sm, const uint32_t* key, uint16_t* rank, uint32_t n, uint32_t shift,
+                                            uint32_t dbits, uint32_t per) {
+    constexpr uint32_t NW = SGS_EXP_THREADS / 32;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nd = 1u << dbits;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(&sm.whist[0][0]);
+        for (uint32_t i = tid; i < NW * SGS_SORT_ND / 2; i += SGS_EXP_THREADS) z[i] = 0u;
+    }
+    __syncthreads();
+    const uint32_t beg = warp * per, end = min(n, beg + per);
+    uint16_t* wh = sm.whist[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t i0 = beg; i0 < end; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < end;
+        const uint32_t d = valid ? ((key[i] >> shift) & (nd - 1u)) : 0u;
+        uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+        for (uint32_t b = 0; b < 9; b++) {
+            if (b < dbits) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? m : ~m;
+            }
+        }
+        const uint32_t before = peers & lt_mask;
+        uint32_t old = 0;
+        if (valid) old = wh[d];
+        __syncwarp();
+        if (valid && before == 0u) wh[d] = (uint16_t)(old + __popc(peers));
+        __syncwarp();
+        if (valid) rank[i] = (uint16_t)(old + __popc(before));
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    if (tid < nd) {
+#pragma unroll 4
+        for (uint32_t w = 0; w < NW; w++) {
+            const uint32_t c = sm.whist[w][tid];
+            sm.whist[w][tid] = (uint16_t)total;
+            total += c;
+        }
+    }
+    return total;
+}
+
+// block-wide exclusive scan over the digits: thread d < nd holds `v`, sm.cnt[d] receives the sum of the smaller digits
+__device__ __forceinline__ void fs_digit_scan(FillSmem& sm, uint32_t v, uint32_t nd) {
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    if (lane == 31) sm.wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < warp; w++) woff += sm.wsum[w];
+    if (tid < nd) sm.cnt[tid] = woff + inc - v;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const ExpandArgs a) {
+    constexpr uint32_t NW = SGS_EXP_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char fs_raw[];
+    FillSmem& sm = *reinterpret_cast<FillSmem*>(fs_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s = blockIdx.x;
+    const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    const uint2 cr = a.cranges[s];
+    if (cr.y == cr.x) return;
+    if (__ldcg(&a.ctl->kept) > a.cap) return;      // over capacity: the host re-launches
+    const uint32_t n = cr.y - cr.x;
+    const unsigned long long* bucket = a.pairs + cr.x;
+
+    // the frame's key range -> passes (every block derives the same numbers)
+    const uint32_t key_max = __ldcg(&a.ctl->key_max), key_nmin = __ldcg(&a.ctl->key_nmin);
+    const uint32_t key_min = ~key_nmin;
+    const uint32_t span = (key_nmin != 0u && key_max >= key_min) ? key_max - key_min + 1u : 0u;
+    const uint32_t nbits = span > 1u ? 32u - (uint32_t)__clz(span - 1u) : 0u;   // keys are in [0, span)
+    const uint32_t npass = (nbits + 8u) / 9u;
+    const uint32_t dbits = npass ? (nbits + npass - 1u) / npass : 0u;
+    const uint32_t nd = 1u << dbits;
+
+    if (tid < 16) {
+        const uint32_t tx = tx0 + (tid & 3u), ty = ty0 + (tid >> 2);
+        sm.run[tid] = (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) ? a.ranges[ty * a.tiles_x + tx].x : 0u;
+    }
+
+    uint32_t cur = 0;                    // side of key / idx holding the current order (resident path)
+    const uint32_t* gorder = nullptr;    // long buckets: the order lives in global scratch
+    if (n <= SGS_FS_CAP) {
+        for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) {
+            const uint32_t gid = (uint32_t)__ldcg(bucket + i);
+            sm.key[0][i] = __ldcg(a.depth_raw + gid) - key_min;
+            sm.idx[0][i] = (uint16_t)i;
+        }
+        __syncthreads();
+        const uint32_t per = (((n + NW - 1) / NW) + 31u) & ~31u;
+        for (uint32_t p = 0; p < npass; p++) {
+            const uint32_t shift = p * dbits;
+            uint16_t* rank = sm.idx[cur ^ 1u];
+            const uint32_t total = fs_rank(sm, sm.key[cur], rank, n, shift, dbits, per);
+            fs_digit_scan(sm, total, nd);
+            // two-phase scatter: the rank array aliases the destination index array
+            uint32_t k[SGS_FS_IPT], dst[SGS_FS_IPT];
+            uint16_t v[SGS_FS_IPT];
+#pragma unroll
+            for (int u = 0; u < SGS_FS_IPT; u++) {
+                const uint32_t i = tid + u * SGS_EXP_THREADS;
+                if (i < n) {
+                    k[u] = sm.key[cur][i];
+                    v[u] = sm.idx[cur][i];
+                    const uint32_t d = (k[u] >> shift) & (nd - 1u);
+                    dst[u] = sm.cnt[d] + sm.whist[i / per][d] + rank[i];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < SGS_FS_IPT; u++) {
+                const uint32_t i = tid + u * SGS_EXP_THREADS;
+                if (i < n) {
+                    sm.key[cur ^ 1u][dst[u]] = k[u];
+                    sm.idx[cur ^ 1u][dst[u]] = v[u];
+                }
+            }
+            __syncthreads();
+            cur ^= 1u;
+        }
+    } else {
+        uint32_t* K[2] = {a.scratch_key[0] + cr.x, a.scratch_key[1] + cr.x};
+        uint32_t* V[2] = {a.scratch_val[0] + cr.x, a.scratch_val[1] + cr.x};
+        for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) {
+            const uint32_t gid = (uint32_t)__ldcg(bucket + i);
+            K[0][i] = __ldcg(a.depth_raw + gid) - key_min;
+            V[0][i] = i;
+        }
+        __syncthreads();
+        uint32_t side = 0;
+        for (uint32_t p = 0; p < npass; p++) {
+            const uint32_t shift = p * dbits;
+            // digit totals of the whole bucket -> bucket starts
+            for (uint32_t d = tid; d < SGS_SORT_ND; d += SGS_EXP_THREADS) sm.cnt[d] = 0u;
+            __syncthreads();
+            for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) atomicAdd(&sm.cnt[(K[side][i] >> shift) & (nd - 1u)], 1u);
+            __syncthreads();
+            const uint32_t tot_all = tid < nd ? sm.cnt[tid] : 0u;
+            __syncthreads();
+            fs_digit_scan(sm, tot_all, nd);
+            for (uint32_t c0 = 0; c0 < n; c0 += SGS_FS_CAP) {
+                const uint32_t m = min((uint32_t)SGS_FS_CAP, n - c0);
+                for (uint32_t i = tid; i < m; i += SGS_EXP_THREADS) sm.key[0][i] = K[side][c0 + i];
+                __syncthreads();
+                const uint32_t per = (((m + NW - 1) / NW) + 31u) & ~31u;
+                const uint32_t total = fs_rank(sm, sm.key[0], sm.idx[0], m, shift, dbits, per);
+                __syncthreads();
+                for (uint32_t i = tid; i < m; i += SGS_EXP_THREADS) {
+                    const uint32_t kk = sm.key[0][i];
+                    const uint32_t d = (kk >> shift) & (nd - 1u);
+                    const uint32_t dst = sm.cnt[d] + sm.whist[i / per][d] + sm.idx[0][i];
+                    K[side ^ 1u][dst] = kk;
+                    V[side ^ 1u][dst] = V[side][c0 + i];
+                }
+                __syncthreads();
+                if (tid < nd) sm.cnt[tid] += total;     // the next chunk continues behind this one
+                __syncthreads();
+            }
+            side ^= 1u;
+        }
+        gorder = V[side];
+    }
+
+    // ---- expansion of the depth-ordered bucket into the 16 tile lists (as tile_fill_kernel)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t i0 = 0; i0 < n; i0 += SGS_EXP_THREADS) {
+        const uint32_t i = i0 + tid;
+        unsigned long long pr = 0ull;
+        if (i < n) pr = __ldcg(bucket + (gorder ? gorder[i] : (uint32_t)sm.idx[cur][i]));
+        const uint32_t gid = (uint32_t)pr;
+        const uint32_t m = (uint32_t)(pr >> 48);
+        uint32_t before[16];
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (m >> t) & 1u);
+            before[t] = __popc(bal & lt_mask);
+            if (lane == t) sm.wc[t][warp] = __popc(bal);
+        }
+        __syncthreads();   // also: run[] of the previous chunk is final
+        uint32_t myoff = 0, total = 0;
+        if (lane < 16) {
+#pragma unroll
+            for (uint32_t w = 0; w < NW; w++) {
+                const uint32_t c = sm.wc[lane][w];
+                if (w < warp) myoff += c;
+                total += c;
+            }
+            myoff += sm.run[lane];
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) {
+            const uint32_t off = __shfl_sync(0xFFFFFFFFu, myoff, t);
+            if ((m >> t) & 1u) a.point_list[off + before[t]] = gid;
+        }
+        __syncthreads();   // every warp has read wc / run of this chunk
+        if (warp == 0 && lane < 16) sm.run[lane] += total;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -893,6 +1143,7 @@ int binning_grid_blocks() {
         cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(coarse_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(binning_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        cudaFuncSetAttribute(tile_fill_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
         cached = sms;
         cached_dev = dev;
     }
@@ -910,9 +1161,20 @@ static int vblocks_for(size_t n) {
 int binning_depth_vblocks(int P) { return vblocks_for((size_t)P); }
 size_t binning_hist_words(size_t n) { return ((size_t)vblocks_for(n) + 1) * SGS_SORT_ND; }
 
+// 1 (default): the supertiles sort themselves (tile_fill_sorted_kernel); 0: depth-sort the Gaussians first.
+// Developer switch for A/B measurements: SGS_BIN_MODE.
+static int binning_mode() {
+    static const int mode = [] {
+        const char* e = getenv("SGS_BIN_MODE");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+
 static DepthArgs make_depth_args(int P, const GeomState& g, HostSlot* slot, unsigned long long ticket) {
     DepthArgs a;
     a.P = P;
+    a.sort = binning_mode() == 0 ? 1 : 0;
     a.vblocks = g.depth_vblocks;
     a.slice = (P + a.vblocks - 1) / a.vblocks;
     a.raw = g.depth_raw;
@@ -944,9 +1206,9 @@ static CoarseArgs make_coarse_args(int P, const ViewParams& vp, const GeomState&
     a.super_bits = bits_for(a.n_super);
     a.keep = keep;
     a.cap = (unsigned long long)b.cap;
-    a.order = g.depth_vals[0];
+    a.order = binning_mode() == 0 ? g.depth_vals[0] : nullptr;
     a.coffs = g.coffs;
-    a.rect_sorted = g.rect_sorted;
+    a.rect_sorted = binning_mode() == 0 ? g.rect_sorted : g.rect_kept;
     a.pairs = b.coarse_pairs;
     a.keys[0] = b.coarse_keys[0];
     a.keys[1] = b.coarse_keys[1];
@@ -976,8 +1238,16 @@ static cudaError_t launch_expand(const CoarseArgs& a, const ViewParams& vp, cons
     x.ranges = img.ranges;
     x.point_list = b.point_list;
     x.done = &g.ctl->expand_done;
+    x.depth_raw = g.depth_raw;
+    x.ctl = g.ctl;
+    x.cap = a.cap;
+    x.scratch_key[0] = b.coarse_keys[0];
+    x.scratch_key[1] = b.coarse_keys[1];
+    x.scratch_val[0] = b.coarse_vals[0];
+    x.scratch_val[1] = b.coarse_vals[1];
     tile_count_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
-    tile_fill_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
+    if (binning_mode() == 0) tile_fill_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
+    else tile_fill_sorted_kernel<<<a.n_super, SGS_EXP_THREADS, sizeof(FillSmem), s>>>(x);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,15 @@ def test_multi_slice_tile_sort(sgs, dev):
     assert R > 6_000_000
 
 
+def test_long_supertile_buckets(sgs, dev):
+    """200 k Gaussians on a 320 x 240 image: 20 supertiles whose buckets (tens of thousands of entries) exceed what a
+    block sorts in shared memory — the chunked path of tile_fill_sorted_kernel through global scratch."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=200_000, seed=9, width=320, height=240, fx=180.0, log_scale_mean=-3.8)
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R > 200_000
+
+
 def test_three_pass_tile_sort(sgs, dev):
     """> 65 536 tiles (17 tile bits = 3 radix passes): 4800 x 3600 image."""
     from saro_gs_b200 import synthetic
