@@ -128,6 +128,9 @@ int sgs_last_forward_counts(int64_t* out5);
  * sgs_forward calls, e.g. 0 to exercise the "prediction too small -> re-launch with the exact size" path;
  * a negative value restores the predictor. */
 void sgs_debug_set_capacity(int64_t instances);
+/* Tests / measurements: where the depth sort of the binning stage happens — 1 inside every supertile, 0 one global sort
+ * of the Gaussians first, -1 (default) chosen per call from the previous frame's counts.  Both are exact. */
+void sgs_debug_set_binning_mode(int mode);
 
 /* Developer aid: phase timestamps (%globaltimer, ns) of the two persistent binning kernels, written by block 0 into
  * pinned memory while enabled.  Slots 0.. : depth-sort kernel, 64.. : tile-sort kernel.  out128 (host, 128 entries,

@@ -37,6 +37,7 @@ ABI = {
     "sgs_debug_export": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp] + [_vp] * 10 + [_vp]),
     "sgs_debug_kept": (_i64, [_vp, _vp]),
     "sgs_debug_set_capacity": (None, [_i64]),
+    "sgs_debug_set_binning_mode": (None, [_i]),
     "sgs_last_forward_counts": (_i, [_vp]),
     "sgs_debug_binning_profile": (_i, [_i, _vp]),
     "sgs_loss_workspace_floats": (ctypes.c_size_t, [_i, _i, _i, _i]),

@@ -204,6 +204,25 @@ CapPredictor& cap_predictor() {
     return p;
 }
 std::atomic<long long> g_forced_cap{-1};   // sgs_debug_set_capacity: tests force the over-capacity path
+std::atomic<int> g_forced_bin_mode{-1};    // sgs_debug_set_binning_mode: -1 automatic, 0 global depth sort, 1 per supertile
+
+// Depth sort inside the supertiles (mode 1) while the expected bucket — (supertile, Gaussian) pairs per supertile,
+// about two supertiles per visible Gaussian — stays well inside what a block sorts in shared memory; the global sort
+// (mode 0) for denser frames.  Estimated from the previous call of this thread; a wrong guess only costs time.
+int choose_binning_mode(int P, size_t supers) {
+    const int forced = g_forced_bin_mode.load();
+    if (forced >= 0) return forced ? 1 : 0;
+    static const int env = [] {
+        const char* e = getenv("SGS_BIN_MODE");
+        return e ? atoi(e) : -1;
+    }();
+    if (env >= 0) return env ? 1 : 0;
+    const CapPredictor& pr = cap_predictor();
+    const unsigned long long vis = pr.last_P > 0 ? (unsigned long long)((double)pr.visible * (P > pr.last_P ? (double)P / pr.last_P : 1.0))
+                                                 : (unsigned long long)P;
+    const unsigned long long est = 2ull * vis / (supers ? supers : 1);
+    return est * 4ull > 3ull * (unsigned long long)sgs::binning_bucket_capacity() ? 0 : 1;
+}
 size_t predict_capacity(int P) {
     const long long forced = g_forced_cap.load();
     size_t cap;
@@ -344,6 +363,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     const int cull = (flags & SGS_FLAG_NO_TILE_CULL) ? 0 : 1;
     const bool keep = (flags & SGS_FLAG_KEEP_FOR_BACKWARD) != 0;
     if (sgs::binning_grid_blocks() <= 0) return fail(SGS_ERR_CUDA, "sgs_forward: no CUDA device");
+    sgs::binning_set_mode(choose_binning_mode(P, supers));
 
     // Binning buffer sized from a PREDICTION (see predict_capacity): every kernel of the pass is queued before the
     // host learns the true instance count, so the GPU never idles while the host waits for it.
@@ -568,6 +588,8 @@ int sgs_last_forward_counts(int64_t* out5) {
     out5[4] = (int64_t)pr.relaunched;
     return 0;
 }
+
+void sgs_debug_set_binning_mode(int mode) { g_forced_bin_mode.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
 
 void sgs_debug_set_capacity(int64_t instances) { g_forced_cap.store(instances < 0 ? -1 : (long long)instances); }
 

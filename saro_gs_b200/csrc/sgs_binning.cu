@@ -30,6 +30,7 @@
 // matrix, grid-wide barrier, every block scatters.  All counts are read on the device: the host never waits between
 // the stages (see sgs_api.cu).  Round 1 used CUB here: 10 launches and 34-CTA decoupled look-back chains, 205 us.
 #include "sgs_common.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -748,14 +749,23 @@ struct ExpandArgs {
     uint2* ranges;          // [n_tiles]: the count kernel writes .y = count, its last block turns that into [start, end)
     uint32_t* point_list;
     uint32_t* done;         // last-block ticket (zero before and after the kernel)
+    uint32_t* counts;       // [n_tiles] per-tile instance counts (tile_count_kernel<false>; the forward render kernel
+                            // later overwrites the array with its packed-record counts)
+    int local_scan;         // tile_fill_sorted_kernel derives its tiles' list starts from `counts` itself
     // tile_fill_sorted_kernel only
     const uint32_t* depth_raw;   // [P] float bits of the view-space depth
     const BinCtl* ctl;           // key range of the frame, kept count
     unsigned long long cap;
     uint32_t* scratch_key[2];    // [cap] per-bucket scratch (the coarse sort's ping-pong buffers, free by now): only
     uint32_t* scratch_val[2];    //       buckets longer than SGS_FS_CAP use them
+    unsigned long long* prof;    // developer aid (sgs_debug_binning_profile): phase timestamps of blocks 0 and 200
 };
 
+// SCAN = true: counts go to ranges[t].y and the last block to finish turns them into [start, end) (any grid size).
+// SCAN = false (grids of at most SGS_LOCALSCAN_TILES tiles): counts go to `counts` and every block of
+// tile_fill_sorted_kernel derives the starts of its own 16 tiles from them — no serial tail behind a last block
+// (14 of the kernel's 18 us at configs[1]).
+template <bool SCAN>
 __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const ExpandArgs a) {
     __shared__ uint32_t s_cnt[16];
     __shared__ uint32_t s_last;
@@ -763,6 +773,7 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const Expan
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t s = blockIdx.x;
     const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    pdl_wait();
     const uint2 cr = a.cranges[s];
     if (tid < 16) s_cnt[tid] = 0;
     __syncthreads();
@@ -783,8 +794,12 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_count_kernel(const Expan
     __syncthreads();
     if (tid < 16) {
         const uint32_t tx = tx0 + (tid & 3u), ty = ty0 + (tid >> 2);
-        if (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) a.ranges[ty * a.tiles_x + tx].y = s_cnt[tid];
+        if (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) {
+            if (SCAN) a.ranges[ty * a.tiles_x + tx].y = s_cnt[tid];
+            else a.counts[ty * a.tiles_x + tx] = s_cnt[tid];
+        }
     }
+    if (!SCAN) return;
     // the last block to finish turns the counts into [start, end) ranges (exclusive scan over the tile ids)
     __threadfence();
     __syncthreads();
@@ -823,6 +838,7 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const Expand
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s = blockIdx.x;
     const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    pdl_wait();
     const uint2 cr = a.cranges[s];
     if (cr.y == cr.x) return;
     if (tid < 16) {
@@ -876,29 +892,31 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const Expand
 // Buckets longer than SGS_FS_CAP run the same passes chunk by chunk through global scratch (slow but exact).
 // ------------------------------------------------------------------------------------------------
 #define SGS_FS_CAP 4096
-#define SGS_FS_IPT (SGS_FS_CAP / SGS_EXP_THREADS)
+#define SGS_LOCALSCAN_TILES 8192   // up to here every fill block reads all tile counts itself (32 KB from L2)
+template <int NT>
 struct FillSmem {
-    uint16_t whist[SGS_EXP_THREADS / 32][SGS_SORT_ND];   // per-warp digit counts -> exclusive prefix over the warps
+    uint16_t whist[NT / 32][SGS_SORT_ND];   // per-warp digit counts -> exclusive prefix over the warps
     uint32_t cnt[SGS_SORT_ND];                            // exclusive scan of the digit totals (bucket starts)
     uint32_t key[2][SGS_FS_CAP];
     uint16_t idx[2][SGS_FS_CAP];                          // position in the index-ordered bucket; the side being
                                                           // written doubles as the rank array of the pass
-    uint32_t wsum[SGS_EXP_THREADS / 32];
-    uint32_t wc[16][SGS_EXP_THREADS / 32];
+    uint32_t wsum[NT / 32];
+    uint32_t wc[16][NT / 32];
     uint32_t run[16];
 };
 
 // Stable ranks of key[0..n) on digit (key >> shift) & (nd - 1): rank[i] = position among the keys of the same digit
 // within the owning warp's contiguous range; whist[w][d] = keys of digit d in the warps before w.  Returns, in the
 // thread d < nd, the total of digit d.
-__device__ __forceinline__ uint32_t fs_rank(FillSmem& sm, const uint32_t* key, uint16_t* rank, uint32_t n, uint32_t shift,
+template <int NT>
+__device__ __forceinline__ uint32_t fs_rank(FillSmem<NT>& sm, const uint32_t* key, uint16_t* rank, uint32_t n, uint32_t shift,
                                             uint32_t dbits, uint32_t per) {
-    constexpr uint32_t NW = SGS_EXP_THREADS / 32;
+    constexpr uint32_t NW = NT / 32;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nd = 1u << dbits;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&sm.whist[0][0]);
-        for (uint32_t i = tid; i < NW * SGS_SORT_ND / 2; i += SGS_EXP_THREADS) z[i] = 0u;
+        for (uint32_t i = tid; i < NW * SGS_SORT_ND / 2; i += NT) z[i] = 0u;
     }
     __syncthreads();
     const uint32_t beg = warp * per, end = min(n, beg + per);
@@ -908,14 +926,10 @@ __device__ __forceinline__ uint32_t fs_rank(FillSmem& sm, const uint32_t* key, u
         const uint32_t i = i0 + lane;
         const bool valid = i < end;
         const uint32_t d = valid ? ((key[i] >> shift) & (nd - 1u)) : 0u;
-        uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
-#pragma unroll
-        for (uint32_t b = 0; b < 9; b++) {
-            if (b < dbits) {
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
-                peers &= ((d >> b) & 1u) ? m : ~m;
-            }
-        }
+        // peers = lanes holding the same digit.  One match.any instead of the nine ballots of the persistent sort
+        // kernels: there a warp is alone on its scheduler and the instruction's latency (~200 cycles when the 32
+        // digits differ) is exposed; here 48 warps per SM hide it and the kernel is bound by instruction issue.
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu) & __ballot_sync(0xFFFFFFFFu, valid);
         const uint32_t before = peers & lt_mask;
         uint32_t old = 0;
         if (valid) old = wh[d];
@@ -938,7 +952,8 @@ __device__ __forceinline__ uint32_t fs_rank(FillSmem& sm, const uint32_t* key, u
 }
 
 // block-wide exclusive scan over the digits: thread d < nd holds `v`, sm.cnt[d] receives the sum of the smaller digits
-__device__ __forceinline__ void fs_digit_scan(FillSmem& sm, uint32_t v, uint32_t nd) {
+template <int NT>
+__device__ __forceinline__ void fs_digit_scan(FillSmem<NT>& sm, uint32_t v, uint32_t nd) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t inc = v;
 #pragma unroll
@@ -954,17 +969,30 @@ __device__ __forceinline__ void fs_digit_scan(FillSmem& sm, uint32_t v, uint32_t
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const ExpandArgs a) {
-    constexpr uint32_t NW = SGS_EXP_THREADS / 32;
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 3 : 4) tile_fill_sorted_kernel(const ExpandArgs a) {
+    constexpr int SGS_FS_IPT = SGS_FS_CAP / NT;
+    constexpr uint32_t NW = NT / 32;
     extern __shared__ __align__(16) unsigned char fs_raw[];
-    FillSmem& sm = *reinterpret_cast<FillSmem*>(fs_raw);
+    FillSmem<NT>& sm = *reinterpret_cast<FillSmem<NT>*>(fs_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s = blockIdx.x;
     const uint32_t tx0 = (s % a.super_x) * SGS_ST, ty0 = (s / a.super_x) * SGS_ST;
+    pdl_wait();
     const uint2 cr = a.cranges[s];
     if (cr.y == cr.x) return;
     if (__ldcg(&a.ctl->kept) > a.cap) return;      // over capacity: the host re-launches
     const uint32_t n = cr.y - cr.x;
+    int pslot = blockIdx.x == 0 ? 96 : 112;
+    auto mark = [&]() {
+        if (a.prof && (blockIdx.x == 0 || blockIdx.x == 200) && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.prof[pslot] = t;
+        }
+        pslot++;
+    };
+    mark();
     const unsigned long long* bucket = a.pairs + cr.x;
 
     // the frame's key range -> passes (every block derives the same numbers)
@@ -972,59 +1000,105 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const
     const uint32_t key_min = ~key_nmin;
     const uint32_t span = (key_nmin != 0u && key_max >= key_min) ? key_max - key_min + 1u : 0u;
     const uint32_t nbits = span > 1u ? 32u - (uint32_t)__clz(span - 1u) : 0u;   // keys are in [0, span)
-    const uint32_t npass = (nbits + 8u) / 9u;
+    constexpr uint32_t MAXB = NT >= 512 ? 9u : 8u;      // one thread per digit in the prefix phases
+    const uint32_t npass = (nbits + MAXB - 1u) / MAXB;
     const uint32_t dbits = npass ? (nbits + npass - 1u) / npass : 0u;
     const uint32_t nd = 1u << dbits;
 
-    if (tid < 16) {
+    if (a.local_scan) {
+        // list start of tile t = number of instances in the tiles before t (tile-id order, like the reference's sorted
+        // list): one pass over all counts accumulates, per tile row r of this supertile, the sum before the row's
+        // first tile here
+        const uint32_t nt = (uint32_t)a.n_tiles;
+        uint32_t rowfirst[SGS_ST], acc[SGS_ST];
+#pragma unroll
+        for (uint32_t r = 0; r < SGS_ST; r++) {
+            rowfirst[r] = (ty0 + r < (uint32_t)a.tiles_y) ? (ty0 + r) * (uint32_t)a.tiles_x + tx0 : nt;
+            acc[r] = 0u;
+        }
+        for (uint32_t t = tid; t < nt; t += NT) {
+            const uint32_t c = __ldcg(a.counts + t);
+#pragma unroll
+            for (uint32_t r = 0; r < SGS_ST; r++) acc[r] += (t < rowfirst[r]) ? c : 0u;
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < SGS_ST; r++) {
+            const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, acc[r]);
+            if (lane == 0) sm.wc[r][warp] = v;
+        }
+        __syncthreads();
+        if (tid < 16) {
+            const uint32_t r = tid >> 2, x = tid & 3u;
+            const uint32_t tx = tx0 + x, ty = ty0 + r;
+            uint32_t start = 0;
+            if (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) {
+                uint32_t cx[SGS_ST];      // the row's counts up to this tile, all loads in flight together
+#pragma unroll
+                for (uint32_t xx = 0; xx < SGS_ST; xx++) cx[xx] = xx <= x ? __ldcg(a.counts + rowfirst[r] + xx) : 0u;
+                for (uint32_t w = 0; w < NW; w++) start += sm.wc[r][w];
+#pragma unroll
+                for (uint32_t xx = 0; xx < SGS_ST; xx++) start += xx < x ? cx[xx] : 0u;
+                const uint32_t c = cx[x];
+                a.ranges[ty * a.tiles_x + tx] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            }
+            sm.run[tid] = start;
+        }
+        __syncthreads();
+    } else if (tid < 16) {
         const uint32_t tx = tx0 + (tid & 3u), ty = ty0 + (tid >> 2);
         sm.run[tid] = (tx < (uint32_t)a.tiles_x && ty < (uint32_t)a.tiles_y) ? a.ranges[ty * a.tiles_x + tx].x : 0u;
     }
 
+    mark();
     uint32_t cur = 0;                    // side of key / idx holding the current order (resident path)
     const uint32_t* gorder = nullptr;    // long buckets: the order lives in global scratch
     if (n <= SGS_FS_CAP) {
-        for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) {
+        for (uint32_t i = tid; i < n; i += NT) {
             const uint32_t gid = (uint32_t)__ldcg(bucket + i);
             sm.key[0][i] = __ldcg(a.depth_raw + gid) - key_min;
             sm.idx[0][i] = (uint16_t)i;
         }
         __syncthreads();
+        mark();
         const uint32_t per = (((n + NW - 1) / NW) + 31u) & ~31u;
+        // i / per for i < 4096 as a multiplication: m = ceil(2^24 / per), error m per - 2^24 < per <= 256, i * 256 < 2^24
+        const uint32_t per_inv = ((1u << 24) + per - 1u) / per;
+        const uint32_t rounds = (n + NT - 1) / NT;
         for (uint32_t p = 0; p < npass; p++) {
             const uint32_t shift = p * dbits;
             uint16_t* rank = sm.idx[cur ^ 1u];
             const uint32_t total = fs_rank(sm, sm.key[cur], rank, n, shift, dbits, per);
             fs_digit_scan(sm, total, nd);
-            // two-phase scatter: the rank array aliases the destination index array
-            uint32_t k[SGS_FS_IPT], dst[SGS_FS_IPT];
-            uint16_t v[SGS_FS_IPT];
+            // scatter: the keys move at once; the rank array aliases the destination index array, so the indices
+            // wait in registers (destination and index packed, 12 bits each) until every rank has been read
+            uint32_t dv[SGS_FS_IPT];
 #pragma unroll
             for (int u = 0; u < SGS_FS_IPT; u++) {
-                const uint32_t i = tid + u * SGS_EXP_THREADS;
+                if ((uint32_t)u >= rounds) break;     // block-uniform
+                const uint32_t i = tid + u * NT;
                 if (i < n) {
-                    k[u] = sm.key[cur][i];
-                    v[u] = sm.idx[cur][i];
-                    const uint32_t d = (k[u] >> shift) & (nd - 1u);
-                    dst[u] = sm.cnt[d] + sm.whist[i / per][d] + rank[i];
+                    const uint32_t k = sm.key[cur][i];
+                    const uint32_t d = (k >> shift) & (nd - 1u);
+                    const uint32_t dst = sm.cnt[d] + sm.whist[(i * per_inv) >> 24][d] + rank[i];
+                    sm.key[cur ^ 1u][dst] = k;
+                    dv[u] = dst | ((uint32_t)sm.idx[cur][i] << 16);
                 }
             }
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < SGS_FS_IPT; u++) {
-                const uint32_t i = tid + u * SGS_EXP_THREADS;
-                if (i < n) {
-                    sm.key[cur ^ 1u][dst[u]] = k[u];
-                    sm.idx[cur ^ 1u][dst[u]] = v[u];
-                }
+                if ((uint32_t)u >= rounds) break;
+                const uint32_t i = tid + u * NT;
+                if (i < n) sm.idx[cur ^ 1u][dv[u] & 0xFFFFu] = (uint16_t)(dv[u] >> 16);
             }
             __syncthreads();
             cur ^= 1u;
+            mark();
         }
     } else {
         uint32_t* K[2] = {a.scratch_key[0] + cr.x, a.scratch_key[1] + cr.x};
         uint32_t* V[2] = {a.scratch_val[0] + cr.x, a.scratch_val[1] + cr.x};
-        for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) {
+        for (uint32_t i = tid; i < n; i += NT) {
             const uint32_t gid = (uint32_t)__ldcg(bucket + i);
             K[0][i] = __ldcg(a.depth_raw + gid) - key_min;
             V[0][i] = i;
@@ -1034,21 +1108,21 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const
         for (uint32_t p = 0; p < npass; p++) {
             const uint32_t shift = p * dbits;
             // digit totals of the whole bucket -> bucket starts
-            for (uint32_t d = tid; d < SGS_SORT_ND; d += SGS_EXP_THREADS) sm.cnt[d] = 0u;
+            for (uint32_t d = tid; d < SGS_SORT_ND; d += NT) sm.cnt[d] = 0u;
             __syncthreads();
-            for (uint32_t i = tid; i < n; i += SGS_EXP_THREADS) atomicAdd(&sm.cnt[(K[side][i] >> shift) & (nd - 1u)], 1u);
+            for (uint32_t i = tid; i < n; i += NT) atomicAdd(&sm.cnt[(K[side][i] >> shift) & (nd - 1u)], 1u);
             __syncthreads();
             const uint32_t tot_all = tid < nd ? sm.cnt[tid] : 0u;
             __syncthreads();
             fs_digit_scan(sm, tot_all, nd);
             for (uint32_t c0 = 0; c0 < n; c0 += SGS_FS_CAP) {
                 const uint32_t m = min((uint32_t)SGS_FS_CAP, n - c0);
-                for (uint32_t i = tid; i < m; i += SGS_EXP_THREADS) sm.key[0][i] = K[side][c0 + i];
+                for (uint32_t i = tid; i < m; i += NT) sm.key[0][i] = K[side][c0 + i];
                 __syncthreads();
                 const uint32_t per = (((m + NW - 1) / NW) + 31u) & ~31u;
                 const uint32_t total = fs_rank(sm, sm.key[0], sm.idx[0], m, shift, dbits, per);
                 __syncthreads();
-                for (uint32_t i = tid; i < m; i += SGS_EXP_THREADS) {
+                for (uint32_t i = tid; i < m; i += NT) {
                     const uint32_t kk = sm.key[0][i];
                     const uint32_t d = (kk >> shift) & (nd - 1u);
                     const uint32_t dst = sm.cnt[d] + sm.whist[i / per][d] + sm.idx[0][i];
@@ -1066,7 +1140,7 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const
 
     // ---- expansion of the depth-ordered bucket into the 16 tile lists (as tile_fill_kernel)
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint32_t i0 = 0; i0 < n; i0 += SGS_EXP_THREADS) {
+    for (uint32_t i0 = 0; i0 < n; i0 += NT) {
         const uint32_t i = i0 + tid;
         unsigned long long pr = 0ull;
         if (i < n) pr = __ldcg(bucket + (gorder ? gorder[i] : (uint32_t)sm.idx[cur][i]));
@@ -1098,6 +1172,7 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_sorted_kernel(const
         __syncthreads();   // every warp has read wc / run of this chunk
         if (warp == 0 && lane < 16) sm.run[lane] += total;
     }
+    mark();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1143,7 +1218,8 @@ int binning_grid_blocks() {
         cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(coarse_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(binning_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-        cudaFuncSetAttribute(tile_fill_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
+        cudaFuncSetAttribute(tile_fill_sorted_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem<512>));
+        cudaFuncSetAttribute(tile_fill_sorted_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 3 blocks per SM
         cached = sms;
         cached_dev = dev;
     }
@@ -1161,15 +1237,13 @@ static int vblocks_for(size_t n) {
 int binning_depth_vblocks(int P) { return vblocks_for((size_t)P); }
 size_t binning_hist_words(size_t n) { return ((size_t)vblocks_for(n) + 1) * SGS_SORT_ND; }
 
-// 1 (default): the supertiles sort themselves (tile_fill_sorted_kernel); 0: depth-sort the Gaussians first.
-// Developer switch for A/B measurements: SGS_BIN_MODE.
-static int binning_mode() {
-    static const int mode = [] {
-        const char* e = getenv("SGS_BIN_MODE");
-        return e ? atoi(e) : 1;
-    }();
-    return mode;
-}
+// Where the depth sort happens.  1: inside every supertile (tile_fill_sorted_kernel; fastest while a bucket fits a
+// block's shared memory); 0: one global sort of the P Gaussians first (round-2a design; scales to dense scenes).
+// Chosen per forward call by sgs_api.cu (binning_set_mode) from the previous frame's counts; both are exact.
+static thread_local int g_binning_mode = 1;
+void binning_set_mode(int mode) { g_binning_mode = mode ? 1 : 0; }
+static int binning_mode() { return g_binning_mode; }
+int binning_bucket_capacity() { return SGS_FS_CAP; }
 
 static DepthArgs make_depth_args(int P, const GeomState& g, HostSlot* slot, unsigned long long ticket) {
     DepthArgs a;
@@ -1245,9 +1319,17 @@ static cudaError_t launch_expand(const CoarseArgs& a, const ViewParams& vp, cons
     x.scratch_key[1] = b.coarse_keys[1];
     x.scratch_val[0] = b.coarse_vals[0];
     x.scratch_val[1] = b.coarse_vals[1];
-    tile_count_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
-    if (binning_mode() == 0) tile_fill_kernel<<<a.n_super, SGS_EXP_THREADS, 0, s>>>(x);
-    else tile_fill_sorted_kernel<<<a.n_super, SGS_EXP_THREADS, sizeof(FillSmem), s>>>(x);
+    x.counts = img.tile_count;
+    x.prof = g_prof_on ? g_prof_host : nullptr;
+    x.local_scan = (binning_mode() != 0 && x.n_tiles <= SGS_LOCALSCAN_TILES) ? 1 : 0;
+    const dim3 grid(a.n_super);
+    cudaError_t e;
+    if (x.local_scan) e = launch_pdl(tile_count_kernel<false>, grid, dim3(SGS_EXP_THREADS), 0, s, x);
+    else e = launch_pdl(tile_count_kernel<true>, grid, dim3(SGS_EXP_THREADS), 0, s, x);
+    if (e != cudaSuccess) return e;
+    if (binning_mode() == 0) e = launch_pdl(tile_fill_kernel, grid, dim3(SGS_EXP_THREADS), 0, s, x);
+    else e = launch_pdl(tile_fill_sorted_kernel<512>, grid, dim3(512), sizeof(FillSmem<512>), s, x);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

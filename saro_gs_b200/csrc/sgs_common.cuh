@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #define SGS_TILE_X 16
 #define SGS_TILE_Y 16
@@ -168,6 +169,37 @@ __host__ __device__ inline void carve(char*& chunk, T*& ptr, size_t count, size_
 }
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be scheduled while its predecessor in
+// the stream is still draining (its launch latency, ~3 us per kernel boundary on B200, disappears); it must execute
+// pdl_wait() before it touches anything the predecessor wrote.  pdl_wait() is a no-op for a normal launch.
+// SGS_NO_PDL=1 turns the attribute off (A/B measurements).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SGS_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------
 // Small device helpers
 // ---------------------------------------------------------------------------------------
 
@@ -265,6 +297,8 @@ int    binning_depth_vblocks(int P);
 size_t binning_hist_words(size_t n);
 int    binning_supertiles(int tiles_x, int tiles_y, int* super_x);
 int    binning_coarse_list_side(int n_super);
+void   binning_set_mode(int mode);                  // this thread's next launches: 1 sort inside the supertiles, 0 globally
+int    binning_bucket_capacity();                   // entries a supertile block sorts in shared memory
 cudaError_t launch_depth_sort(int P, GeomState g, HostSlot* slot, unsigned long long ticket, cudaStream_t s);
 cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
                                 cudaStream_t s);

@@ -54,7 +54,8 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     // SH rows travel through shared memory so that both the 192-B reads and the 192-B gradient writes of a
     // warp are fully coalesced (32 consecutive rows = 6 KB contiguous)
     __shared__ float4 s_sh[VEC_SH ? (SGS_PRE_THREADS / 32) * 32 * SGS_SH_PAD4 : 1];
-    stage_view(cam, vp);
+    stage_view(cam, vp);     // camera constants: inputs of the call, not written by the predecessor
+    pdl_wait();              // launched programmatically dependent on the backward render kernel (writes `acc`)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = idx < P;
     const int M = vp.sh_coeffs;
@@ -421,13 +422,13 @@ void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, co
     // 128-bit accesses to the caller's rotations / dL_drot only when both pointers are 16-byte aligned
     const int rot_vec = (((reinterpret_cast<size_t>(rotations) | reinterpret_cast<size_t>(dL_drot)) & 15) == 0) ? 1 : 0;
     if (vec)
-        preprocess_bwd_kernel<true><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
-                                                          g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
+        launch_pdl(preprocess_bwd_kernel<true>, dim3(grid), dim3(block), 0, s, P, vp, means3D, radii, shs, scales, rotations,
+                   cov3D, (const uint8_t*)g.clamped, (const float4*)g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
+                   dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
     else
-        preprocess_bwd_kernel<false><<<grid, block, 0, s>>>(P, vp, means3D, radii, shs, scales, rotations, cov3D,
-                                                           g.clamped, g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
-                                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
+        launch_pdl(preprocess_bwd_kernel<false>, dim3(grid), dim3(block), 0, s, P, vp, means3D, radii, shs, scales, rotations,
+                   cov3D, (const uint8_t*)g.clamped, (const float4*)g.conic_opacity, acc, dL_dmean2D, dL_dopacity, dL_dcolor,
+                   dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, rot_vec, sink);
 }
 
 }  // namespace sgs

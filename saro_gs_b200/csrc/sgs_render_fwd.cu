@@ -97,6 +97,7 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     uint32_t a2 = (uint32_t)__cvta_generic_to_shared(s_g2);
     asm volatile("" : "+r"(a0), "+r"(a1), "+r"(a2));
 
+    pdl_wait();     // launched programmatically dependent on the expansion kernel that writes ranges / point_list
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
 
@@ -224,10 +225,9 @@ void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageS
                        float* out_depth, cudaStream_t s) {
     dim3 grid(vp.tiles_x, vp.tiles_y, 1);
 #define SGS_LAUNCH_RF(WP, TC)                                                                              \
-    render_fwd_kernel<WP, TC><<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, point_list, g.means2D,         \
-                                                             g.conic_opacity, g.rgbd, img.final_T,         \
-                                                             img.n_contrib, img.tile_count, b.packed,      \
-                                                             out_color, out_depth)
+    launch_pdl(render_fwd_kernel<WP, TC>, grid, dim3(SGS_R_THREADS), 0, s, vp, img.ranges, point_list,      \
+               g.means2D, g.conic_opacity, g.rgbd, img.final_T, img.n_contrib, img.tile_count, b.packed,    \
+               out_color, out_depth)
     if (write_packed) {
         if (tile_cull) SGS_LAUNCH_RF(true, true); else SGS_LAUNCH_RF(true, false);
     } else {

@@ -77,14 +77,25 @@ def check_against_reference_order(sgs, dev, scene, cam):
     return R, color, depth
 
 
-def test_config2_lists_equal_one_stable_64bit_sort(sgs, dev):
+@pytest.fixture(params=[1, 0], ids=["sort-in-supertile", "global-depth-sort"])
+def bin_mode(request):
+    """Both places the depth sort can happen (sgs_debug_set_binning_mode); the automatic choice is exercised by
+    every other test of the suite."""
+    from saro_gs_b200 import _lib
+    lib = _lib.load()
+    lib.sgs_debug_set_binning_mode(request.param)
+    yield request.param
+    lib.sgs_debug_set_binning_mode(-1)
+
+
+def test_config2_lists_equal_one_stable_64bit_sort(sgs, dev, bin_mode):
     from saro_gs_b200 import synthetic
     scene, cam = synthetic.config2_scene()
     R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
     assert R == 3927052
 
 
-def test_multi_slice_depth_sort(sgs, dev):
+def test_multi_slice_depth_sort(sgs, dev, bin_mode):
     """P = 2.6 M: more keys than the depth-sort blocks keep resident in shared memory (148 x 16 384)."""
     from saro_gs_b200 import synthetic
     scene, cam = synthetic.config2_scene(P=2_600_000, seed=5, width=320, height=240, fx=180.0, log_scale_mean=-4.2)
@@ -92,7 +103,7 @@ def test_multi_slice_depth_sort(sgs, dev):
     assert R > 0
 
 
-def test_multi_slice_tile_sort(sgs, dev):
+def test_multi_slice_tile_sort(sgs, dev, bin_mode):
     """> 3.03 M instances: more than the tile-sort blocks keep resident (148 x 20 480); config 2 with 1.8x larger splats."""
     from saro_gs_b200 import synthetic
     scene, cam = synthetic.config2_scene(log_scale_mean=-2.4)
@@ -100,7 +111,7 @@ def test_multi_slice_tile_sort(sgs, dev):
     assert R > 6_000_000
 
 
-def test_long_supertile_buckets(sgs, dev):
+def test_long_supertile_buckets(sgs, dev, bin_mode):
     """200 k Gaussians on a 320 x 240 image: 20 supertiles whose buckets (tens of thousands of entries) exceed what a
     block sorts in shared memory — the chunked path of tile_fill_sorted_kernel through global scratch."""
     from saro_gs_b200 import synthetic
@@ -109,7 +120,7 @@ def test_long_supertile_buckets(sgs, dev):
     assert R > 200_000
 
 
-def test_three_pass_tile_sort(sgs, dev):
+def test_three_pass_tile_sort(sgs, dev, bin_mode):
     """> 65 536 tiles (17 tile bits = 3 radix passes): 4800 x 3600 image."""
     from saro_gs_b200 import synthetic
     scene, cam = synthetic.config2_scene(P=60_000, seed=2, width=4800, height=3600, fx=2600.0, log_scale_mean=-3.4)
@@ -118,7 +129,7 @@ def test_three_pass_tile_sort(sgs, dev):
 
 
 @pytest.mark.parametrize("P", [1, 31, 1023, 1025, 70_001])
-def test_small_and_ragged_sizes(sgs, dev, P):
+def test_small_and_ragged_sizes(sgs, dev, P, bin_mode):
     from saro_gs_b200 import synthetic
     scene, cam = synthetic.small_scene(P=P, seed=P)
     check_against_reference_order(sgs, dev, scene, cam)
@@ -141,7 +152,7 @@ def test_prediction_too_small_relaunches_with_exact_size(sgs, dev):
     assert torch.equal(st0["n_contrib"], st1["n_contrib"])
 
 
-def test_nothing_visible_and_all_same_depth(sgs, dev):
+def test_nothing_visible_and_all_same_depth(sgs, dev, bin_mode):
     """Degenerate key ranges: every Gaussian culled (zero radix passes) and every Gaussian at the same depth
     (one-bit key range; ties keep ascending index)."""
     from saro_gs_b200 import synthetic

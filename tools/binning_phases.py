@@ -28,11 +28,14 @@ with torch.no_grad():
         if i >= 2:
             acc.append(np.array(buf[:], dtype=np.int64))
 a = np.stack(acc)
-for name, lo in (("depth_sort_kernel", 0), ("tile_sort_kernel", 64)):
-    seg = a[:, lo:lo + 64]
+for name, lo, w in (("depth_sort_kernel", 0, 64), ("tile_sort_kernel", 64, 32), ("tile_fill_sorted block 0", 96, 16),
+                    ("tile_fill_sorted block 200", 112, 16)):
+    seg = a[:, lo:lo + w]
     n = int((seg[0] > 0).sum())
     rel = (seg[:, :n] - seg[:, :1]) / 1e3
     print(name, "phase marks (us from kernel start, median over runs):")
     print("  ", np.round(np.median(rel, 0), 1).tolist())
     print("   deltas:", np.round(np.diff(np.median(rel, 0)), 1).tolist())
 print("gap depth end -> tile start (us):", float(np.median(a[:, 64] - a[:, :64].max(1))) / 1e3)
+print("fill block 0 start - coarse end (us):", float(np.median(a[:, 96] - a[:, 64:96].max(1))) / 1e3,
+      " block 200 start - block 0 start (us):", float(np.median(a[:, 112] - a[:, 96])) / 1e3)
