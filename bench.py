@@ -56,6 +56,18 @@ UNIT = "ms/frame"
 WORKLOAD = "configs[1]: synthetic N3D-like cook_spinach stand-in, P=300000, 1352x1014, SH deg 3, R=3927052"
 
 
+def pin_rank_to_cores(local_rank, world):
+    """One-process-per-GPU runs: give every rank its own slice of the host cores so that eight Python processes (plus
+    their CUDA / NCCL helper threads) do not migrate across each other inside the timed region."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(1, world)
+        if world > 1 and per >= 2:
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+    except (AttributeError, OSError):
+        pass
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -122,6 +134,7 @@ def make_inputs(dev, rank):
 
 def run_native_or_ref(args, impl):
     rank, world, local = dist_setup(args.gpus)
+    pin_rank_to_cores(local, world)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     import saro_gs_b200 as sgs
@@ -215,8 +228,19 @@ def run_native_or_ref(args, impl):
         torch.cuda.synchronize()
 
     def timed(step_fn, K, W_, profile=False):
+        import gc
         for i in range(W_):
             step_fn(i)
+        # measurement hygiene for the multi-rank runs (round 1: single 1.1 - 2.0 ms steps on one rank of eight cost the
+        # whole job 8 %, the per-rank medians were identical): no cyclic-GC pause inside a timed step
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(step_fn, K, W_, profile)
+        finally:
+            gc.enable()
+
+    def _timed(step_fn, K, W_, profile):
         barrier()
         if profile:
             _lib.load().sgs_profile_read(None, None, None)  # reset
@@ -404,10 +428,11 @@ def run_native_or_ref(args, impl):
                                          "peak_Tinst_s": issue_peak / 1e12, "frac": wi / (k_ms * 1e-3) / issue_peak}
         # the HBM-bound stages, each against the same measured copy bandwidth; bytes = what THIS implementation has to
         # move at minimum, not the reference's 172 B per instance of sort traffic
-        Rc = 0.35 * Rk                                    # (supertile, Gaussian) instances: ~0.35 per kept instance
+        Rc = 0.233 * Rk                                   # (supertile, Gaussian) instances per kept instance (measured
+                                                          # at configs[1]: 504 k of 2.16 M, tools/bucket_stats.py)
         stage_bytes = {
             "preprocess_fwd": 52 * P + (192 + 67) * V,
-            "depth_sort_scan": (4 + 3 * 16 + 16) * P,
+            "depth_sort_scan": 12 * P,                    # since round 2b only the supertile-count scan is left here
             "tile_sort": 4 * Rk + 28 * Rc + 12 * P,
             "preprocess_bwd": 48 * P + (107 + 192) * V + (40 + 192) * P,
         }
@@ -426,9 +451,11 @@ def run_native_or_ref(args, impl):
         line["stage_ms_per_step"] = {n: stage["ms"][n] / K for n in stage["ms"]}
         line["ms_per_step_with_stage_events"] = prof_ms / K
         line["gpu_launches"] = stage["own_launches"]
-        line["gpu_launches_note"] = "hand-written kernels only (9 per step: preprocess, depth sort, coarse sort, tile " \
-                                    "count, tile fill, render | render bwd, preprocess bwd + one 14 MB memset); no " \
-                                    "library (CUB / cuBLAS) kernels on this path since round 2"
+        line["gpu_launches_note"] = "hand-written kernels only, counted in the stage-profiled pass (8 per step: preprocess, " \
+                                    "supertile scan, supertile bucketing, tile count, per-supertile sort + tile fill, " \
+                                    "render | render bwd, preprocess bwd, + one 14 MB memset; the timed pass fuses " \
+                                    "scan + bucketing into one cooperative launch); no library (CUB / cuBLAS) " \
+                                    "kernels on this path since round 2"
         if rank == 0 and not args.no_extras:
             import contextlib
             with contextlib.redirect_stdout(sys.stderr):     # stdout carries exactly one JSON line
@@ -447,7 +474,8 @@ def run_native_or_ref(args, impl):
 
 
 # newest `ncu --set full` capture of the render kernels on this exact workload (tools/ncu_summary.py output)
-NCU_SUMMARIES = ["profiles/r2_render_ncu_summary.csv", "profiles/r02f_render_ncu_summary.csv"]
+NCU_SUMMARIES = ["profiles/r2m_render_ncu_summary.csv", "profiles/r2_render_ncu_summary.csv",
+                 "profiles/r02f_render_ncu_summary.csv"]
 
 
 def load_ncu_summary(kernel):

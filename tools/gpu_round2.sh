@@ -44,7 +44,7 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'render_(fwd|bwd)_kernel' -s 6 -c 2 \
       -f -o $OUT/${TAG}_render python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sequence > $OUT/${TAG}_ncu_render.log 2>&1
   echo "=== ncu full: binning kernels"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'(depth_sort|coarse_sort|tile_count|tile_fill)_kernel' -s 12 -c 4 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"(binning_fused|tile_count|tile_fill_sorted)_kernel" -s 9 -c 3 \
       -f -o $OUT/${TAG}_binning python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sequence > $OUT/${TAG}_ncu_binning.log 2>&1
   ls -la $OUT | tail -12
 fi
