@@ -892,6 +892,7 @@ __global__ void __launch_bounds__(SGS_EXP_THREADS) tile_fill_kernel(const Expand
 // Buckets longer than SGS_FS_CAP run the same passes chunk by chunk through global scratch (slow but exact).
 // ------------------------------------------------------------------------------------------------
 #define SGS_FS_CAP 4096
+#define SGS_FS_FIX_MAX 96          // longest top-digit bucket the single-pass sort places by counting
 #define SGS_LOCALSCAN_TILES 8192   // up to here every fill block reads all tile counts itself (32 KB from L2)
 template <int NT>
 struct FillSmem {
@@ -1064,7 +1065,63 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 3 : 4) tile_fill_sorted_kernel
         // i / per for i < 4096 as a multiplication: m = ceil(2^24 / per), error m per - 2^24 < per <= 256, i * 256 < 2^24
         const uint32_t per_inv = ((1u << 24) + per - 1u) / per;
         const uint32_t rounds = (n + NT - 1) / NT;
-        for (uint32_t p = 0; p < npass; p++) {
+        // Fast path for keys that spread over the frame's depth range (the normal case): ONE stable pass on the TOP
+        // digit, then every entry finds its exact place inside its digit bucket — a handful of entries — by counting
+        // the bucket's entries that precede it in (key, position) order.  8 barrier-separated phases instead of 18.
+        // Buckets longer than SGS_FS_FIX_MAX (depths clustered in a sliver of the range) fall through to the LSD
+        // passes below; sides 0 of key / idx are untouched until then.
+        bool sorted_msd = false;
+        if (npass >= 2u) {
+            const uint32_t mbits = min(9u, nbits), mshift = nbits - mbits, mnd = 1u << mbits;
+            uint16_t* rank = sm.idx[1];
+            const uint32_t total = fs_rank(sm, sm.key[0], rank, n, mshift, mbits, per);
+            fs_digit_scan(sm, total, mnd);
+            if (__syncthreads_or(total > SGS_FS_FIX_MAX ? 1 : 0) == 0) {
+                uint32_t dv[SGS_FS_IPT];
+#pragma unroll
+                for (int u = 0; u < SGS_FS_IPT; u++) {
+                    if ((uint32_t)u >= rounds) break;     // block-uniform
+                    const uint32_t i = tid + u * NT;
+                    if (i < n) {
+                        const uint32_t k = sm.key[0][i];
+                        const uint32_t d = k >> mshift;
+                        const uint32_t dst = sm.cnt[d] + sm.whist[(i * per_inv) >> 24][d] + rank[i];
+                        sm.key[1][dst] = k;
+                        dv[u] = dst | ((uint32_t)sm.idx[0][i] << 16);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < SGS_FS_IPT; u++) {
+                    if ((uint32_t)u >= rounds) break;
+                    const uint32_t i = tid + u * NT;
+                    if (i < n) sm.idx[1][dv[u] & 0xFFFFu] = (uint16_t)(dv[u] >> 16);
+                }
+                __syncthreads();
+                // exact placement inside the digit bucket [b0, b1)
+#pragma unroll
+                for (int u = 0; u < SGS_FS_IPT; u++) {
+                    if ((uint32_t)u >= rounds) break;
+                    const uint32_t j = tid + u * NT;
+                    if (j < n) {
+                        const uint32_t k = sm.key[1][j];
+                        const uint32_t d = k >> mshift;
+                        const uint32_t b0 = sm.cnt[d], b1 = (d + 1u < mnd) ? sm.cnt[d + 1u] : n;
+                        uint32_t c = 0;
+                        for (uint32_t q = b0; q < b1; q++) {
+                            const uint32_t kq = sm.key[1][q];
+                            c += (kq < k || (kq == k && q < j)) ? 1u : 0u;
+                        }
+                        sm.idx[0][b0 + c] = sm.idx[1][j];
+                    }
+                }
+                __syncthreads();
+                cur = 0u;
+                sorted_msd = true;
+                mark();
+            }
+        }
+        for (uint32_t p = 0; p < (sorted_msd ? 0u : npass); p++) {
             const uint32_t shift = p * dbits;
             uint16_t* rank = sm.idx[cur ^ 1u];
             const uint32_t total = fs_rank(sm, sm.key[cur], rank, n, shift, dbits, per);

@@ -38,8 +38,10 @@ struct FwdPix2 {
 // ($R/cuda_rasterizer/forward.cu:342-379).  A pixel that does not blend (inactive, alpha < 1/255, or saturating)
 // runs through the same packed code with alpha = 0: then test_T = T * 1 = T and C += (c * 0) * T = C exactly
 // (C is never -0: it starts at +0 and a round-to-nearest sum that cancels gives +0).
+// `median_open` (warp-uniform): some pixel of the warp still has T > 0.5, i.e. the median-depth test can still fire;
+// once every pixel is past it the six instructions of the test are skipped (T only decreases).
 __forceinline__ __device__ void blend_pixels2(FwdPix2& s, float2 pw, bool act0, bool act1, float o, const float4 c,
-                                              uint32_t pos) {
+                                              uint32_t pos, bool median_open) {
     const float2 e = expf2_exact(pw);
     float2 alpha = __fmul2_rn(make_float2(o, o), e);
     alpha.x = min(0.99f, alpha.x);
@@ -54,13 +56,15 @@ __forceinline__ __device__ void blend_pixels2(FwdPix2& s, float2 pw, bool act0, 
     s.C0 = __ffma2_rn(__fmul2_rn(make_float2(c.x, c.x), alpha), s.T, s.C0);
     s.C1 = __ffma2_rn(__fmul2_rn(make_float2(c.y, c.y), alpha), s.T, s.C1);
     s.C2 = __ffma2_rn(__fmul2_rn(make_float2(c.z, c.z), alpha), s.T, s.C2);
+    if (median_open) {
+        if (go0 && s.T.x > 0.5f && test_T.x < 0.5) s.D.x = c.w;
+        if (go1 && s.T.y > 0.5f && test_T.y < 0.5) s.D.y = c.w;
+    }
     if (go0) {
-        if (s.T.x > 0.5f && test_T.x < 0.5) s.D.x = c.w;
         s.T.x = test_T.x;
         s.last0 = pos + 1u;
     }
     if (go1) {
-        if (s.T.y > 0.5f && test_T.y < 0.5) s.D.y = c.w;
         s.T.y = test_T.y;
         s.last1 = pos + 1u;
     }
@@ -177,6 +181,9 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
             // saturation of the whole quadrant is tested once per 32 staged slots, not once per visit
             both_done = px2.done0 && px2.done1;
             if (__all_sync(0xFFFFFFFFu, both_done)) break;
+            // can the median-depth test still fire for some pixel of the warp?  (T never increases; a finished or
+            // out-of-image pixel cannot blend any more)
+            const bool median_open = __any_sync(0xFFFFFFFFu, (!px2.done0 && px2.T.x > 0.5f) || (!px2.done1 && px2.T.y > 0.5f));
             uint32_t word = __shfl_sync(0xFFFFFFFFu, mywords, k);
             while (word) {
                 const uint32_t j = k * 32 + (__ffs(word) - 1);
@@ -192,7 +199,7 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                 if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;
                 const float4 c = lds128(a2 + j * 16u);
                 const uint32_t pos = __float_as_uint(g1.z);
-                blend_pixels2(px2, pw, act0, act1, g1.w, c, pos);
+                blend_pixels2(px2, pw, act0, act1, g1.w, c, pos, median_open);
             }
         }
         both_done = px2.done0 && px2.done1;

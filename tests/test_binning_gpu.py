@@ -120,6 +120,22 @@ def test_long_supertile_buckets(sgs, dev, bin_mode):
     assert R > 200_000
 
 
+def test_clustered_depths(sgs, dev, bin_mode):
+    """Nearly all Gaussians within a sliver of the frame's depth range (a few far ones stretch it): the per-supertile
+    sort's single-pass fast path (top digit + counting inside the digit bucket) must hand over to the LSD passes."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=20_000, seed=11, width=320, height=240, fx=180.0, log_scale_mean=-3.8)
+    m = scene.means3D.clone()
+    near = m[:, 2] > 0.5
+    g = torch.Generator().manual_seed(3)
+    z = 10.0 + 1e-3 * torch.rand(m.shape[0], generator=g)
+    z[::97] = 35.0
+    scale = torch.where(near, z / m[:, 2].clamp_min(0.5), torch.ones_like(z))
+    m = torch.where(near[:, None], m * scale[:, None], m)      # same pixel, new depth
+    R, _, _ = check_against_reference_order(sgs, dev, scene._replace(means3D=m.contiguous()), cam)
+    assert R > 20_000
+
+
 def test_three_pass_tile_sort(sgs, dev, bin_mode):
     """> 65 536 tiles (17 tile bits = 3 radix passes): 4800 x 3600 image."""
     from saro_gs_b200 import synthetic
