@@ -120,6 +120,15 @@ def test_long_supertile_buckets(sgs, dev, bin_mode):
     assert R > 200_000
 
 
+def test_large_splats_small_image(sgs, dev, bin_mode):
+    """300 k large splats on a 320 x 240 image: every Gaussian overlaps most of the 20 supertiles, buckets of > 100 k
+    entries (multi-slice bucketing pass + the chunked per-supertile sort)."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=300_000, seed=13, width=320, height=240, fx=180.0, log_scale_mean=-2.2)
+    R, _, _ = check_against_reference_order(sgs, dev, scene, cam)
+    assert R > 1_000_000
+
+
 def test_clustered_depths(sgs, dev, bin_mode):
     """Nearly all Gaussians within a sliver of the frame's depth range (a few far ones stretch it): the per-supertile
     sort's single-pass fast path (top digit + counting inside the digit bucket) must hand over to the LSD passes."""
