@@ -32,9 +32,11 @@
  *
  * Differences from the reference ABI, all additive:
  *   - `stream` and `flags` parameters;
- *   - sgs_backward takes `dL_dacc` ([P][12] float scratch, need not be initialised) where
- *     the reference takes dL_dconic ([P][2][2], must be zero), and it WRITES every output
- *     element, so outputs need not be zero-initialised;
+ *   - where the reference takes dL_dconic ([P][2][2], must be zero) sgs_backward keeps the parameter
+ *     `dL_dacc` for ABI stability but ignores it (may be NULL): its [P][12] moment accumulator is
+ *     part of the geometry state, zeroed by the forward pass (which therefore must have run with
+ *     SGS_FLAG_KEEP_FOR_BACKWARD) and left zeroed again by the backward pass; and it WRITES every
+ *     output element, so outputs need not be zero-initialised;
  *   - errors are reported by a negative return code + sgs_last_error() instead of C++
  *     exceptions.
  */
@@ -92,7 +94,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user,
 /* Backward: R is the value sgs_forward returned.  Outputs (all fully written):
  *   dL_dmean2D [P][3] (z = 0), dL_dopacity [P], dL_dcolor [P][3], dL_dmean3D [P][3],
  *   dL_dcov3D [P][6], dL_dsh [P][M][3], dL_dscale [P][3], dL_drot [P][4].
- * dL_dacc: [P][12] float scratch. */
+ * dL_dacc: ignored (NULL allowed) — kept from ABI version 1, where it was a [P][12] float scratch. */
 int sgs_backward(int P, int D, int M, int64_t R,
                  const float* background, int width, int height,
                  const float* means3D, const float* shs, const float* colors_precomp,

@@ -207,7 +207,6 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     dL_dsh = torch.empty((P, M, 3), **opts)
     dL_dscales = torch.empty((P, 3), **opts)
     dL_drotations = torch.empty((P, 4), **opts)
-    dL_dacc = torch.empty((P, 12), **opts)
 
     sink = _take_densify_sink()
     if sink is not None and (sink.P != P or sink.device != dev):
@@ -223,7 +222,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
             _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
             _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
-            _ptr(dL_dout_color), _ptr(dL_dmeans2D), _ptr(dL_dacc), _ptr(dL_dopacity), _ptr(dL_dcolors),
+            _ptr(dL_dout_color), _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
             _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations),
             ctypes.c_void_p(stream))
     _check(rc, "sgs_backward")

@@ -59,6 +59,9 @@ sgs::GeomState carve_geom(char*& chunk, size_t P) {
     g.depth_vblocks = sgs::binning_depth_vblocks((int)P);
     sgs::carve(chunk, g.hist, ((size_t)g.depth_vblocks + 1) * 512);
     sgs::carve(chunk, g.blocksum, (size_t)g.depth_vblocks);
+    // always carved (an inference-mode forward merely never touches it): a backward call on such a state must not
+    // write outside the buffer
+    sgs::carve(chunk, g.acc, P * 12);
     return g;
 }
 
@@ -388,7 +391,7 @@ int64_t sgs_forward(sgs_resize_fn geometry_buffer, void* geometry_user, sgs_resi
     }
     auto render = [&]() -> int {
         StageScope sc(SGS_STAGE_RENDER_FWD, s, 1);
-        sgs::launch_render_fwd(vp, g, bin, img, bin.point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
+        sgs::launch_render_fwd(P, vp, g, bin, img, bin.point_list, keep ? 1 : 0, cull, out_color, out_depth, s);
         SGS_CUDA_OK(cudaGetLastError());
         return 0;
     };
@@ -495,8 +498,9 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     if (P == 0) return 0;
     if (!geom_buffer || !binning_buffer || !image_buffer)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null state buffer");
+    (void)dL_dacc;   // ABI compatibility: the accumulator is part of the geometry state since round 2 (may be NULL)
     if (!means3D || !viewmatrix || !projmatrix || !campos || !background || !radii || !dL_dpix || !dL_dmean2D ||
-        !dL_dacc || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+        !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
         return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null required pointer");
     if (shs != nullptr && M > 0 && !dL_dsh) return fail(SGS_ERR_INVALID_ARGUMENT, "sgs_backward: null dL_dsh");
 
@@ -509,19 +513,17 @@ int sgs_backward(int P, int D, int M, int64_t R, const float* background, int wi
     // only the header + packed records are needed: their position does not depend on the kept count
     sgs::BinningState bin = carve_binning(binning_buffer, 0, true, /*header_and_packed_only=*/true);
 
-    {
-        StageScope sc(SGS_STAGE_BWD_ZERO, s, 0);
-        SGS_CUDA_OK(cudaMemsetAsync(dL_dacc, 0, sizeof(float) * 12 * (size_t)P, s));
-    }
+    // No zero-fill here (round 1 issued a 14 MB memset): the moment accumulator g.acc was zeroed by the forward render
+    // kernel and is left zeroed again by the backward-preprocess kernel below.
     if (R > 0) {
         StageScope sc(SGS_STAGE_RENDER_BWD, s, 1);
-        sgs::launch_render_bwd(vp, bin, img, dL_dpix, dL_dacc, s);
+        sgs::launch_render_bwd(vp, bin, img, dL_dpix, g.acc, s);
     }
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
     {
         StageScope sc(SGS_STAGE_PREPROCESS_BWD, s, 1);
         sgs::launch_preprocess_bwd(P, vp, means3D, radii, shs, cov3D_precomp ? nullptr : scales,
-                                   cov3D_precomp ? nullptr : rotations, cov3D, g, dL_dacc, dL_dmean2D, dL_dopacity,
+                                   cov3D_precomp ? nullptr : rotations, cov3D, g, g.acc, dL_dmean2D, dL_dopacity,
                                    dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, sink, s);
     }
     (void)colors_precomp;

@@ -126,6 +126,10 @@ struct GeomState {
     uint32_t* hist;           // [depth_vblocks + 1][512] per-block digit histograms of the current radix pass
     uint32_t* blocksum;       // [depth_vblocks] per-slice supertile count of the scan
     int       depth_vblocks;  // virtual blocks of the depth sort (multiple of the grid size)
+    float*    acc;            // [P][12] moment accumulators of the backward render kernel; present only when the state
+                              // is kept for backward: zeroed by the forward render kernel (its memory system is idle),
+                              // consumed AND re-zeroed by the backward-preprocess kernel (a second backward pass over
+                              // the same state starts clean) — no memset launch in backward
 };
 
 // Opaque "image" state: per pixel + per tile.  Replaces ImageState ($R/.../rasterizer_impl.h:50-57).
@@ -306,7 +310,7 @@ cudaError_t launch_tile_binning(int P, const ViewParams& vp, GeomState g, Binnin
 cudaError_t launch_binning_fused(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img, int keep,
                                  HostSlot* slot, unsigned long long ticket, cudaStream_t s);
 
-void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
+void launch_render_fwd(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,
                        float* out_depth, cudaStream_t s);
 
@@ -322,7 +326,7 @@ struct DensifySink {
 
 void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, const int* radii, const float* shs,
                            const float* scales, const float* rotations, const float* cov3D, GeomState g,
-                           const float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+                           float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                            DensifySink sink, cudaStream_t s);
 

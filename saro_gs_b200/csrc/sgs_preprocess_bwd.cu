@@ -46,7 +46,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
                       const int* __restrict__ radii, const float* __restrict__ shs,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
                       const float* __restrict__ cov3Ds, const uint8_t* __restrict__ clamped,
-                      const float4* __restrict__ conic_opacity, const float* __restrict__ acc, float* __restrict__ dL_dmean2D,
+                      const float4* __restrict__ conic_opacity, float* __restrict__ acc, float* __restrict__ dL_dmean2D,
                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot, int rot_vec, const DensifySink sink) {
@@ -68,7 +68,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
     uint8_t pre_cm = 0;
     if (valid) {
         pre_radius = radii[idx];
-        const float4* arow = reinterpret_cast<const float4*>(acc + (size_t)idx * 12);
+        float4* arow = reinterpret_cast<float4*>(acc + (size_t)idx * 12);
         pre_a0 = arow[0]; pre_a1 = arow[1]; pre_a2 = arow[2];
         pre_co = conic_opacity[idx];
         pre_mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
@@ -353,6 +353,12 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
             dL_dscale[3 * idx + i] = o_scale[i];
         }
         dL_dopacity[idx] = o_opacity;
+        // leave the moment accumulator of this Gaussian zeroed again (only visible Gaussians ever receive atomics): a
+        // second backward pass over the same forward state starts clean without any memset (sgs_common.cuh: GeomState)
+        if (pre_radius > 0) {
+            float4* arow = reinterpret_cast<float4*>(acc + (size_t)idx * 12);
+            arow[0] = arow[1] = arow[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         // densification statistics of this view (train.py:211-215 of the reference) as an epilogue: the means2D gradient
         // and the radius are in registers, so sgs_densify_add_view costs no launch and no re-read (csrc/sgs_densify.cu
         // holds the stand-alone kernel with the same arithmetic).  Culled Gaussians would add 0 / 0 / max(., 0).
@@ -412,7 +418,7 @@ preprocess_bwd_kernel(int P, const __grid_constant__ ViewParams vp, const float*
 
 void launch_preprocess_bwd(int P, const ViewParams& vp, const float* means3D, const int* radii, const float* shs,
                            const float* scales, const float* rotations, const float* cov3D, GeomState g,
-                           const float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+                           float* acc, float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
                            float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                            DensifySink sink, cudaStream_t s) {
     if (P <= 0) return;

@@ -171,6 +171,7 @@ render_bwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     const float pxf = pin_reg((float)px);
     const float2 npy = {pin_reg(-(float)py0), pin_reg(-(float)py1)};
 
+    pdl_wait();     // launched programmatically dependent on whatever precedes it in the stream (forward render, loss)
     const uint32_t start = ranges[tile].x;
     const int count = (int)tile_count[tile];
     if (count == 0) return;
@@ -392,8 +393,9 @@ void launch_render_bwd(const ViewParams& vp, BinningState b, ImageState img, con
         return e ? atoi(e) : 1;
     }();
 #define SGS_LAUNCH_RB(BATCH, G, MINB)                                                                        \
-    render_bwd_kernel<BATCH, G, MINB><<<grid, SGS_R_THREADS, 0, s>>>(vp, img.ranges, img.tile_count, b.packed, \
-                                                                     img.final_T, img.n_contrib, dL_dpix, acc)
+    launch_pdl(render_bwd_kernel<BATCH, G, MINB>, grid, dim3(SGS_R_THREADS), 0, s, vp, (const uint2*)img.ranges,   \
+               (const uint32_t*)img.tile_count, (const PackedInst*)b.packed, (const float*)img.final_T,          \
+               (const uint32_t*)img.n_contrib, dL_dpix, acc)
     if (variant == 0) SGS_LAUNCH_RB(128, 0, 10);
     else if (variant == 2) SGS_LAUNCH_RB(64, 5, 7);
     else if (variant == 3) SGS_LAUNCH_RB(64, 4, 8);

@@ -77,7 +77,8 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
                   const float4* __restrict__ conic_opacity, const float4* __restrict__ rgbd,
                   float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                   uint32_t* __restrict__ tile_count, PackedInst* __restrict__ packed,
-                  float* __restrict__ out_color, float* __restrict__ out_depth) {
+                  float* __restrict__ out_color, float* __restrict__ out_depth, float4* __restrict__ acc4,
+                  uint32_t acc_n4) {
     __shared__ float4 s_g0[SGS_R_BATCH];   // x, y, A, -B
     __shared__ float4 s_g1[SGS_R_BATCH];   // C, thr, list_pos(bits), opacity
     __shared__ float4 s_g2[SGS_R_BATCH];   // r, g, b, depth
@@ -101,6 +102,15 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     uint32_t a2 = (uint32_t)__cvta_generic_to_shared(s_g2);
     asm volatile("" : "+r"(a0), "+r"(a1), "+r"(a2));
 
+    if (WRITE_PACKED) {
+        // zero this CTA's share of the backward pass's moment accumulator ([P][12] floats): the kernel is bound by
+        // instruction issue and its memory system is idle, so the 14 MB fill costs nothing here and the backward pass
+        // needs no memset launch.  Independent of the predecessor kernel: done before the dependency wait.
+        const uint32_t ctas = gridDim.x * gridDim.y;
+        const uint32_t per = (acc_n4 + ctas - 1) / ctas;
+        const uint32_t b0 = tile * per, b1 = min(acc_n4, b0 + per);
+        for (uint32_t i = b0 + tid; i < b1; i += SGS_R_THREADS) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     pdl_wait();     // launched programmatically dependent on the expansion kernel that writes ranges / point_list
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -227,14 +237,14 @@ render_fwd_kernel(const __grid_constant__ ViewParams vp, const uint2* __restrict
     }
 }
 
-void launch_render_fwd(const ViewParams& vp, GeomState g, BinningState b, ImageState img,
+void launch_render_fwd(int P, const ViewParams& vp, GeomState g, BinningState b, ImageState img,
                        const uint32_t* point_list, int write_packed, int tile_cull, float* out_color,
                        float* out_depth, cudaStream_t s) {
     dim3 grid(vp.tiles_x, vp.tiles_y, 1);
 #define SGS_LAUNCH_RF(WP, TC)                                                                              \
     launch_pdl(render_fwd_kernel<WP, TC>, grid, dim3(SGS_R_THREADS), 0, s, vp, img.ranges, point_list,      \
                g.means2D, g.conic_opacity, g.rgbd, img.final_T, img.n_contrib, img.tile_count, b.packed,    \
-               out_color, out_depth)
+               out_color, out_depth, reinterpret_cast<float4*>(g.acc), (uint32_t)P * 3u)
     if (write_packed) {
         if (tile_cull) SGS_LAUNCH_RF(true, true); else SGS_LAUNCH_RF(true, false);
     } else {

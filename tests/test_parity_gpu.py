@@ -293,9 +293,15 @@ def test_full_size_backward_vs_f64_oracle(sgs, dev, oracle_mod):
         assert err_max <= bar_max, (k, err_max, bar_max)
         assert err_nrm <= bar_nrm, (k, err_nrm, bar_nrm)
         assert q9999 <= GRAD_TOL, (k, q9999)
-        colsum = got.reshape(got.shape[0], -1).sum(axis=0)
+        # no systematic bias: the column sums of the error stay within 2e-5 of the column sums of |gradient| plus the
+        # one-entry noise of the ill-conditioned Gaussians discussed above (2e-3 of the largest entry).  (Round 2a
+        # compared the column sums themselves with 2e-3 of the largest column sum: where a column nearly cancels, the
+        # run-to-run flip of a single needle-shaped Gaussian exceeded that and the test failed about one run in five.)
+        G2, W2 = got.reshape(got.shape[0], -1), want.reshape(want.shape[0], -1)
         ref_colsum = d[f"colsum_{k}"]
-        assert np.abs(colsum - ref_colsum).max() <= 2e-3 * np.abs(ref_colsum).max() + 1e-12, k
+        assert np.abs(W2.sum(axis=0) - ref_colsum).max() <= 1e-7 * np.abs(W2).sum(axis=0).max() + 1e-12, k   # pin
+        bias = np.abs((G2 - W2).sum(axis=0))
+        assert (bias <= 2e-5 * np.abs(W2).sum(axis=0) + 2e-3 * float(np.abs(W2).max())).all(), (k, bias)
 
 
 def test_config3_sequence_bit_exact(sgs, dev):
@@ -593,6 +599,28 @@ def test_runs_on_a_non_default_stream(sgs, dev):
         assert maxrel(g1[k], g0[k]) < GRAD_TOL, k
 
 
+def test_backward_twice_on_the_same_forward_state(sgs, dev):
+    """retain_graph=True: the second backward pass over the same saved state must find the moment accumulator of the
+    geometry buffer zeroed again (the backward-preprocess kernel re-zeroes what it consumes; there is no memset)."""
+    from saro_gs_b200 import synthetic
+    scene, cam = synthetic.config2_scene(P=20_000, width=320, height=240, fx=250.0)
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                           cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    leaves = {k: getattr(scene, k).to(dev).requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    color, radii, depth = sgs.GaussianRasterizer(rs)(means2D=m2d, **leaves)
+    cot = synthetic.cotangent(cam.height, cam.width).to(dev)
+    color.backward(cot, retain_graph=True)
+    first = {k: v.grad.clone() for k, v in leaves.items()}
+    for v in leaves.values():
+        v.grad = None
+    color.backward(cot)
+    for k, v in leaves.items():
+        scale = float(first[k].abs().max())
+        # only the order of the float atomics differs (a stale accumulator would double the gradient)
+        assert float((v.grad - first[k]).abs().max()) <= 1e-3 * scale, k
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_fuzz_vs_live_reference(sgs, dev, seed):
     """Random scenes, image sizes, ROTATED cameras, SH degrees, scale modifiers and backgrounds through both the
@@ -626,7 +654,7 @@ def test_fuzz_vs_live_reference(sgs, dev, seed):
                                            cam.projmatrix.to(dev), deg, cam.campos.to(dev), False)
     cot = torch.randn(3, H, W, generator=gen).to(dev)
     outs = []
-    for Rast in (sgs.GaussianRasterizer, RefRast, RefRast):
+    for Rast in (sgs.GaussianRasterizer, RefRast, RefRast, RefRast):
         leaves = {k: v.to(dev).clone().requires_grad_(True)
                   for k, v in dict(means3D=means, scales=scales, rotations=rots, opacities=op, shs=shs).items()}
         m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
@@ -635,8 +663,9 @@ def test_fuzz_vs_live_reference(sgs, dev, seed):
         g = {k: v.grad for k, v in leaves.items()}
         g["means2D"] = m2d.grad
         outs.append((color.detach(), radii, depth.detach(), g))
-    (c0, r0, d0, g0), (c1, r1, d1, g1), (_, _, _, g2) = outs
+    (c0, r0, d0, g0), (c1, r1, d1, g1), (_, _, _, g2), (_, _, _, g3) = outs
     assert torch.equal(r0, r1) and torch.equal(c0, c1) and torch.equal(d0, d1)
+    g64 = None      # float64 oracle gradients, computed only if some row needs the arbiter
     for k in g0:
         scale = float(g1[k].abs().max())
         if scale == 0.0:
@@ -648,8 +677,22 @@ def test_fuzz_vs_live_reference(sgs, dev, seed):
         # is 3e-5 there and they sit closer to the float64 oracle than the reference does).  Rows on which the
         # reference does not reproduce itself to 1e-5 cannot arbitrate and are left out; every other row must agree
         # to 2e-4 of the largest entry, and such rows must be the overwhelming majority.
-        a, b1, b2 = (t.reshape(t.shape[0], -1) for t in (g0[k], g1[k], g2[k]))
-        stable = (b1 - b2).abs().amax(dim=1) <= 1e-5 * scale
-        assert float(stable.float().mean()) > 0.97, (k, float(stable.float().mean()))
-        err = float((a - b1).abs().amax(dim=1)[stable].max()) / scale
-        assert err < 2e-4, (k, err)
+        # Three reference runs decide which rows are stable (two runs can agree by chance: the full suite then failed
+        # about once in ten runs on a "stable" row).  A stable row that still differs by more than 2e-4 goes to the
+        # float64 oracle: it must find the native value at least as close to the truth as the reference's.
+        a, b1, b2, b3 = (t.reshape(t.shape[0], -1) for t in (g0[k], g1[k], g2[k], g3[k]))
+        stable = ((b1 - b2).abs().amax(dim=1) <= 1e-5 * scale) & ((b1 - b3).abs().amax(dim=1) <= 1e-5 * scale)
+        assert float(stable.float().mean()) > 0.95, (k, float(stable.float().mean()))
+        row_err = (a - b1).abs().amax(dim=1) / scale
+        doubtful = stable & (row_err >= 2e-4)
+        if bool(doubtful.any()):
+            if g64 is None:
+                from oracle import oracle as oracle_mod
+                ctx = oracle_mod.forward(means, op, cam.viewmatrix, cam.projmatrix, cam.campos, bg, W, H, cam.tanfovx,
+                                         cam.tanfovy, sh_degree=deg, shs=shs, scales=scales, rotations=rots,
+                                         scale_modifier=mod, precision="f64")
+                g64 = ctx.backward(cot.cpu())
+            o = torch.as_tensor(np.asarray(g64[k], dtype=np.float64)).reshape(a.shape[0], -1).to(dev)
+            nat = (a.double() - o).abs().amax(dim=1)[doubtful]
+            ref = (b1.double() - o).abs().amax(dim=1)[doubtful]
+            assert bool((nat <= 1.05 * ref + 1e-6 * scale).all()), (k, int(doubtful.sum()), float(row_err[doubtful].max()))

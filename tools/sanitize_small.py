@@ -10,8 +10,16 @@ sys.path.insert(0, '.')
 import saro_gs_b200 as sgs
 from saro_gs_b200 import synthetic, loss_utils
 
+from saro_gs_b200 import _lib
+from saro_gs_b200.densify import BatchDensifyStats
+
 dev = torch.device('cuda:0')
-for (P, seed, kw) in [(3000, 0, dict(width=160, height=112, fx=120.0, log_scale_mean=-1.6)), (64, 1, {})]:
+# both places the depth sort can happen (round 2: per-supertile sort / global sort); P = 9000 on 160 x 112 pixels gives
+# supertile buckets beyond the 4096 entries a block sorts in shared memory (chunked path through global scratch)
+for (P, seed, kw, mode) in [(3000, 0, dict(width=160, height=112, fx=120.0, log_scale_mean=-1.6), 1),
+                            (3000, 0, dict(width=160, height=112, fx=120.0, log_scale_mean=-1.6), 0),
+                            (9000, 2, dict(width=160, height=112, fx=120.0, log_scale_mean=-1.6), 1), (64, 1, {}, 1)]:
+    _lib.load().sgs_debug_set_binning_mode(mode)
     scene, cam = synthetic.small_scene(P=P, seed=seed, **kw)
     rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev),
                                            1.0, cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
@@ -22,13 +30,16 @@ for (P, seed, kw) in [(3000, 0, dict(width=160, height=112, fx=120.0, log_scale_
                                                     scales=leaves["scales"], rotations=leaves["rotations"])
     gt = torch.rand_like(image)
     loss = loss_utils.l1_dssim_loss(image, gt, 0.2)
+    sink = BatchDensifyStats(P, dev)
+    sink.attach_next_backward()          # densification statistics in the epilogue of the backward-preprocess kernel
     loss.backward()
     torch.cuda.synchronize()
-    print("ok", P, float(loss), int((radii > 0).sum()), float(leaves["means3D"].grad.abs().sum()))
+    print("ok", P, "mode", mode, float(loss), int((radii > 0).sum()), float(leaves["means3D"].grad.abs().sum()),
+          int(sink.vis_count.sum()))
+_lib.load().sgs_debug_set_binning_mode(-1)
 
 # deformation hand-off (tcgen05 / TMEM kernel) and densification statistics on small clouds
 from saro_gs_b200 import deformation
-from saro_gs_b200.densify import BatchDensifyStats
 import types
 for P in (700, 129):
     scene, _ = synthetic.small_scene(P=P, seed=3)
@@ -61,7 +72,6 @@ torch.cuda.synchronize()
 print("plane ok", tuple(feats.shape), float(field.grids[0][0].grad.abs().sum()))
 
 # the capacity re-launch path of the binning (prediction forced to a few instances)
-from saro_gs_b200 import _lib
 _lib.load().sgs_debug_set_capacity(64)
 scene, cam = synthetic.small_scene(P=900, seed=5)
 rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
