@@ -224,7 +224,9 @@ int choose_binning_mode(int P, size_t supers) {
     const unsigned long long vis = pr.last_P > 0 ? (unsigned long long)((double)pr.visible * (P > pr.last_P ? (double)P / pr.last_P : 1.0))
                                                  : (unsigned long long)P;
     const unsigned long long est = 2ull * vis / (supers ? supers : 1);
-    return est * 4ull > 3ull * (unsigned long long)sgs::binning_bucket_capacity() ? 0 : 1;
+    // measured (tools/sweep.py, profiles/r2n_workload_sweep.json): buckets of ~4 700 entries (P = 1 M at 1352x1014, chunked
+    // path for most supertiles) still favour the per-supertile sort by 3 %, ~6 400 (P = 2 M at 1920x1080) the global one
+    return est * 10ull > 13ull * (unsigned long long)sgs::binning_bucket_capacity() ? 0 : 1;
 }
 size_t predict_capacity(int P) {
     const long long forced = g_forced_cap.load();

@@ -28,9 +28,13 @@ for name, kw in CASES:
     m2d = torch.zeros_like(params["means3D"], requires_grad=True)
     cot = synthetic.cotangent(cam.height, cam.width).to(dev)
     res = {}
-    for tag, Rast in (("native", sgs.GaussianRasterizer), ("reference", Ref)):
+    from saro_gs_b200 import _lib
+    for tag, Rast in (("native", sgs.GaussianRasterizer), ("native_sort_in_supertile", sgs.GaussianRasterizer),
+                      ("native_global_depth_sort", sgs.GaussianRasterizer), ("reference", Ref)):
         if Rast is None:
             continue
+        # where the binning stage sorts by depth: automatic choice (what users get) and both forced modes
+        _lib.load().sgs_debug_set_binning_mode({"native_sort_in_supertile": 1, "native_global_depth_sort": 0}.get(tag, -1))
         ts = []
         for i in range(13):
             for p in list(params.values()) + [m2d]:
