@@ -212,6 +212,41 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
                         float* out_rotations, float* out_scales, float* out_opacity, float* out_shs, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Training-time deformation (training half) — the MLP evaluations of
+ * GaussianModel.get_deformation (scene/saro_gaussian.py:779-847) over ALL N Gaussians and their backward.  Each
+ * evaluation is a job; all jobs of a call run in ONE persistent tcgen05 launch.
+ *
+ * sgs_deform_pack_general(backward = 0): image of an MLP  in_w -> 128 -> hid2 -> n_out  (nn.Linear parameters, W
+ *   [out][in] row-major; in_w = feat_dim [opacity_mlp, :103] or feat_dim + 9 [motion/rot/shs, :102,:106,:108];
+ *   hid2 <= 128; n_out <= 8 or == 48).  backward = 1: image of its data-gradient chain (transposed weights, no biases)
+ *   n_out -> hid2 -> 128 -> feat_dim.  `image`: sgs_deform_image_bytes() device bytes.
+ * sgs_deform_train_forward: per job, out[N][n_io] = MLP([feature | embedding(d)]) with d = timestamp - temporal_pos
+ *   (zero_time = 0, :788-790) or d = 0 (zero_time = 1: base feature :793-794, and opacity_mlp whose image has zero
+ *   weights on the time columns); writes the ReLU sign bits of both hidden layers (mask_a: layer 1, mask_b: layer 2;
+ *   N x 16 bytes each, may be NULL) and, if save_a / save_b are given, the hidden activations h1 / h2 as float32 [N][128].
+ * sgs_deform_train_backward: per job, in = dL/d out [N][n_io]; out = dL/d feature [N][feat_dim] of this job (the
+ *   caller sums the jobs); mask_a = the forward's LAYER-2 bits, mask_b = its LAYER-1 bits; save_a / save_b receive
+ *   dL/d(pre-activation) of layer 2 / layer 1 as float32 [N][128] (operands of the weight-gradient GEMMs).
+ * All pointers are device memory, 16-byte aligned.  Return 0 or a negative error code. */
+typedef struct sgs_mlp_job {
+    const void* packed;
+    const float* in;
+    float* out;
+    float* save_a;
+    float* save_b;
+    void* mask_a;
+    void* mask_b;
+    int n_io;
+    int zero_time;
+} sgs_mlp_job_t;
+size_t sgs_deform_image_bytes(void);
+int sgs_deform_pack_general(int backward, int in_w, int hid2, int n_out, int feat_dim, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* W3, const float* b3, void* image, void* stream);
+int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* temporal_pos, const float* feature, int n_jobs,
+                             const sgs_mlp_job_t* jobs, void* stream);
+int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Densification statistics of one training iteration — replaces the per-view lists and
  * the batch reduction of the reference's train.py:192-218 and :281-292 (with scene/saro_gaussian.py:745-747).
  *

@@ -49,6 +49,10 @@ ABI = {
     "sgs_deform_workspace_bytes": (ctypes.c_size_t, [_i]),
     "sgs_deform_pack_mlp": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_deform_eval": (_i64, [_i, _i, _f] + [_vp] * 10 + [_vp, ctypes.c_size_t] + [_vp] * 5 + [_vp]),
+    "sgs_deform_image_bytes": (ctypes.c_size_t, []),
+    "sgs_deform_pack_general": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_deform_train_forward": (_i, [_i, _i, _f, _vp, _vp, _i, _vp, _vp]),
+    "sgs_deform_train_backward": (_i, [_i, _i, _i, _vp, _vp]),
     "sgs_densify_add_view": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_densify_attach": (_i, [_i, _vp, _vp, _vp]),
     "sgs_densify_commit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -71,6 +75,13 @@ class PlaneDesc(ctypes.Structure):
     """sgs_plane_t of include/saro_gs_b200.h"""
     _fields_ = [("pyramid", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int), ("dim_u", ctypes.c_int),
                 ("dim_v", ctypes.c_int), ("max_mip_level", ctypes.c_int)]
+
+
+class MLPJob(ctypes.Structure):
+    """sgs_mlp_job_t of include/saro_gs_b200.h"""
+    _fields_ = [("packed", ctypes.c_void_p), ("inp", ctypes.c_void_p), ("out", ctypes.c_void_p), ("save_a", ctypes.c_void_p),
+                ("save_b", ctypes.c_void_p), ("mask_a", ctypes.c_void_p), ("mask_b", ctypes.c_void_p), ("n_io", ctypes.c_int),
+                ("zero_time", ctypes.c_int)]
 
 
 _lib = None

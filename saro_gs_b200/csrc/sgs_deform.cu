@@ -580,6 +580,344 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_mlp_kernel(const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
 
+
+// =====================================================================================================================
+// Training path (training half): GaussianModel.get_deformation (scene/saro_gaussian.py:
+// 779-847) evaluates, per view and over ALL Gaussians, opacity_mlp on the plane feature (lifespan, :782), the three
+// deformation MLPs on [feature | time embedding of t - temporal_pos] (:812,:819,:845) and again on the base feature
+// [feature | embedding of 0] (:796-803: regularisation residuals, real_xyz) — up to seven MLP evaluations — and
+// autograd runs their backward.  Here every evaluation is a "job" of ONE persistent tcgen05 launch (CTAs split between
+// the jobs by cost); forward jobs write raw outputs, the ReLU sign bits (16 bytes per row and layer) and, for the
+// weight-gradient kernel, the hidden activations.  The data-gradient chain  dy -> (.W3) o mask2 -> (.W2) o mask1 ->
+// (.W1[:, :F]) -> d feature  is the SAME three-layer pipeline with an image packed from the transposed weights and a
+// mask multiply in place of bias + ReLU, so it runs through the same code (BWD = true).
+constexpr int MAX_JOBS = 8;
+constexpr int TRAIN_SMEM_BYTES = IMG_PAD + 64;
+
+struct TrainJob {
+    const uint8_t* img;            // packed image (forward: from W; backward: from the transposed W)
+    const float* in;               // backward: dL/d out [N][n_io]
+    float* out;                    // forward: raw outputs [N][n_io]; backward: dL/d feature [N][feat_dim]
+    float* save_a; float* save_b;  // [N][128] float32 or NULL: forward h1, h2; backward d h2, d h1 (after the mask)
+    uint2* mask_a; uint2* mask_b;  // [N][2]: sign bits of the two hidden layers, 64 columns per entry (forward writes:
+                                   // a = layer 1, b = layer 2; backward reads: a = layer 2, b = layer 1)
+    int n_io;
+    int n3p;                       // forward 16 | 48, backward 32
+    int zero_time;                 // forward: the base feature (time embedding of 0)
+    int cta_first, cta_count;
+};
+struct TrainParams {
+    int N, feat_dim, n_jobs;
+    float timestamp;
+    const float* tpos; const float* feat;
+    TrainJob jobs[MAX_JOBS];
+};
+
+// general packer: forward image of an MLP in_w -> 128 -> hid2 -> n_out (zero padded to 48 / 128 / n3p), or the image
+// of its data-gradient chain n_out -> hid2 -> 128 -> feat_dim (transposed weights, no biases, n3p = 32)
+__global__ void pack_general_kernel(int backward, int in_w, int hid2, int n_out, int feat_dim, int n3p,
+                                    const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                                    const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ b3,
+                                    uint8_t* __restrict__ img) {
+    const int total = HID * K1 + HID * HID + 2 * n3p * HID + 2 * HID + N3_MAX;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int i = e;
+        if (i < HID * K1) {
+            const int n = i / K1, k = i % K1;
+            float v;
+            if (!backward) v = k < in_w ? W1[n * in_w + k] : 0.f;
+            else v = (k < n_out && n < hid2) ? W3[k * hid2 + n] : 0.f;
+            __nv_bfloat16 hi, lo;
+            split_bf16(v, hi, lo);
+            const int off = (k / 8) * (HID * 16) + n * 16 + (k % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W1HI + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W1LO + off) = lo;
+            continue;
+        }
+        i -= HID * K1;
+        if (i < HID * HID) {
+            const int n = i / HID, k = i % HID;
+            float v;
+            if (!backward) v = n < hid2 ? W2[n * HID + k] : 0.f;
+            else v = k < hid2 ? W2[k * HID + n] : 0.f;
+            __nv_bfloat16 hi, lo;
+            split_bf16(v, hi, lo);
+            const int off = (k / 8) * (HID * 16) + n * 16 + (k % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W2HI + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W2LO + off) = lo;
+            continue;
+        }
+        i -= HID * HID;
+        if (i < 2 * n3p * HID) {
+            const int ns = i / HID, k = i % HID, n = ns % n3p;
+            float v;
+            if (!backward) v = (n < n_out && k < hid2) ? W3[n * hid2 + k] : 0.f;
+            else v = n < feat_dim ? W1[k * in_w + n] : 0.f;
+            __nv_bfloat16 hi, lo;
+            split_bf16(v, hi, lo);
+            const int off = (k / 8) * (2 * n3p * 16) + ns * 16 + (k % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3 + off) = ns < n3p ? hi : lo;
+            continue;
+        }
+        i -= 2 * n3p * HID;
+        if (i < HID) { reinterpret_cast<float*>(img + OFF_B1)[i] = backward ? 0.f : b1[i]; continue; }
+        i -= HID;
+        if (i < HID) { reinterpret_cast<float*>(img + OFF_B2)[i] = (backward || i >= hid2) ? 0.f : b2[i]; continue; }
+        i -= HID;
+        reinterpret_cast<float*>(img + OFF_B3)[i] = (backward || i >= n_out) ? 0.f : b3[i];
+    }
+}
+
+// hidden layer epilogue of the training kernels.  Forward: + bias, ReLU, sign bits out.  Backward: multiply by the
+// saved sign bits.  Both: next layer's TMEM operand, optional float32 copy of the row for the weight-gradient kernel.
+template <bool BWD>
+__device__ __forceinline__ void hidden_epilogue_train(uint32_t t_acc, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias,
+                                                      int half, bool valid, float* __restrict__ save_row, uint2* __restrict__ mask_slot,
+                                                      uint2 mask_in) {
+    const int cbase = half * (HID / 2);
+    uint32_t mw[2] = {BWD ? mask_in.x : 0u, BWD ? mask_in.y : 0u};
+    uint32_t r[2][16];
+    tmem_ld16_async(t_acc + cbase, r[0]);
+#pragma unroll
+    for (int it = 0; it < HID / 32; ++it) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (it + 1 < HID / 32) tmem_ld16_async(t_acc + cbase + (it + 1) * 16, r[(it + 1) & 1]);
+        const int c0 = cbase + it * 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int bit = (it * 16 + h * 8 + 2 * i) & 31, word = it >> 1;      // 64 columns -> two 32-bit words
+                const float2 a = make_float2(__uint_as_float(r[it & 1][h * 8 + 2 * i]), __uint_as_float(r[it & 1][h * 8 + 2 * i + 1]));
+                if (!BWD) {
+                    const float2 b = *reinterpret_cast<const float2*>(bias + c0 + h * 8 + 2 * i);
+                    const float2 y = __fadd2_rn(a, b);
+                    x[i] = make_float2(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f));
+                    mw[word] |= (y.x > 0.f ? 1u : 0u) << bit;
+                    mw[word] |= (y.y > 0.f ? 1u : 0u) << (bit + 1);
+                } else {
+                    x[i] = make_float2((mw[word] >> bit) & 1u ? a.x : 0.f, (mw[word] >> (bit + 1)) & 1u ? a.y : 0.f);
+                }
+            }
+            store_chunk(t_hi, t_lo, c0 / 8 + h, x);
+            if (save_row != nullptr && valid) {
+                float4* dst = reinterpret_cast<float4*>(save_row + c0 + h * 8);
+                dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+                dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            }
+        }
+    }
+    if (!BWD && mask_slot != nullptr && valid) *mask_slot = make_uint2(mw[0], mw[1]);
+}
+
+struct TrainRow {
+    float tpos;
+    float4 v[6];       // forward: up to two 8-wide feature chunks in v[0..3]; backward: three 8-wide dy chunks
+};
+
+template <bool BWD, int K1STEPS>
+__device__ __forceinline__ void load_train_row(const TrainParams& p, const TrainJob& job, int src, int nf, int half, TrainRow& r) {
+    if (!BWD) {
+        r.tpos = __ldg(p.tpos + src);
+        const float4* frow = reinterpret_cast<const float4*>(p.feat + (size_t)src * p.feat_dim);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (2 * c + half < nf) {
+                r.v[2 * c] = __ldg(frow + 2 * (2 * c + half));
+                r.v[2 * c + 1] = __ldg(frow + 2 * (2 * c + half) + 1);
+            }
+    } else if (K1STEPS == 3) {                 // 48 gradient columns, 16-byte aligned rows
+        const float4* q = reinterpret_cast<const float4*>(job.in + (size_t)src * 48);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            r.v[2 * c] = __ldg(q + 2 * (2 * c + half));
+            r.v[2 * c + 1] = __ldg(q + 2 * (2 * c + half) + 1);
+        }
+    } else {                                   // at most 8 gradient columns: chunk 0, owned by half 0
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = (half == 0 && i < job.n_io) ? __ldg(job.in + (size_t)src * job.n_io + i) : 0.f;
+        r.v[0] = make_float4(t[0], t[1], t[2], t[3]);
+        r.v[1] = make_float4(t[4], t[5], t[6], t[7]);
+    }
+}
+
+template <bool BWD, int N3P, int K1STEPS>
+__device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& job, const uint8_t* img, int group, int worker,
+                                          int workers, uint32_t tmem_group, uint32_t mbar) {
+    const int gt = threadIdx.x & (GROUP_THREADS - 1);
+    const int row = gt & (ROWS - 1), half = gt >> 7, warp_in_group = gt >> 5;
+    const bool issuer = warp_in_group == 0;
+    const uint32_t lane_base = (uint32_t)((warp_in_group & 3) * 32) << 16;
+    const uint32_t acc_u = tmem_group, hi_u = tmem_group + 128, lo_u = tmem_group + 192;
+    const uint32_t t_acc = acc_u + lane_base, t_hi = hi_u + lane_base, t_lo = lo_u + lane_base;
+    const uint32_t simg = smem_u32(img);
+    const float* b1 = reinterpret_cast<const float*>(img + OFF_B1);
+    const float* b2 = reinterpret_cast<const float*>(img + OFF_B2);
+    const float* b3 = reinterpret_cast<const float*>(img + OFF_B3);
+    const int N = p.N;
+    const int tiles = (N + ROWS - 1) / ROWS;
+    const int nf = p.feat_dim >> 3;
+    uint32_t phase = 0;
+
+    TrainRow cur;
+    if (worker < tiles) {
+        const int j0 = worker * ROWS + row;
+        load_train_row<BWD, K1STEPS>(p, job, j0 < N ? j0 : N - 1, nf, half, cur);
+    }
+#pragma unroll 1
+    for (int tile = worker; tile < tiles; tile += workers) {
+        const int j = tile * ROWS + row;
+        const bool valid = j < N;
+        const size_t jr = (size_t)(valid ? j : N - 1);
+
+        // ---- layer-1 operand
+        if (!BWD) {
+            const float d = job.zero_time ? 0.f : p.timestamp - cur.tpos;       // saro_gaussian.py:788-794
+            float emb[TIME_DIMS];
+            emb[0] = d;
+            sincosf(d, &emb[1], &emb[2]);
+#pragma unroll
+            for (int f = 1; f < 4; ++f) {
+                emb[1 + 2 * f] = 2.f * emb[2 * f - 1] * emb[2 * f];
+                emb[2 + 2 * f] = 1.f - 2.f * emb[2 * f - 1] * emb[2 * f - 1];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int kc = 2 * c + half;
+                float2 x[4];
+                if (c < 2 && kc < nf) {
+                    const float4 u = cur.v[2 * (c < 2 ? c : 0)], w = cur.v[2 * (c < 2 ? c : 0) + 1];
+                    x[0] = make_float2(u.x, u.y); x[1] = make_float2(u.z, u.w);
+                    x[2] = make_float2(w.x, w.y); x[3] = make_float2(w.z, w.w);
+                } else if (kc == nf) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(emb[2 * i], emb[2 * i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(0.f, 0.f);
+                    if (kc == nf + 1) x[0].x = emb[8];
+                }
+                store_chunk(t_hi, t_lo, kc, x);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < (K1STEPS == 3 ? 3 : 1); ++c) {
+                const int kc = 2 * c + half;
+                const float4 u = cur.v[2 * c], w = cur.v[2 * c + 1];
+                float2 x[4] = {make_float2(u.x, u.y), make_float2(u.z, u.w), make_float2(w.x, w.y), make_float2(w.z, w.w)};
+                store_chunk(t_hi, t_lo, kc, x);
+            }
+        }
+        publish_operand(group);
+        if (issuer) issue_layer<K1STEPS>(acc_u, hi_u, lo_u, simg + OFF_W1HI, simg + OFF_W1LO, HID, mbar);
+
+        // ---- while the tensor core works: the next tile's inputs, this tile's sign bits (backward)
+        TrainRow nxt = cur;
+        if (tile + workers < tiles) {
+            const int jn = (tile + workers) * ROWS + row;
+            load_train_row<BWD, K1STEPS>(p, job, jn < N ? jn : N - 1, nf, half, nxt);
+        }
+        uint2 m_a = make_uint2(0u, 0u), m_b = make_uint2(0u, 0u);
+        if (BWD && valid) {
+            m_a = __ldg(job.mask_a + jr * 2 + half);
+            m_b = __ldg(job.mask_b + jr * 2 + half);
+        }
+
+        mbar_wait(mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b1, half, valid, job.save_a ? job.save_a + jr * HID : nullptr,
+                                   job.mask_a ? job.mask_a + jr * 2 + half : nullptr, m_a);
+        publish_operand(group);
+        if (issuer) issue_layer<HID / 16>(acc_u, hi_u, lo_u, simg + OFF_W2HI, simg + OFF_W2LO, HID, mbar);
+        mbar_wait(mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b2, half, valid, job.save_b ? job.save_b + jr * HID : nullptr,
+                                   job.mask_b ? job.mask_b + jr * 2 + half : nullptr, m_b);
+        publish_operand(group);
+        if (issuer) issue_last_layer(acc_u, hi_u, lo_u, simg + OFF_W3, N3P, mbar);
+        mbar_wait(mbar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- output epilogue: accumulator columns [0, N3P) hold hi*hi + lo*hi, [N3P, 2 N3P) hold hi*lo
+        if (N3P == 16) {
+            float r[8], r2[8];
+            tmem_ld8(t_acc, r);
+            tmem_ld8(t_acc + N3P, r2);
+            if (valid && half == 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < job.n_io) job.out[jr * job.n_io + c] = (r[c] + r2[c]) + b3[c];
+            }
+        } else {
+            constexpr int PER = N3P / 2;                         // 24 (forward, 48 outputs) or 16 (backward, <= 32 feature columns)
+            const int width = BWD ? p.feat_dim : 48;
+#pragma unroll
+            for (int c0 = 0; c0 < PER; c0 += 8) {
+                float r[8], r2[8];
+                tmem_ld8(t_acc + half * PER + c0, r);
+                tmem_ld8(t_acc + N3P + half * PER + c0, r2);
+                const int col = half * PER + c0;
+                if (valid && col < width) {
+                    float4* dst = reinterpret_cast<float4*>(job.out + jr * width + col);
+                    const float* bb = b3 + col;
+                    dst[0] = make_float4((r[0] + r2[0]) + bb[0], (r[1] + r2[1]) + bb[1], (r[2] + r2[2]) + bb[2], (r[3] + r2[3]) + bb[3]);
+                    dst[1] = make_float4((r[4] + r2[4]) + bb[4], (r[5] + r2[5]) + bb[5], (r[6] + r2[6]) + bb[6], (r[7] + r2[7]) + bb[7]);
+                }
+            }
+        }
+        cur = nxt;
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_train_kernel(const __grid_constant__ TrainParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* img = smem;
+    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + IMG_PAD);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, group = tid / GROUP_THREADS;
+    int ji = 0;
+    while (ji + 1 < p.n_jobs && (int)blockIdx.x >= p.jobs[ji].cta_first + p.jobs[ji].cta_count) ++ji;
+    const TrainJob& job = p.jobs[ji];
+    const int worker = ((int)blockIdx.x - job.cta_first) * 2 + group;
+    const int workers = job.cta_count * 2;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(job.img);
+        uint4* dst = reinterpret_cast<uint4*>(img);
+        for (int i = tid; i < IMG_BYTES / 16; i += 2 * GROUP_THREADS) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + 1)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t tmem_group = tmem + (uint32_t)group * 256;
+    const uint32_t mbar = smem_u32(mbar_p + group);
+
+    if (!BWD) {
+        if (job.n3p == 16) run_train<false, 16, K1 / 16>(p, job, img, group, worker, workers, tmem_group, mbar);
+        else run_train<false, 48, K1 / 16>(p, job, img, group, worker, workers, tmem_group, mbar);
+    } else {
+        if (job.n_io <= 8) run_train<true, 32, 1>(p, job, img, group, worker, workers, tmem_group, mbar);
+        else run_train<true, 32, 3>(p, job, img, group, worker, workers, tmem_group, mbar);
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+
 std::mutex g_mu;
 int* g_pinned_count = nullptr;
 cudaEvent_t g_count_ready = nullptr;
@@ -707,6 +1045,96 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
     // selection pass is, while the MLP kernel keeps running
     if (cudaEventSynchronize(g_count_ready) != cudaSuccess) return SGS_ERR_CUDA;
     return (int64_t)*g_pinned_count;
+}
+
+
+size_t sgs_deform_image_bytes(void) { return (size_t)sgs_deform::IMG_BYTES; }
+
+int sgs_deform_pack_general(int backward, int in_w, int hid2, int n_out, int feat_dim, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* W3, const float* b3, void* image, void* stream) {
+    using namespace sgs_deform;
+    if (in_w <= 0 || in_w > K1 || hid2 <= 0 || hid2 > HID || n_out <= 0 || n_out > N3_MAX || (n_out > 8 && n_out != 48) ||
+        feat_dim <= 0 || (feat_dim & 7) || feat_dim > 32 || feat_dim > in_w || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !image)
+        return SGS_ERR_INVALID_ARGUMENT;
+    const int n3p = backward ? 32 : (n_out <= 8 ? 16 : 48);
+    pack_general_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(backward, in_w, hid2, n_out, feat_dim, n3p, W1, b1, W2, b2, W3, b3,
+                                                              reinterpret_cast<uint8_t*>(image));
+    return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
+}
+
+static int sgs_deform_train_launch(bool backward, int N, int feat_dim, float timestamp, const float* temporal_pos,
+                                   const float* feature, int n_jobs, const sgs_mlp_job_t* jobs, void* stream) {
+    using namespace sgs_deform;
+    if (N < 0 || feat_dim <= 0 || (feat_dim & 7) || feat_dim > 32 || n_jobs <= 0 || n_jobs > MAX_JOBS || !jobs)
+        return SGS_ERR_INVALID_ARGUMENT;
+    if (N == 0) return 0;
+    if (!backward && (!temporal_pos || !feature || (reinterpret_cast<size_t>(feature) & 15))) return SGS_ERR_INVALID_ARGUMENT;
+    static int sm_count = 0;
+    static bool attr_set[2] = {false, false};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (sm_count == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        }
+        if (!attr_set[backward]) {
+            const cudaError_t e = backward
+                ? cudaFuncSetAttribute(deform_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIN_SMEM_BYTES)
+                : cudaFuncSetAttribute(deform_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIN_SMEM_BYTES);
+            if (e != cudaSuccess) return SGS_ERR_CUDA;
+            attr_set[backward] = true;
+        }
+    }
+    TrainParams p;
+    p.N = N; p.feat_dim = feat_dim; p.n_jobs = n_jobs; p.timestamp = timestamp; p.tpos = temporal_pos; p.feat = feature;
+    float cost[MAX_JOBS], total = 0.f;
+    for (int i = 0; i < n_jobs; ++i) {
+        const sgs_mlp_job_t& j = jobs[i];
+        if (!j.packed || !j.out || j.n_io <= 0 || (j.n_io > 8 && j.n_io != 48)) return SGS_ERR_INVALID_ARGUMENT;
+        if (backward && (!j.in || !j.mask_a || !j.mask_b)) return SGS_ERR_INVALID_ARGUMENT;
+        if ((reinterpret_cast<size_t>(j.out) | reinterpret_cast<size_t>(j.in) | reinterpret_cast<size_t>(j.save_a) |
+             reinterpret_cast<size_t>(j.save_b) | reinterpret_cast<size_t>(j.mask_a) | reinterpret_cast<size_t>(j.mask_b)) & 15)
+            return SGS_ERR_INVALID_ARGUMENT;
+        TrainJob& t = p.jobs[i];
+        t.img = reinterpret_cast<const uint8_t*>(j.packed);
+        t.in = j.in; t.out = j.out; t.save_a = j.save_a; t.save_b = j.save_b;
+        t.mask_a = reinterpret_cast<uint2*>(j.mask_a); t.mask_b = reinterpret_cast<uint2*>(j.mask_b);
+        t.n_io = j.n_io; t.n3p = backward ? 32 : (j.n_io <= 8 ? 16 : 48); t.zero_time = j.zero_time;
+        cost[i] = (j.n_io > 8 ? COST_SHS : COST_ROT) + ((j.save_a || j.save_b) ? 2.f : 0.f);
+        total += cost[i];
+    }
+    const int tiles = (N + ROWS - 1) / ROWS;
+    int grid = sm_count > 0 ? sm_count : 148;
+    const int useful = n_jobs * ((tiles + 1) / 2);
+    if (grid > useful) grid = useful;
+    if (grid < n_jobs) grid = n_jobs;
+    // CTAs in proportion to the jobs' cost per tile, at least one each (largest remainder to the costliest jobs)
+    int given = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        int c = (int)(grid * (cost[i] / total));
+        if (c < 1) c = 1;
+        p.jobs[i].cta_count = c;
+        given += c;
+    }
+    for (int i = 0; given < grid; i = (i + 1) % n_jobs) { ++p.jobs[i].cta_count; ++given; }
+    for (int i = 0; given > grid; i = (i + 1) % n_jobs)
+        if (p.jobs[i].cta_count > 1) { --p.jobs[i].cta_count; --given; }
+    int first = 0;
+    for (int i = 0; i < n_jobs; ++i) { p.jobs[i].cta_first = first; first += p.jobs[i].cta_count; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (backward) deform_train_kernel<true><<<grid, 2 * GROUP_THREADS, TRAIN_SMEM_BYTES, s>>>(p);
+    else deform_train_kernel<false><<<grid, 2 * GROUP_THREADS, TRAIN_SMEM_BYTES, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
+}
+
+int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* temporal_pos, const float* feature, int n_jobs,
+                             const sgs_mlp_job_t* jobs, void* stream) {
+    return sgs_deform_train_launch(false, N, feat_dim, timestamp, temporal_pos, feature, n_jobs, jobs, stream);
+}
+
+int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream) {
+    return sgs_deform_train_launch(true, N, feat_dim, 0.f, nullptr, nullptr, n_jobs, jobs, stream);
 }
 
 }  // extern "C"

@@ -181,3 +181,213 @@ def get_deformation_eval(self, timestamp, rays=None):
     if torch.is_tensor(timestamp):
         timestamp = float(timestamp)
     return _run(timestamp, n, cache["inputs"], cache["packed"], ws)
+
+
+# ======================================================================================================================
+# Training path: GaussianModel.get_deformation (scene/saro_gaussian.py:779-847)
+# ======================================================================================================================
+_TRAIN_MLPS = ("motion_mlp", "rot_mlp", "shs_mlp", "opacity_mlp")
+
+
+class TrainImages:
+    """Forward and data-gradient tensor-core images of the four MLPs get_deformation evaluates (motion, rot, shs and
+    opacity_mlp, scene/saro_gaussian.py:102-108); re-packed when a weight tensor was written (optimizer step)."""
+
+    def __init__(self, motion_mlp, rot_mlp, shs_mlp, opacity_mlp):
+        lib = _lib.load()
+        self._modules = (motion_mlp, rot_mlp, shs_mlp, opacity_mlp)
+        self.shapes = []
+        params = [_linears(m) for m in self._modules]
+        dev = params[0][0].device
+        in_w = params[0][0].shape[1]
+        self.feat_dim = in_w - TIME_DIMS
+        if self.feat_dim not in (8, 16, 24, 32):
+            raise UnsupportedDeformationConfig(f"plane feature width {self.feat_dim}: the kernels support 8, 16, 24 and 32")
+        for m, ps in enumerate(params):
+            W1, b1, W2, b2, W3, b3 = ps
+            w_in, hid2, n_out = W1.shape[1], W2.shape[0], W3.shape[0]
+            ok = (W1.shape[0] == HIDDEN and W2.shape[1] == HIDDEN and W3.shape[1] == hid2 and hid2 <= HIDDEN and
+                  w_in == (self.feat_dim if m == 3 else in_w) and (n_out <= 8 or n_out == 48) and
+                  tuple(b1.shape) == (HIDDEN,) and tuple(b2.shape) == (hid2,) and tuple(b3.shape) == (n_out,))
+            if not ok:
+                raise UnsupportedDeformationConfig(f"{_TRAIN_MLPS[m]}: parameter shapes {[tuple(t.shape) for t in ps]} are not "
+                                                   f"a {w_in}-128-(<=128)-(<=8 | 48) MLP")
+            self.shapes.append((w_in, hid2, n_out))
+        nbytes = lib.sgs_deform_image_bytes()
+        self.stride = (nbytes + 255) // 256 * 256
+        self.buffer = torch.empty(8 * self.stride, dtype=torch.uint8, device=dev)      # [mlp][forward | backward]
+        self.versions = None
+
+    def params(self):
+        """The 24 parameter tensors as they are now (modules may swap them)."""
+        return [t for m in self._modules for t in _linears(m)]
+
+    def image(self, mlp, backward):
+        return self.buffer.data_ptr() + (2 * mlp + int(backward)) * self.stride
+
+    def refresh(self, params):
+        cur = [(t.data_ptr(), t._version) for t in params]
+        if cur == self.versions:
+            return
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(self.buffer.device).cuda_stream
+        with torch.cuda.device(self.buffer.device):
+            for m in range(4):
+                ts = [_check(t, f"{_TRAIN_MLPS[m]} parameter", None) for t in params[6 * m:6 * m + 6]]
+                w_in, hid2, n_out = self.shapes[m]
+                for backward in (0, 1):
+                    rc = lib.sgs_deform_pack_general(backward, w_in, hid2, n_out, self.feat_dim, *[_ptr(t) for t in ts],
+                                                     self.image(m, backward), stream)
+                    if rc != 0:
+                        raise RuntimeError(f"sgs_deform_pack_general failed ({rc}): {_lib.last_error()}")
+        self.versions = cur
+
+
+def _time_embedding(d):
+    """get_embedder(4) on d [N,1] (saro_gaussian.py:922-969): [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d]"""
+    cols = [d]
+    for f in (1.0, 2.0, 4.0, 8.0):
+        cols += [torch.sin(d * f), torch.cos(d * f)]
+    return torch.cat(cols, dim=1)
+
+
+class _TrainMLPs(torch.autograd.Function):
+    """All MLP evaluations of one get_deformation call: one tcgen05 launch forward, one for the data-gradient chains.
+    jobs: tuple of (mlp index, zero_time, differentiable).  Returns one raw output [N, n_out] per job."""
+
+    @staticmethod
+    def forward(ctx, feat, tpos, timestamp, jobs, images, *params):
+        lib = _lib.load()
+        images.refresh(params)
+        n, F = feat.shape[0], images.feat_dim
+        dev = feat.device
+        feat_c = _check(feat, "hexplane feature", [(F,)], n)
+        tpos_c = _check(tpos, "temporal_pos", [(1,), ()], n)
+        want = any(ctx.needs_input_grad)          # all False under no_grad: nothing is saved then
+        outs, keep = [], []
+        arr = (_lib.MLPJob * len(jobs))()
+        f32 = dict(dtype=torch.float32, device=dev)
+        for k, (m, zero_time, diff) in enumerate(jobs):
+            n_out = images.shapes[m][2]
+            out = torch.empty((n, n_out), **f32)
+            outs.append(out)
+            save = want and diff
+            h1 = torch.empty((n, HIDDEN), **f32) if save else None
+            h2 = torch.empty((n, HIDDEN), **f32) if save else None
+            m1 = torch.empty((n, 4), dtype=torch.int32, device=dev) if save else None
+            m2 = torch.empty((n, 4), dtype=torch.int32, device=dev) if save else None
+            keep.append((h1, h2, m1, m2))
+            p0 = lambda t: t.data_ptr() if t is not None else None
+            arr[k] = _lib.MLPJob(images.image(m, 0), None, out.data_ptr(), p0(h1), p0(h2), p0(m1), p0(m2), n_out, int(zero_time))
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = lib.sgs_deform_train_forward(n, F, float(timestamp), tpos_c.data_ptr(), feat_c.data_ptr(), len(jobs), arr,
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"sgs_deform_train_forward failed ({rc}): {_lib.last_error()}")
+        ctx.jobs, ctx.images, ctx.keep, ctx.timestamp = jobs, images, keep, float(timestamp)
+        ctx.save_for_backward(feat_c, tpos_c, *params)
+        ctx.mark_non_differentiable(*[o for o, (_, _, diff) in zip(outs, jobs) if not diff])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        feat, tpos, *params = ctx.saved_tensors
+        jobs, images, keep = ctx.jobs, ctx.images, ctx.keep
+        n, F = feat.shape
+        dev = feat.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        live = [k for k, (m, z, diff) in enumerate(jobs) if diff and gouts[k] is not None and keep[k][0] is not None]
+        grads = [None] * len(params)
+        if not live or n == 0:
+            return (torch.zeros_like(feat) if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
+        arr = (_lib.MLPJob * len(live))()
+        slabs = torch.empty((len(live), n, F), **f32)
+        work = []
+        for i, k in enumerate(live):
+            m, zero_time, _ = jobs[k]
+            h1, h2, m1, m2 = keep[k]
+            dy = gouts[k].contiguous()
+            dh2 = torch.empty((n, HIDDEN), **f32)
+            dh1 = torch.empty((n, HIDDEN), **f32)
+            work.append((m, zero_time, dy, h1, h2, dh1, dh2))
+            arr[i] = _lib.MLPJob(images.image(m, 1), dy.data_ptr(), slabs[i].data_ptr(), dh2.data_ptr(), dh1.data_ptr(),
+                                 m2.data_ptr(), m1.data_ptr(), dy.shape[1], 0)
+        with torch.cuda.device(dev):
+            rc = lib.sgs_deform_train_backward(n, F, len(live), arr, torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"sgs_deform_train_backward failed ({rc}): {_lib.last_error()}")
+        dfeat = slabs.sum(dim=0) if len(live) > 1 else slabs[0]
+        # weight gradients: plain GEMMs over the saved operands (dW = dH^T X), summed over the jobs that share an MLP
+        emb = {}
+        for m, zero_time, dy, h1, h2, dh1, dh2 in work:
+            w_in, hid2, n_out = images.shapes[m]
+            if w_in == F:
+                x = feat
+            else:
+                if zero_time not in emb:
+                    d = torch.zeros((n, 1), **f32) if zero_time else (ctx.timestamp - tpos.reshape(n, 1))
+                    emb[zero_time] = torch.cat([feat, _time_embedding(d)], dim=1)
+                x = emb[zero_time]
+            parts = (dh1.t() @ x, dh1.sum(0), dh2[:, :hid2].t() @ h1, dh2[:, :hid2].sum(0), dy.t() @ h2[:, :hid2], dy.sum(0))
+            for q, g in enumerate(parts):
+                idx = 6 * m + q
+                if ctx.needs_input_grad[5 + idx]:
+                    grads[idx] = g if grads[idx] is None else grads[idx] + g
+        ctx.keep = None
+        return (dfeat if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
+
+
+def get_deformation(self, timestamp, rays=None):
+    """Drop-in for GaussianModel.get_deformation (scene/saro_gaussian.py:779-847): same side effects (`_lifespan`,
+    `scale_residual`, `shs_residual`, `motion_residual`, `real_xyz`), same return order.  The plane field is whatever
+    module the model carries (`saro_gs_b200.hexplane.ScaleAwareResField` for the native sampler); the seven MLP
+    evaluations and their backward run in the tcgen05 kernels of csrc/sgs_deform.cu; the residual adds and activations
+    are the reference's own elementwise statements."""
+    args = self.args
+    if not (args.dx and args.drot and args.dopacity and args.dsh):
+        raise UnsupportedDeformationConfig(
+            "the fused training path implements the configuration all shipped configs use (dx, drot, dopacity, dsh all on); "
+            f"got dx={args.dx} drot={args.drot} dopacity={args.dopacity} dsh={args.dsh}")
+    if not self._xyz.is_cuda:
+        raise RuntimeError("get_deformation: the model must live on a CUDA device (there is no CPU path)")
+    cache = getattr(self, "_sgs_train_cache", None)
+    key = tuple(id(getattr(self, k)) for k in _TRAIN_MLPS)
+    if cache is None or cache["key"] != key:
+        cache = {"key": key, "images": TrainImages(*[getattr(self, k) for k in _TRAIN_MLPS])}
+        self._sgs_train_cache = cache
+    images = cache["images"]
+
+    hexplane_feature = self.hexplane(self._xyz.detach(), self.get_temporalpos.detach(), self.get_scaling.detach())   # :780
+    jobs = [(3, True, True), (0, False, True), (1, False, True), (2, False, True)]       # lifespan, motion, rot, shs at t
+    names = ["life", "motion", "rot", "shs"]
+    if args.scale_reg:                                                                    # :796-797
+        jobs.append((1, True, True)); names.append("rot_base")
+    if args.shs_reg:                                                                      # :798-799
+        jobs.append((2, True, True)); names.append("shs_base")
+    jobs.append((0, True, bool(args.motion_reg))); names.append("motion_base")            # :800-804
+    outs = dict(zip(names, _TrainMLPs.apply(hexplane_feature, self.get_temporalpos.detach(), timestamp, tuple(jobs), images,
+                                            *images.params())))
+
+    lifespan = 1 - torch.sigmoid(outs["life"])                                            # :782 (opacity_mlp ends in Sigmoid)
+    min_scale = self.args.min_interval / (self.duration)
+    lifespan = (1 - min_scale) * lifespan + min_scale
+    self._lifespan = lifespan
+    distance = timestamp - self.get_temporalpos                                           # :788
+    trbfoutput = self.get_survival_state(distance / lifespan)
+    if args.scale_reg:
+        self.scale_residual = outs["rot_base"][:, 4:]
+    if args.shs_reg:
+        self.shs_residual = outs["shs_base"].reshape(-1, 16, 3)
+    if args.motion_reg:
+        self.motion_residual = outs["motion_base"]
+    with torch.no_grad():
+        self.real_xyz = self._xyz + outs["motion_base"].detach()                          # :803-804
+    motion = self._xyz + outs["motion"]                                                   # :807-809
+    rot_residual = outs["rot"]
+    rot = self.rotation_activation(self._rotation + rot_residual[:, :4])                  # :813-817
+    scale = self.scaling_activation(self._scaling + rot_residual[:, 4:])                  # :819-821
+    opacity = self.opacity_activation(self._opacity) * trbfoutput                         # :830-831
+    shs = torch.cat((self._features_dc, self._features_rest), dim=1) + outs["shs"].reshape(-1, 16, 3)   # :837-841
+    return motion, rot, scale, opacity, shs
