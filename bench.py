@@ -461,6 +461,7 @@ def run_native_or_ref(args, impl):
             with contextlib.redirect_stdout(sys.stderr):     # stdout carries exactly one JSON line
                 line["loss_path"] = loss_path_timing(dev, H, W)
                 line["deform_path"] = deform_path_timing(dev)
+                line["deform_train_path"] = deform_train_path_timing(dev)
                 line["densify_path"] = densify_path_timing(dev)
                 line["plane_path"] = plane_path_timing(dev)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -579,6 +580,64 @@ def deform_path_timing(dev, iters=15):
         out["test_time_frame_ms"]["reference_ops_and_rasterizer"] = frame_ref
         out["test_time_frame_ms"]["speedup"] = frame_ref / frame_native
     return out
+
+
+def deform_train_path_timing(dev, N=300_000, iters=8):
+    """SURVEY.md section 8(f) rank 1, training half: GaussianModel.get_deformation (scene/saro_gaussian.py:779-847) forward
+    + backward on the headline cloud with the N3D configuration's flags (scale_reg on: six MLP evaluations per view,
+    five of them differentiated), native tcgen05 job kernels vs the same function as the float32 PyTorch ops SaRO-GS
+    runs.  The plane field is a resident feature table on both sides (the sampler has its own leg, plane_path).
+    CUDA events, inputs resident."""
+    from saro_gs_b200 import deformation
+    from oracle import deform_torch
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    t = dict(xyz=rn(N, 3) * 2, rotation=rn(N, 4), scaling=rn(N, 3) * 0.5 - 3.5, opacity=rn(N, 1) * 2, features_dc=rn(N, 1, 3) * 0.5,
+             features_rest=rn(N, 15, 3) * 0.1, temporal_pos=torch.rand(N, 1, generator=g), hexplane_feature=rn(N, 32) * 0.5)
+    leaves = {k: v.to(dev).requires_grad_(True) for k, v in t.items()}
+    mlps = deform_torch.make_train_mlps(32, device=dev, seed=6)
+    pc = deform_torch.TrainModelStandIn(leaves, mlps, (1, 0, 0), 6.0, 300.0)
+    w = [rn(N, 3).to(dev), rn(N, 4).to(dev), (rn(N, 3) * 20).to(dev), rn(N, 1).to(dev), rn(N, 16, 3).to(dev)]
+    params = [p for m in mlps.values() for p in m.parameters()] + list(leaves.values())
+
+    def run(fn, steps, marks=None):
+        f_ms, b_ms, phases = [], [], {}
+        for i in range(steps + 2):
+            for p in params:
+                p.grad = None
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            deformation._phase_marks = [] if marks else None
+            e0.record()
+            outs = fn(pc, 0.35 + 0.05 * (i - steps - 1))      # both arms end on the same timestamp
+            loss = deform_torch.train_objective(pc, outs, w, (8e-6, 0.0, 0.0))
+            e1.record()
+            loss.backward()
+            e2.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                f_ms.append(e0.elapsed_time(e1))
+                b_ms.append(e1.elapsed_time(e2))
+                ms = deformation._phase_marks or []
+                for (_, a), (name, b) in zip(ms, ms[1:]):
+                    phases[name] = phases.get(name, 0.0) + a.elapsed_time(b) / steps
+        deformation._phase_marks = None
+        grads = {i: p.grad.detach().clone() for i, p in enumerate(params) if p.grad is not None}
+        return sum(f_ms) / len(f_ms), sum(b_ms) / len(b_ms), phases, grads
+
+    nf, nb, phases, g_n = run(deformation.get_deformation, iters, marks=True)
+    tf, tb, _, g_t = run(deform_torch.torch_get_deformation, 3)
+    agree = max(float((g_n[i] - g_t[i]).abs().max() / g_t[i].abs().max().clamp_min(1e-30)) for i in g_t)
+    flops = N * 2 * (5 * (41 * 128 + 128 * 128) + 128 * (1 + 3 + 7 + 48 + 7)) + N * 2 * 128 * 3
+    return {"what": "get_deformation forward + backward on %d Gaussians (scale_reg on: lifespan, motion, rot, shs at t, rot and "
+                    "motion at the base feature), objective = weighted outputs + scale regulariser" % N,
+            "native_forward_ms": nf, "native_backward_ms": nb, "pytorch_ops_forward_ms": tf, "pytorch_ops_backward_ms": tb,
+            "speedup_forward": tf / nf, "speedup_backward": tb / nb, "speedup_total": (tf + tb) / (nf + nb),
+            "native_backward_phases_ms": phases, "forward_mlp_GFLOP": flops / 1e9,
+            "max_rel_diff_gradients_vs_pytorch_float32": agree,
+            "note": "forward = one tcgen05 launch for the six evaluations + the reference's elementwise epilogues; backward = "
+                    "autograd of those epilogues, one tcgen05 launch for the five data-gradient chains, weight gradients; "
+                    "gradient agreement on random rows is limited by ReLU kinks (tests/test_deform_train_gpu.py), not by "
+                    "arithmetic"}
 
 
 def plane_path_timing(dev, N=300_000, iters=10):

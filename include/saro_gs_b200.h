@@ -246,6 +246,24 @@ int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* 
                              const sgs_mlp_job_t* jobs, void* stream);
 int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream);
 
+/* Weight gradients of the training-time deformation: every task is one GEMM over the N rows,
+ *   D[m][n] = sum_r A[r][m] * B[r][n]   (m < 128, n < ldb)   and, with ones = 1,   D[m][ldb] = sum_r A[r][m]
+ * (A = dL/d pre-activation -> weight and bias gradient of that layer; for the last layer A = the hidden activation and
+ * B = dL/d out, giving the transposed weight gradient).  A: [N][128], B: [N][ldb] float32, ldb a multiple of 8, both
+ * 16-byte aligned.  The kernel writes one partial per CTA: `partials` holds sgs_deform_wgrad_max_ctas() blocks of
+ * sgs_deform_wgrad_partial_floats() floats ([128][144] row-major); task i's result is the sum of blocks
+ * cta_first[i] .. cta_first[i] + cta_count[i] - 1 (host arrays filled by the call).  Returns 0 or a negative error. */
+typedef struct sgs_wgrad_task {
+    const float* A;
+    const float* B;
+    int ldb;
+    int ones;
+} sgs_wgrad_task_t;
+int sgs_deform_wgrad_max_ctas(void);
+size_t sgs_deform_wgrad_partial_floats(void);
+int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, int* cta_first, int* cta_count,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Densification statistics of one training iteration — replaces the per-view lists and
  * the batch reduction of the reference's train.py:192-218 and :281-292 (with scene/saro_gaussian.py:745-747).

@@ -918,6 +918,194 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_train_kernel(cons
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradients of the training path: dW = G^T X summed over the N rows, for every (job, layer).  The batch row is
+// the GEMM's K dimension, and both operands sit in HBM row-major as float32 [row][feature] — exactly the MN-major
+// shared-memory operand form of tcgen05.mma (element (mn, k) at (mn % 8) * 2 + (mn / 8) * SBO + (k % 8) * 16 +
+// (k / 8) * 128 bytes; descriptor fields pinned on hardware by tools/microbench/umma_mn_probe.cu), so a thread that
+// loaded 8 consecutive features of a row stores them as ONE 16-byte row of a core matrix: no transposition anywhere.
+// Each CTA owns one task and a contiguous range of 64-row tiles: global float32 -> registers (next tile in flight) ->
+// bf16 hi / lo planes in a two-stage shared-memory ring -> 12 MMAs per tile (hi*hi + hi*lo + lo*hi, f32 accumulate in
+// TMEM across the whole range) -> the CTA's partial [128][N] to global; the host adds the few partials of a task.
+// Bias gradients ride along as a constant-one column of the B operand.  HBM-bound: every operand element is read once.
+constexpr int WG_KT = 64;                       // batch rows per ring stage (4 MMA K-steps)
+constexpr int WG_THREADS = 256;
+constexpr int WG_MAX_TASKS = 24;
+constexpr int WG_NG_MAX = 18;                   // B column groups of 8: 16 real + the ones group, N = 144
+constexpr int WG_A_PLANE = 16 * WG_KT * 16;     // 16 KB: 128 features x 64 rows x bf16
+constexpr int WG_B_PLANE = WG_NG_MAX * WG_KT * 16;
+constexpr int WG_STAGE_BYTES = 2 * WG_A_PLANE + 2 * WG_B_PLANE;       // 69 632
+constexpr int WG_SMEM_BYTES = 2 * WG_STAGE_BYTES + 64;
+constexpr int WG_OUT_STRIDE = WG_NG_MAX * 8;    // floats per row of a partial
+
+struct WTask {
+    const float* A;          // [N][128] float32: becomes the M dimension
+    const float* B;          // [N][ldb] float32, ldb a multiple of 8
+    float* partial;          // [cta_count][128][WG_OUT_STRIDE]
+    int ldb;
+    int ngroups;             // B column groups the MMA covers (even): ldb / 8 real ones, then constants
+    int ones_group;          // index of the group whose column 0 is the constant 1 (bias gradient), or -1
+    int cta_first, cta_count;
+};
+struct WParams {
+    int N, n_tasks;
+    WTask tasks[WG_MAX_TASKS];
+};
+
+__device__ __forceinline__ void wg_split8(const float4& u, const float4& w, uint4& hi, uint4& lo) {
+    const float2 v[4] = {make_float2(u.x, u.y), make_float2(u.z, u.w), make_float2(w.x, w.y), make_float2(w.z, w.w)};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __float22bfloat162_rn(v[i]);
+        const float2 rest = __ffma2_rn(__bfloat1622float2(hh), make_float2(-1.f, -1.f), v[i]);
+        const __nv_bfloat162 ll = __float22bfloat162_rn(rest);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __grid_constant__ WParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + 2 * WG_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int ti = 0;
+    while (ti + 1 < p.n_tasks && (int)blockIdx.x >= p.tasks[ti].cta_first + p.tasks[ti].cta_count) ++ti;
+    const WTask& task = p.tasks[ti];
+    const int local = (int)blockIdx.x - task.cta_first;
+    const int tiles = (p.N + WG_KT - 1) / WG_KT;
+    const int t0 = (int)((long long)tiles * local / task.cta_count), t1 = (int)((long long)tiles * (local + 1) / task.cta_count);
+    const int real_groups = task.ldb >> 3;
+    const int nmma = task.ngroups * 8;
+
+    // constant column groups of B (zero padding, the ones column): written once per stage
+    for (int s = 0; s < 2; ++s) {
+        uint8_t* st = smem + s * WG_STAGE_BYTES + 2 * WG_A_PLANE;
+        for (int u = tid; u < (task.ngroups - real_groups) * WG_KT; u += WG_THREADS) {
+            const int g = real_groups + u / WG_KT, k = u % WG_KT;
+            const uint32_t one = g == task.ones_group ? 0x3F80u : 0u;          // bf16(1.0) in element 0
+            const uint32_t off = g * (WG_KT * 16) + (k >> 3) * 128 + (k & 7) * 16;
+            *reinterpret_cast<uint4*>(st + off) = make_uint4(one, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(st + WG_B_PLANE + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + 1)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    // load units: (row k of the tile, group g of 8 features).  Within a warp the 8 rows of a k-block vary fastest and 4
+    // groups next, so each quarter-warp of a 16-byte shared store covers one contiguous 128-byte core matrix.
+    const int k_in = lane & 7, g_in = lane >> 3;
+    const int kb = warp;                                    // 8 warps = the 8 k-blocks of a tile; i = quad of groups
+    float4 ra[4][2], rb[4][2];
+    auto load_tile = [&](int t) {
+        const int row = t * WG_KT + kb * 8 + k_in;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = i * 4 + g_in;
+            if (row < p.N) {
+                const float4* src = reinterpret_cast<const float4*>(task.A + (size_t)row * 128 + g * 8);
+                ra[i][0] = __ldg(src); ra[i][1] = __ldg(src + 1);
+            } else { ra[i][0] = ra[i][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            if (g < real_groups && row < p.N) {
+                const float4* src = reinterpret_cast<const float4*>(task.B + (size_t)row * task.ldb + g * 8);
+                rb[i][0] = __ldg(src); rb[i][1] = __ldg(src + 1);
+            } else { rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+    };
+    auto store_tile = [&](int s) {
+        uint8_t* st = smem + s * WG_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = i * 4 + g_in;
+            const uint32_t off = g * (WG_KT * 16) + kb * 128 + k_in * 16;
+            uint4 hi, lo;
+            wg_split8(ra[i][0], ra[i][1], hi, lo);
+            *reinterpret_cast<uint4*>(st + off) = hi;
+            *reinterpret_cast<uint4*>(st + WG_A_PLANE + off) = lo;
+            if (g < real_groups) {
+                wg_split8(rb[i][0], rb[i][1], hi, lo);
+                *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + off) = hi;
+                *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + WG_B_PLANE + off) = lo;
+            }
+        }
+    };
+
+    // D = f32, A = B = bf16, both MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) | ((128u >> 4) << 24);
+    if (t0 < t1) load_tile(t0);
+    uint32_t ph[2] = {0u, 0u};
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        const int s = (t - t0) & 1;
+        if (t - t0 >= 2) { mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }      // the MMAs that read this stage are done
+        store_tile(s);
+        if (t + 1 < t1) load_tile(t + 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES), a_lo = a_hi + WG_A_PLANE;
+            const uint32_t b_hi = a_hi + 2 * WG_A_PLANE, b_lo = b_hi + WG_B_PLANE;
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+                const uint32_t a = prod == 2 ? a_lo : a_hi, b = prod == 1 ? b_lo : b_hi;
+#pragma unroll
+                for (int ks = 0; ks < WG_KT / 16; ++ks) {
+                    const uint64_t da = (uint64_t)(((a + ks * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+                                        ((uint64_t)((WG_KT * 16) >> 4) << 32) | ((uint64_t)1 << 46);
+                    const uint64_t db = (uint64_t)(((b + ks * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+                                        ((uint64_t)((WG_KT * 16) >> 4) << 32) | ((uint64_t)1 << 46);
+                    const uint32_t acc = (t > t0 || prod > 0 || ks > 0) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred pe, pa;\n\tsetp.ne.b32 pa, %4, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+                                 :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                }
+            }
+            asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                         :: "r"(smem_u32(mbar_p + s)) : "memory");
+            __syncwarp();
+        }
+    }
+    // drain: every stage's outstanding commit (MMAs complete in order, but both barriers must be consumed before exit)
+    const int n_t = t1 - t0;
+    if (n_t >= 2) { const int s = (n_t - 2) & 1; mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }
+    if (n_t >= 1) { const int s = (n_t - 1) & 1; mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // partial [128][N]: warp w reads TMEM lanes 32 (w % 4) ..., the two warps of a lane quarter split the columns
+    float* out = task.partial + (size_t)local * 128 * WG_OUT_STRIDE + (size_t)((warp & 3) * 32 + lane) * WG_OUT_STRIDE;
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = (warp >> 2) * 8; c0 < nmma; c0 += 16) {
+        float v[8];
+        if (n_t > 0) tmem_ld8(t_row + c0, v);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        reinterpret_cast<float4*>(out + c0)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(out + c0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u));
+}
+
 std::mutex g_mu;
 int* g_pinned_count = nullptr;
 cudaEvent_t g_count_ready = nullptr;
@@ -1135,6 +1323,74 @@ int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* 
 
 int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream) {
     return sgs_deform_train_launch(true, N, feat_dim, 0.f, nullptr, nullptr, n_jobs, jobs, stream);
+}
+
+
+int sgs_deform_wgrad_max_ctas(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return sms > 0 ? sms : 148;
+}
+
+size_t sgs_deform_wgrad_partial_floats(void) { return (size_t)128 * sgs_deform::WG_OUT_STRIDE; }
+
+int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, int* cta_first, int* cta_count,
+                     void* stream) {
+    using namespace sgs_deform;
+    if (N <= 0 || n_tasks <= 0 || n_tasks > WG_MAX_TASKS || !tasks || !partials || !cta_first || !cta_count)
+        return SGS_ERR_INVALID_ARGUMENT;
+    static bool attr_set = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(deform_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES) != cudaSuccess)
+                return SGS_ERR_CUDA;
+            attr_set = true;
+        }
+    }
+    const int tiles = (N + WG_KT - 1) / WG_KT;
+    int grid = sgs_deform_wgrad_max_ctas();
+    if (grid < n_tasks) return SGS_ERR_INVALID_ARGUMENT;
+    if ((long long)grid > (long long)n_tasks * tiles) grid = n_tasks * tiles;
+    WParams p;
+    p.N = N; p.n_tasks = n_tasks;
+    float cost[WG_MAX_TASKS], total = 0.f;
+    for (int i = 0; i < n_tasks; ++i) {
+        const sgs_wgrad_task_t& t = tasks[i];
+        if (!t.A || !t.B || t.ldb <= 0 || (t.ldb & 7) || t.ldb > 128 ||
+            ((reinterpret_cast<size_t>(t.A) | reinterpret_cast<size_t>(t.B)) & 15))
+            return SGS_ERR_INVALID_ARGUMENT;
+        WTask& w = p.tasks[i];
+        w.A = t.A; w.B = t.B; w.ldb = t.ldb;
+        const int real = t.ldb >> 3;
+        w.ones_group = t.ones ? real : -1;
+        w.ngroups = (real + (t.ones ? 1 : 0) + 1) & ~1;
+        cost[i] = 128.f + (float)t.ldb;
+        total += cost[i];
+    }
+    int given = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        int c = (int)(grid * (cost[i] / total));
+        if (c < 1) c = 1;
+        if (c > tiles) c = tiles;
+        p.tasks[i].cta_count = c;
+        given += c;
+    }
+    for (int i = 0, guard = 0; given < grid && guard < 4 * grid; i = (i + 1) % n_tasks, ++guard)
+        if (p.tasks[i].cta_count < tiles) { ++p.tasks[i].cta_count; ++given; }
+    for (int i = 0; given > grid; i = (i + 1) % n_tasks)
+        if (p.tasks[i].cta_count > 1) { --p.tasks[i].cta_count; --given; }
+    grid = given;
+    int first = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        p.tasks[i].cta_first = first;
+        p.tasks[i].partial = partials + (size_t)first * 128 * WG_OUT_STRIDE;
+        cta_first[i] = first;
+        cta_count[i] = p.tasks[i].cta_count;
+        first += p.tasks[i].cta_count;
+    }
+    deform_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
 }
 
 }  // extern "C"

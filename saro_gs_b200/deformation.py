@@ -11,6 +11,8 @@ and ``renderer/__init__.py:190`` runs on the fused tcgen05 kernel unchanged.  Al
 memory and the current stream only.  There is no PyTorch fallback: CPU tensors, other dtypes or an unsupported
 configuration raise.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -251,6 +253,16 @@ def _time_embedding(d):
     return torch.cat(cols, dim=1)
 
 
+_phase_marks = None      # bench.py sets this to a list to collect (name, CUDA event) marks of the backward's phases
+
+
+def _mark(name):
+    if _phase_marks is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _phase_marks.append((name, e))
+
+
 class _TrainMLPs(torch.autograd.Function):
     """All MLP evaluations of one get_deformation call: one tcgen05 launch forward, one for the data-gradient chains.
     jobs: tuple of (mlp index, zero_time, differentiable).  Returns one raw output [N, n_out] per job."""
@@ -302,6 +314,7 @@ class _TrainMLPs(torch.autograd.Function):
         grads = [None] * len(params)
         if not live or n == 0:
             return (torch.zeros_like(feat) if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
+        _mark("bwd_begin")
         arr = (_lib.MLPJob * len(live))()
         slabs = torch.empty((len(live), n, F), **f32)
         work = []
@@ -318,23 +331,47 @@ class _TrainMLPs(torch.autograd.Function):
             rc = lib.sgs_deform_train_backward(n, F, len(live), arr, torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"sgs_deform_train_backward failed ({rc}): {_lib.last_error()}")
+        _mark("data_gradient_kernel")
         dfeat = slabs.sum(dim=0) if len(live) > 1 else slabs[0]
-        # weight gradients: plain GEMMs over the saved operands (dW = dH^T X), summed over the jobs that share an MLP
-        emb = {}
+        # weight gradients: one tcgen05 launch for all (job, layer) GEMMs dW = G^T X over the rows; bias gradients ride
+        # along as a constant-one column.  The per-CTA partials of a task are added here, and jobs that share an MLP
+        # (the evaluation at t and the one at the base feature) are summed.
+        xs = {}
+        tasks, spec = [], []
         for m, zero_time, dy, h1, h2, dh1, dh2 in work:
             w_in, hid2, n_out = images.shapes[m]
-            if w_in == F:
-                x = feat
-            else:
-                if zero_time not in emb:
+            key = "feat" if w_in == F else zero_time
+            if key not in xs:
+                if w_in == F:
+                    cols = [feat]
+                else:
                     d = torch.zeros((n, 1), **f32) if zero_time else (ctx.timestamp - tpos.reshape(n, 1))
-                    emb[zero_time] = torch.cat([feat, _time_embedding(d)], dim=1)
-                x = emb[zero_time]
-            parts = (dh1.t() @ x, dh1.sum(0), dh2[:, :hid2].t() @ h1, dh2[:, :hid2].sum(0), dy.t() @ h2[:, :hid2], dy.sum(0))
+                    cols = [feat, _time_embedding(d)]
+                cols.append(torch.zeros((n, 48 - sum(c.shape[1] for c in cols)), **f32))
+                xs[key] = torch.cat(cols, dim=1)
+            dyp = dy if n_out == 48 else torch.nn.functional.pad(dy, (0, 8 - n_out))
+            tasks += [(dh1, xs[key], 48, 1), (dh2, h1, HIDDEN, 1), (h2, dyp, dyp.shape[1], 0)]
+            spec.append((m, w_in, hid2, n_out, dy))
+        arr_w = (_lib.WgradTask * len(tasks))()
+        for i, (a, b, ldb, ones) in enumerate(tasks):
+            arr_w[i] = _lib.WgradTask(a.data_ptr(), b.data_ptr(), ldb, ones)
+        per = lib.sgs_deform_wgrad_partial_floats()
+        partials = torch.empty((lib.sgs_deform_wgrad_max_ctas(), 128, per // 128), **f32)
+        first = (ctypes.c_int * len(tasks))()
+        count = (ctypes.c_int * len(tasks))()
+        with torch.cuda.device(dev):
+            rc = lib.sgs_deform_wgrad(n, len(tasks), arr_w, partials.data_ptr(), first, count,
+                                      torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"sgs_deform_wgrad failed ({rc}): {_lib.last_error()}")
+        for j, (m, w_in, hid2, n_out, dy) in enumerate(spec):
+            D1, D2, D3 = (partials[first[3 * j + q]:first[3 * j + q] + count[3 * j + q]].sum(0) for q in range(3))
+            parts = (D1[:, :w_in], D1[:, 48], D2[:hid2, :HIDDEN], D2[:hid2, HIDDEN], D3[:hid2, :n_out].t(), dy.sum(0))
             for q, g in enumerate(parts):
                 idx = 6 * m + q
                 if ctx.needs_input_grad[5 + idx]:
                     grads[idx] = g if grads[idx] is None else grads[idx] + g
+        _mark("weight_gradients")
         ctx.keep = None
         return (dfeat if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
