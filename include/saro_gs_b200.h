@@ -227,7 +227,8 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
  * sgs_deform_train_backward: per job, in = dL/d out [N][n_io]; out = dL/d feature [N][feat_dim] of this job (the
  *   caller sums the jobs); mask_a = the forward's LAYER-2 bits, mask_b = its LAYER-1 bits; save_a / save_b receive
  *   dL/d(pre-activation) of layer 2 / layer 1 as float32 [N][128] (operands of the weight-gradient GEMMs).
- * All pointers are device memory, 16-byte aligned.  Return 0 or a negative error code. */
+ * All pointers are device memory, 16-byte aligned; save_a / save_b, the backward's out and 48-wide forward outs 32-byte
+ * aligned (256-bit stores).  Return 0 or a negative error code. */
 typedef struct sgs_mlp_job {
     const void* packed;
     const float* in;
@@ -247,22 +248,31 @@ int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* 
 int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream);
 
 /* Weight gradients of the training-time deformation: every task is one GEMM over the N rows,
- *   D[m][n] = sum_r A[r][m] * B[r][n]   (m < 128, n < ldb)   and, with ones = 1,   D[m][ldb] = sum_r A[r][m]
- * (A = dL/d pre-activation -> weight and bias gradient of that layer; for the last layer A = the hidden activation and
- * B = dL/d out, giving the transposed weight gradient).  A: [N][128], B: [N][ldb] float32, ldb a multiple of 8, both
- * 16-byte aligned.  The kernel writes one partial per CTA: `partials` holds sgs_deform_wgrad_max_ctas() blocks of
- * sgs_deform_wgrad_partial_floats() floats ([128][144] row-major); task i's result is the sum of blocks
- * cta_first[i] .. cta_first[i] + cta_count[i] - 1 (host arrays filled by the call).  Returns 0 or a negative error. */
+ *   D[m][n] = sum_r A[r][m] * B[r][n]   (m < 128)   and, when db is given,   db[m] = sum_r A[r][m],
+ * written as dW[m][n] (row stride ldw; m < rows, n < cols) or, with transposed = 1, dW[n][m] (the last layer: A = the
+ * hidden activation, B = dL/d out).  A: [N][128] float32; B: [N][ldb] float32, ldb a multiple of 8 (time_mode 0), or the
+ * plane feature [N][feat_dim] from which the MLP input [feature | time embedding of d | 0] is rebuilt on the fly
+ * (time_mode 1: d = timestamp - temporal_pos[row]; 2: d = 0).  accumulate = 1 adds to dW / db (the second evaluation of
+ * an MLP in the same call) instead of overwriting.  `partials`: scratch of sgs_deform_wgrad_max_ctas() x
+ * sgs_deform_wgrad_partial_floats() floats.  All pointers device memory; A and B 32-byte aligned (256-bit loads).  One GEMM launch + one or
+ * two reduction launches on `stream`; deterministic (fixed summation order).  Returns 0 or a negative error code. */
 typedef struct sgs_wgrad_task {
     const float* A;
     const float* B;
     int ldb;
-    int ones;
+    int time_mode;
+    float* dW;
+    int ldw;
+    int rows;
+    int cols;
+    int transposed;
+    float* db;
+    int accumulate;
 } sgs_wgrad_task_t;
 int sgs_deform_wgrad_max_ctas(void);
 size_t sgs_deform_wgrad_partial_floats(void);
-int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, int* cta_first, int* cta_count,
-                     void* stream);
+int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal_pos, int n_tasks, const sgs_wgrad_task_t* tasks,
+                     float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Densification statistics of one training iteration — replaces the per-view lists and

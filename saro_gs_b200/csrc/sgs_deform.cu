@@ -668,6 +668,17 @@ __global__ void pack_general_kernel(int backward, int in_w, int hid2, int n_out,
     }
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per thread and instruction — a thread
+// that owns 8 consecutive floats of a row moves them in one request instead of two half-sector ones
+__device__ __forceinline__ void st_global_v8(float* dst, const float2 (&x)[4]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(dst), "f"(x[0].x), "f"(x[0].y), "f"(x[1].x), "f"(x[1].y),
+                 "f"(x[2].x), "f"(x[2].y), "f"(x[3].x), "f"(x[3].y) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* src, float4& u, float4& w) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w), "=f"(w.x),
+                 "=f"(w.y), "=f"(w.z), "=f"(w.w) : "l"(src));
+}
+
 // hidden layer epilogue of the training kernels.  Forward: + bias, ReLU, sign bits out.  Backward: multiply by the
 // saved sign bits.  Both: next layer's TMEM operand, optional float32 copy of the row for the weight-gradient kernel.
 template <bool BWD>
@@ -701,11 +712,7 @@ __device__ __forceinline__ void hidden_epilogue_train(uint32_t t_acc, uint32_t t
                 }
             }
             store_chunk(t_hi, t_lo, c0 / 8 + h, x);
-            if (save_row != nullptr && valid) {
-                float4* dst = reinterpret_cast<float4*>(save_row + c0 + h * 8);
-                dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
-                dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
-            }
+            if (save_row != nullptr && valid) st_global_v8(save_row + c0 + h * 8, x);
         }
     }
     if (!BWD && mask_slot != nullptr && valid) *mask_slot = make_uint2(mw[0], mw[1]);
@@ -860,10 +867,10 @@ __device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& 
                 tmem_ld8(t_acc + N3P + half * PER + c0, r2);
                 const int col = half * PER + c0;
                 if (valid && col < width) {
-                    float4* dst = reinterpret_cast<float4*>(job.out + jr * width + col);
                     const float* bb = b3 + col;
-                    dst[0] = make_float4((r[0] + r2[0]) + bb[0], (r[1] + r2[1]) + bb[1], (r[2] + r2[2]) + bb[2], (r[3] + r2[3]) + bb[3]);
-                    dst[1] = make_float4((r[4] + r2[4]) + bb[4], (r[5] + r2[5]) + bb[5], (r[6] + r2[6]) + bb[6], (r[7] + r2[7]) + bb[7]);
+                    const float2 y[4] = {make_float2((r[0] + r2[0]) + bb[0], (r[1] + r2[1]) + bb[1]), make_float2((r[2] + r2[2]) + bb[2], (r[3] + r2[3]) + bb[3]),
+                                         make_float2((r[4] + r2[4]) + bb[4], (r[5] + r2[5]) + bb[5]), make_float2((r[6] + r2[6]) + bb[6], (r[7] + r2[7]) + bb[7])};
+                    st_global_v8(job.out + jr * width + col, y);
                 }
             }
         }
@@ -929,22 +936,28 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_train_kernel(cons
 // bf16 hi / lo planes in a two-stage shared-memory ring -> 12 MMAs per tile (hi*hi + hi*lo + lo*hi, f32 accumulate in
 // TMEM across the whole range) -> the CTA's partial [128][N] to global; the host adds the few partials of a task.
 // Bias gradients ride along as a constant-one column of the B operand.  HBM-bound: every operand element is read once.
-constexpr int WG_KT = 64;                       // batch rows per ring stage (4 MMA K-steps)
+constexpr int WG_KT = 32;                       // batch rows per ring stage (2 MMA K-steps)
+constexpr int WG_STAGES = 3;
 constexpr int WG_THREADS = 256;
+constexpr int WG_CTAS_PER_SM = 2;               // 512 TMEM columns / 256; 3 x 34 KB of shared memory each
 constexpr int WG_MAX_TASKS = 24;
 constexpr int WG_NG_MAX = 18;                   // B column groups of 8: 16 real + the ones group, N = 144
-constexpr int WG_A_PLANE = 16 * WG_KT * 16;     // 16 KB: 128 features x 64 rows x bf16
+constexpr int WG_A_PLANE = 16 * WG_KT * 16;     // 8 KB: 128 features x 32 rows x bf16
 constexpr int WG_B_PLANE = WG_NG_MAX * WG_KT * 16;
-constexpr int WG_STAGE_BYTES = 2 * WG_A_PLANE + 2 * WG_B_PLANE;       // 69 632
-constexpr int WG_SMEM_BYTES = 2 * WG_STAGE_BYTES + 64;
+constexpr int WG_STAGE_BYTES = 2 * WG_A_PLANE + 2 * WG_B_PLANE;       // 34 816
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 64;
 constexpr int WG_OUT_STRIDE = WG_NG_MAX * 8;    // floats per row of a partial
 
 struct WTask {
     const float* A;          // [N][128] float32: becomes the M dimension
     const float* B;          // [N][ldb] float32, ldb a multiple of 8
+    const float* tpos;       // time mode (B = plane feature rows): the MLP input [feature | embedding(d) | 0] is rebuilt on the fly
+    float timestamp;
+    int time_mode;           // 0 plain, 1 d = timestamp - tpos[row], 2 d = 0
     float* partial;          // [cta_count][128][WG_OUT_STRIDE]
     int ldb;
-    int ngroups;             // B column groups the MMA covers (even): ldb / 8 real ones, then constants
+    int real_groups;         // column groups filled per tile (ldb / 8, + 2 in time mode)
+    int ngroups;             // B column groups the MMA covers (even): the real ones, then constants
     int ones_group;          // index of the group whose column 0 is the constant 1 (bias gradient), or -1
     int cta_first, cta_count;
 };
@@ -968,10 +981,10 @@ __device__ __forceinline__ void wg_split8(const float4& u, const float4& w, uint
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __grid_constant__ WParams p) {
+__global__ void __launch_bounds__(WG_THREADS, WG_CTAS_PER_SM) deform_wgrad_kernel(const __grid_constant__ WParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + 2 * WG_STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + 2);
+    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + WG_STAGES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int ti = 0;
     while (ti + 1 < p.n_tasks && (int)blockIdx.x >= p.tasks[ti].cta_first + p.tasks[ti].cta_count) ++ti;
@@ -979,11 +992,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
     const int local = (int)blockIdx.x - task.cta_first;
     const int tiles = (p.N + WG_KT - 1) / WG_KT;
     const int t0 = (int)((long long)tiles * local / task.cta_count), t1 = (int)((long long)tiles * (local + 1) / task.cta_count);
-    const int real_groups = task.ldb >> 3;
+    const int real_groups = task.real_groups, data_groups = task.ldb >> 3;
     const int nmma = task.ngroups * 8;
 
     // constant column groups of B (zero padding, the ones column): written once per stage
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < WG_STAGES; ++s) {
         uint8_t* st = smem + s * WG_STAGE_BYTES + 2 * WG_A_PLANE;
         for (int u = tid; u < (task.ngroups - real_groups) * WG_KT; u += WG_THREADS) {
             const int g = real_groups + u / WG_KT, k = u % WG_KT;
@@ -998,8 +1011,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p)), "r"(1u));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + 1)), "r"(1u));
+        for (int s = 0; s < WG_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + s)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1009,36 +1022,55 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
 
     // load units: (row k of the tile, group g of 8 features).  Within a warp the 8 rows of a k-block vary fastest and 4
     // groups next, so each quarter-warp of a 16-byte shared store covers one contiguous 128-byte core matrix.
+    // 8 warps = 4 k-blocks x 2 halves of the group quads; i picks the quad within the half.
     const int k_in = lane & 7, g_in = lane >> 3;
-    const int kb = warp;                                    // 8 warps = the 8 k-blocks of a tile; i = quad of groups
-    float4 ra[4][2], rb[4][2];
-    auto load_tile = [&](int t) {
+    const int kb = warp & 3, qh = warp >> 2;
+    // two register sets: the loads of tiles t + 1 and t + 2 are in flight while tile t is converted (the kernel is bound
+    // by HBM latency, not by issue or by the tensor core: ~150 instructions and 6 MMAs per thread and tile)
+    float4 ra0[2][2], rb0[2][2], ra1[2][2], rb1[2][2];
+    auto load_tile = [&](int t, float4 (&ra)[2][2], float4 (&rb)[2][2]) {
         const int row = t * WG_KT + kb * 8 + k_in;
+        const bool in = row < p.N;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = i * 4 + g_in;
-            if (row < p.N) {
-                const float4* src = reinterpret_cast<const float4*>(task.A + (size_t)row * 128 + g * 8);
-                ra[i][0] = __ldg(src); ra[i][1] = __ldg(src + 1);
-            } else { ra[i][0] = ra[i][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            if (g < real_groups && row < p.N) {
-                const float4* src = reinterpret_cast<const float4*>(task.B + (size_t)row * task.ldb + g * 8);
-                rb[i][0] = __ldg(src); rb[i][1] = __ldg(src + 1);
-            } else { rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int i = 0; i < 2; ++i) {
+            const int g = (qh + 2 * i) * 4 + g_in;
+            ra[i][0] = ra[i][1] = rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) {
+                ld_global_nc_v8(task.A + (size_t)row * 128 + g * 8, ra[i][0], ra[i][1]);
+                if (g < data_groups) ld_global_nc_v8(task.B + (size_t)row * task.ldb + g * 8, rb[i][0], rb[i][1]); else if (g < real_groups) {                 // time mode: the embedding columns (saro_gaussian.py:939-969)
+                    rb[i][0].x = task.time_mode == 1 ? __ldg(task.tpos + row) : 0.f;     // raw; expanded in store_tile
+                }
+            }
         }
     };
-    auto store_tile = [&](int s) {
+    auto store_tile = [&](int s, int t, const float4 (&ra)[2][2], const float4 (&rb)[2][2]) {
         uint8_t* st = smem + s * WG_STAGE_BYTES;
+        const bool in = t * WG_KT + kb * 8 + k_in < p.N;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = i * 4 + g_in;
+        for (int i = 0; i < 2; ++i) {
+            const int g = (qh + 2 * i) * 4 + g_in;
             const uint32_t off = g * (WG_KT * 16) + kb * 128 + k_in * 16;
             uint4 hi, lo;
             wg_split8(ra[i][0], ra[i][1], hi, lo);
             *reinterpret_cast<uint4*>(st + off) = hi;
             *reinterpret_cast<uint4*>(st + WG_A_PLANE + off) = lo;
             if (g < real_groups) {
-                wg_split8(rb[i][0], rb[i][1], hi, lo);
+                float4 u = rb[i][0], w = rb[i][1];
+                if (g >= data_groups) {
+                    float e[TIME_DIMS];
+                    const float d = task.time_mode == 1 ? task.timestamp - u.x : 0.f;
+                    e[0] = d;
+                    sincosf(d, &e[1], &e[2]);
+#pragma unroll
+                    for (int f = 1; f < 4; ++f) {
+                        e[1 + 2 * f] = 2.f * e[2 * f - 1] * e[2 * f];
+                        e[2 + 2 * f] = 1.f - 2.f * e[2 * f - 1] * e[2 * f - 1];
+                    }
+                    if (!in) { u = w = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    else if (g == data_groups) { u = make_float4(e[0], e[1], e[2], e[3]); w = make_float4(e[4], e[5], e[6], e[7]); }
+                    else { u = make_float4(e[8], 0.f, 0.f, 0.f); w = make_float4(0.f, 0.f, 0.f, 0.f); }
+                }
+                wg_split8(u, w, hi, lo);
                 *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + off) = hi;
                 *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + WG_B_PLANE + off) = lo;
             }
@@ -1047,14 +1079,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
 
     // D = f32, A = B = bf16, both MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) | ((128u >> 4) << 24);
-    if (t0 < t1) load_tile(t0);
-    uint32_t ph[2] = {0u, 0u};
-#pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
-        const int s = (t - t0) & 1;
-        if (t - t0 >= 2) { mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }      // the MMAs that read this stage are done
-        store_tile(s);
-        if (t + 1 < t1) load_tile(t + 1);
+    if (t0 < t1) load_tile(t0, ra0, rb0);
+    if (t0 + 1 < t1) load_tile(t0 + 1, ra1, rb1);
+    uint32_t phases = 0;                                     // bit s = parity to wait for on stage s
+    int s = 0;
+    auto issue_tile = [&](int t) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (warp == 0) {
@@ -1081,11 +1110,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
                          :: "r"(smem_u32(mbar_p + s)) : "memory");
             __syncwarp();
         }
+        s = s + 1 == WG_STAGES ? 0 : s + 1;
+    };
+#pragma unroll 1
+    for (int t = t0; t < t1; t += 2) {
+        if (t - t0 >= WG_STAGES) { mbar_wait(smem_u32(mbar_p + s), (phases >> s) & 1u); phases ^= 1u << s; }   // stage free again
+        store_tile(s, t, ra0, rb0);
+        if (t + 2 < t1) load_tile(t + 2, ra0, rb0);
+        issue_tile(t);
+        if (t + 1 < t1) {
+            if (t + 1 - t0 >= WG_STAGES) { mbar_wait(smem_u32(mbar_p + s), (phases >> s) & 1u); phases ^= 1u << s; }
+            store_tile(s, t + 1, ra1, rb1);
+            if (t + 3 < t1) load_tile(t + 3, ra1, rb1);
+            issue_tile(t + 1);
+        }
     }
-    // drain: every stage's outstanding commit (MMAs complete in order, but both barriers must be consumed before exit)
+    // drain: the last min(tiles, stages) commits are still unconsumed; walk them oldest first
     const int n_t = t1 - t0;
-    if (n_t >= 2) { const int s = (n_t - 2) & 1; mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }
-    if (n_t >= 1) { const int s = (n_t - 1) & 1; mbar_wait(smem_u32(mbar_p + s), ph[s]); ph[s] ^= 1; }
+    for (int back = n_t < WG_STAGES ? n_t : WG_STAGES; back >= 1; --back) {
+        const int sd = (n_t - back) % WG_STAGES;
+        mbar_wait(smem_u32(mbar_p + sd), (phases >> sd) & 1u);
+        phases ^= 1u << sd;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // partial [128][N]: warp w reads TMEM lanes 32 (w % 4) ..., the two warps of a lane quarter split the columns
@@ -1104,6 +1150,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) deform_wgrad_kernel(const __gri
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u));
+}
+
+// Adds the per-CTA partials of each task (fixed order: deterministic) and writes the parameter-shaped gradients.
+// One block per (task, m); thread n owns column n.  dW[m][n] for n < cols (or dW[n][m] when transposed: the last layer's
+// GEMM yields the transposed weight gradient), db[m] from column bias_col.  accumulate = 1 adds to what is there (the
+// second job of an MLP that is evaluated twice); such tasks run in a second launch.
+struct WReduceTask {
+    const float* partial; int count;
+    float* dW; int ldw; int rows; int cols; int transposed;
+    float* db; int bias_col;
+    int accumulate;
+};
+struct WReduceParams { int n_tasks; WReduceTask tasks[WG_MAX_TASKS]; };
+
+__global__ void __launch_bounds__(160) deform_wgrad_reduce_kernel(const __grid_constant__ WReduceParams p) {
+    const WReduceTask& t = p.tasks[blockIdx.x >> 7];
+    const int m = blockIdx.x & 127, n = threadIdx.x;
+    if (m >= t.rows || n >= WG_OUT_STRIDE) return;
+    const bool is_w = n < t.cols, is_b = t.db != nullptr && n == t.bias_col;
+    if (!is_w && !is_b) return;
+    float sum = 0.f;
+    for (int c = 0; c < t.count; ++c) sum += t.partial[((size_t)c * 128 + m) * WG_OUT_STRIDE + n];
+    float* dst = is_w ? (t.transposed ? t.dW + (size_t)n * t.ldw + m : t.dW + (size_t)m * t.ldw + n) : t.db + m;
+    *dst = t.accumulate ? *dst + sum : sum;
 }
 
 std::mutex g_mu;
@@ -1281,8 +1351,10 @@ static int sgs_deform_train_launch(bool backward, int N, int feat_dim, float tim
         const sgs_mlp_job_t& j = jobs[i];
         if (!j.packed || !j.out || j.n_io <= 0 || (j.n_io > 8 && j.n_io != 48)) return SGS_ERR_INVALID_ARGUMENT;
         if (backward && (!j.in || !j.mask_a || !j.mask_b)) return SGS_ERR_INVALID_ARGUMENT;
-        if ((reinterpret_cast<size_t>(j.out) | reinterpret_cast<size_t>(j.in) | reinterpret_cast<size_t>(j.save_a) |
-             reinterpret_cast<size_t>(j.save_b) | reinterpret_cast<size_t>(j.mask_a) | reinterpret_cast<size_t>(j.mask_b)) & 15)
+        if ((reinterpret_cast<size_t>(j.in) | reinterpret_cast<size_t>(j.mask_a) | reinterpret_cast<size_t>(j.mask_b)) & 15)
+            return SGS_ERR_INVALID_ARGUMENT;
+        if ((reinterpret_cast<size_t>(j.save_a) | reinterpret_cast<size_t>(j.save_b) |
+             ((backward || j.n_io > 8) ? reinterpret_cast<size_t>(j.out) : 0)) & 31)            // 256-bit stores
             return SGS_ERR_INVALID_ARGUMENT;
         TrainJob& t = p.jobs[i];
         t.img = reinterpret_cast<const uint8_t*>(j.packed);
@@ -1328,16 +1400,16 @@ int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job
 
 int sgs_deform_wgrad_max_ctas(void) {
     int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
-    return sms > 0 ? sms : 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    return (sms > 0 ? sms : 148) * sgs_deform::WG_CTAS_PER_SM;
 }
 
 size_t sgs_deform_wgrad_partial_floats(void) { return (size_t)128 * sgs_deform::WG_OUT_STRIDE; }
 
-int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, int* cta_first, int* cta_count,
-                     void* stream) {
+int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal_pos, int n_tasks, const sgs_wgrad_task_t* tasks,
+                     float* partials, void* stream) {
     using namespace sgs_deform;
-    if (N <= 0 || n_tasks <= 0 || n_tasks > WG_MAX_TASKS || !tasks || !partials || !cta_first || !cta_count)
+    if (N <= 0 || n_tasks <= 0 || n_tasks > WG_MAX_TASKS || !tasks || !partials || feat_dim <= 0 || (feat_dim & 7) || feat_dim > 32)
         return SGS_ERR_INVALID_ARGUMENT;
     static bool attr_set = false;
     {
@@ -1357,15 +1429,18 @@ int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* p
     float cost[WG_MAX_TASKS], total = 0.f;
     for (int i = 0; i < n_tasks; ++i) {
         const sgs_wgrad_task_t& t = tasks[i];
-        if (!t.A || !t.B || t.ldb <= 0 || (t.ldb & 7) || t.ldb > 128 ||
-            ((reinterpret_cast<size_t>(t.A) | reinterpret_cast<size_t>(t.B)) & 15))
+        const int ldb = t.time_mode ? feat_dim : t.ldb;
+        if (!t.A || !t.B || ldb <= 0 || (ldb & 7) || ldb > 128 || t.time_mode < 0 || t.time_mode > 2 ||
+            (t.time_mode == 1 && !temporal_pos) || ((reinterpret_cast<size_t>(t.A) | reinterpret_cast<size_t>(t.B)) & 31) ||
+            !t.dW || t.rows <= 0 || t.rows > 128)
             return SGS_ERR_INVALID_ARGUMENT;
         WTask& w = p.tasks[i];
-        w.A = t.A; w.B = t.B; w.ldb = t.ldb;
-        const int real = t.ldb >> 3;
-        w.ones_group = t.ones ? real : -1;
-        w.ngroups = (real + (t.ones ? 1 : 0) + 1) & ~1;
-        cost[i] = 128.f + (float)t.ldb;
+        w.A = t.A; w.B = t.B; w.ldb = ldb; w.tpos = temporal_pos; w.timestamp = timestamp; w.time_mode = t.time_mode;
+        w.real_groups = (ldb >> 3) + (t.time_mode ? 2 : 0);
+        w.ones_group = t.db ? w.real_groups : -1;
+        w.ngroups = (w.real_groups + (t.db ? 1 : 0) + 1) & ~1;
+        if (w.ngroups > WG_NG_MAX || t.cols > w.real_groups * 8) return SGS_ERR_INVALID_ARGUMENT;
+        cost[i] = 128.f + (float)ldb;
         total += cost[i];
     }
     int given = 0;
@@ -1385,11 +1460,23 @@ int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* p
     for (int i = 0; i < n_tasks; ++i) {
         p.tasks[i].cta_first = first;
         p.tasks[i].partial = partials + (size_t)first * 128 * WG_OUT_STRIDE;
-        cta_first[i] = first;
-        cta_count[i] = p.tasks[i].cta_count;
         first += p.tasks[i].cta_count;
     }
-    deform_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    cudaStream_t s = (cudaStream_t)stream;
+    deform_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, s>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return SGS_ERR_CUDA;
+    for (int pass = 0; pass < 2; ++pass) {
+        WReduceParams r;
+        r.n_tasks = 0;
+        for (int i = 0; i < n_tasks; ++i) {
+            if ((tasks[i].accumulate != 0) != (pass == 1)) continue;
+            WReduceTask& q = r.tasks[r.n_tasks++];
+            q.partial = p.tasks[i].partial; q.count = p.tasks[i].cta_count;
+            q.dW = tasks[i].dW; q.ldw = tasks[i].ldw; q.rows = tasks[i].rows; q.cols = tasks[i].cols; q.transposed = tasks[i].transposed;
+            q.db = tasks[i].db; q.bias_col = p.tasks[i].ones_group * 8; q.accumulate = pass;
+        }
+        if (r.n_tasks > 0) deform_wgrad_reduce_kernel<<<r.n_tasks * 128, 160, 0, s>>>(r);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
 }
 

@@ -333,44 +333,38 @@ class _TrainMLPs(torch.autograd.Function):
             raise RuntimeError(f"sgs_deform_train_backward failed ({rc}): {_lib.last_error()}")
         _mark("data_gradient_kernel")
         dfeat = slabs.sum(dim=0) if len(live) > 1 else slabs[0]
-        # weight gradients: one tcgen05 launch for all (job, layer) GEMMs dW = G^T X over the rows; bias gradients ride
-        # along as a constant-one column.  The per-CTA partials of a task are added here, and jobs that share an MLP
-        # (the evaluation at t and the one at the base feature) are summed.
-        xs = {}
-        tasks, spec = [], []
+        # weight gradients: one tcgen05 launch for all (job, layer) GEMMs dW = G^T X over the rows (the first layer's X =
+        # [feature | time embedding] is rebuilt inside the kernel; bias gradients ride along as a constant-one column),
+        # then a deterministic reduction of the per-CTA partials straight into parameter-shaped tensors.  A second
+        # evaluation of the same MLP (base feature) accumulates.
+        out = {}
+        tasks, hold = [], []
         for m, zero_time, dy, h1, h2, dh1, dh2 in work:
             w_in, hid2, n_out = images.shapes[m]
-            key = "feat" if w_in == F else zero_time
-            if key not in xs:
-                if w_in == F:
-                    cols = [feat]
-                else:
-                    d = torch.zeros((n, 1), **f32) if zero_time else (ctx.timestamp - tpos.reshape(n, 1))
-                    cols = [feat, _time_embedding(d)]
-                cols.append(torch.zeros((n, 48 - sum(c.shape[1] for c in cols)), **f32))
-                xs[key] = torch.cat(cols, dim=1)
+            acc = int(m in out)
+            if not acc:
+                out[m] = [torch.empty((HIDDEN, w_in), **f32), torch.empty(HIDDEN, **f32), torch.empty((hid2, HIDDEN), **f32),
+                          torch.empty(hid2, **f32), torch.empty((n_out, hid2), **f32), None]
+            dW1, db1, dW2, db2, dW3, _ = out[m]
             dyp = dy if n_out == 48 else torch.nn.functional.pad(dy, (0, 8 - n_out))
-            tasks += [(dh1, xs[key], 48, 1), (dh2, h1, HIDDEN, 1), (h2, dyp, dyp.shape[1], 0)]
-            spec.append((m, w_in, hid2, n_out, dy))
-        arr_w = (_lib.WgradTask * len(tasks))()
-        for i, (a, b, ldb, ones) in enumerate(tasks):
-            arr_w[i] = _lib.WgradTask(a.data_ptr(), b.data_ptr(), ldb, ones)
-        per = lib.sgs_deform_wgrad_partial_floats()
-        partials = torch.empty((lib.sgs_deform_wgrad_max_ctas(), 128, per // 128), **f32)
-        first = (ctypes.c_int * len(tasks))()
-        count = (ctypes.c_int * len(tasks))()
+            hold.append(dyp)
+            mode = 0 if w_in == F else (2 if zero_time else 1)
+            tasks += [_lib.WgradTask(dh1.data_ptr(), feat.data_ptr(), F, mode, dW1.data_ptr(), w_in, HIDDEN, w_in, 0, db1.data_ptr(), acc),
+                      _lib.WgradTask(dh2.data_ptr(), h1.data_ptr(), HIDDEN, 0, dW2.data_ptr(), HIDDEN, hid2, HIDDEN, 0, db2.data_ptr(), acc),
+                      _lib.WgradTask(h2.data_ptr(), dyp.data_ptr(), dyp.shape[1], 0, dW3.data_ptr(), hid2, hid2, n_out, 1, None, acc)]
+            db3 = dy.sum(0)
+            out[m][5] = db3 if out[m][5] is None else out[m][5] + db3
+        arr_w = (_lib.WgradTask * len(tasks))(*tasks)
+        partials = torch.empty(lib.sgs_deform_wgrad_max_ctas() * lib.sgs_deform_wgrad_partial_floats(), **f32)
         with torch.cuda.device(dev):
-            rc = lib.sgs_deform_wgrad(n, len(tasks), arr_w, partials.data_ptr(), first, count,
+            rc = lib.sgs_deform_wgrad(n, F, ctx.timestamp, tpos.data_ptr(), len(tasks), arr_w, partials.data_ptr(),
                                       torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"sgs_deform_wgrad failed ({rc}): {_lib.last_error()}")
-        for j, (m, w_in, hid2, n_out, dy) in enumerate(spec):
-            D1, D2, D3 = (partials[first[3 * j + q]:first[3 * j + q] + count[3 * j + q]].sum(0) for q in range(3))
-            parts = (D1[:, :w_in], D1[:, 48], D2[:hid2, :HIDDEN], D2[:hid2, HIDDEN], D3[:hid2, :n_out].t(), dy.sum(0))
-            for q, g in enumerate(parts):
-                idx = 6 * m + q
-                if ctx.needs_input_grad[5 + idx]:
-                    grads[idx] = g if grads[idx] is None else grads[idx] + g
+        for m, gs in out.items():
+            for q, g in enumerate(gs):
+                if ctx.needs_input_grad[5 + 6 * m + q]:
+                    grads[6 * m + q] = g
         _mark("weight_gradients")
         ctx.keep = None
         return (dfeat if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
