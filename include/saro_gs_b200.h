@@ -223,44 +223,50 @@ int64_t sgs_deform_eval(int N, int feat_dim, float timestamp, const float* xyz, 
  * sgs_deform_train_forward: per job, out[N][n_io] = MLP([feature | embedding(d)]) with d = timestamp - temporal_pos
  *   (zero_time = 0, :788-790) or d = 0 (zero_time = 1: base feature :793-794, and opacity_mlp whose image has zero
  *   weights on the time columns); writes the ReLU sign bits of both hidden layers (mask_a: layer 1, mask_b: layer 2;
- *   N x 16 bytes each, may be NULL) and, if save_a / save_b are given, the hidden activations h1 / h2 as float32 [N][128].
+ *   N x 16 bytes each, may be NULL) and, where given, operand planes for the weight-gradient GEMMs: save_a / save_b =
+ *   the hidden activations h1 / h2 (16 column groups), save_in = the MLP input [feature | embedding | 0] (6 groups).
  * sgs_deform_train_backward: per job, in = dL/d out [N][n_io]; out = dL/d feature [N][feat_dim] of this job (the
  *   caller sums the jobs); mask_a = the forward's LAYER-2 bits, mask_b = its LAYER-1 bits; save_a / save_b receive
- *   dL/d(pre-activation) of layer 2 / layer 1 as float32 [N][128] (operands of the weight-gradient GEMMs).
- * All pointers are device memory, 16-byte aligned; save_a / save_b, the backward's out and 48-wide forward outs 32-byte
- * aligned (256-bit stores).  Return 0 or a negative error code. */
+ *   dL/d(pre-activation) of layer 2 / layer 1 (16 groups), save_in receives dL/d out (2 groups for n_io <= 8, else 6).
+ * Operand planes: a [rows][8 G] matrix as bf16 hi + lo (x = hi + lo), per 32-row tile a hi plane then a lo plane, each
+ *   G groups of [32 rows][8 columns]: byte offset of (row R, group g, plane p) = ((R / 32) * 2 + p) * G * 512 + g * 512
+ *   + (R % 32) * 16.  sgs_deform_planes_bytes(N, G) bytes (whole 128-row tiles; rows past N are written as zeros).
+ *   This is the tensor-core operand form: sgs_deform_wgrad streams it from HBM to the MMA by TMA, no conversion.
+ * All pointers are device memory, 16-byte aligned; the backward's out and 48-wide forward outs 32-byte aligned
+ * (256-bit stores).  Return 0 or a negative error code. */
 typedef struct sgs_mlp_job {
     const void* packed;
     const float* in;
     float* out;
-    float* save_a;
-    float* save_b;
+    void* save_a;
+    void* save_b;
+    void* save_in;
     void* mask_a;
     void* mask_b;
     int n_io;
     int zero_time;
 } sgs_mlp_job_t;
 size_t sgs_deform_image_bytes(void);
+size_t sgs_deform_planes_bytes(int N, int groups);
 int sgs_deform_pack_general(int backward, int in_w, int hid2, int n_out, int feat_dim, const float* W1, const float* b1,
                             const float* W2, const float* b2, const float* W3, const float* b3, void* image, void* stream);
 int sgs_deform_train_forward(int N, int feat_dim, float timestamp, const float* temporal_pos, const float* feature, int n_jobs,
                              const sgs_mlp_job_t* jobs, void* stream);
 int sgs_deform_train_backward(int N, int feat_dim, int n_jobs, const sgs_mlp_job_t* jobs, void* stream);
 
-/* Weight gradients of the training-time deformation: every task is one GEMM over the N rows,
- *   D[m][n] = sum_r A[r][m] * B[r][n]   (m < 128)   and, when db is given,   db[m] = sum_r A[r][m],
- * written as dW[m][n] (row stride ldw; m < rows, n < cols) or, with transposed = 1, dW[n][m] (the last layer: A = the
- * hidden activation, B = dL/d out).  A: [N][128] float32; B: [N][ldb] float32, ldb a multiple of 8 (time_mode 0), or the
- * plane feature [N][feat_dim] from which the MLP input [feature | time embedding of d | 0] is rebuilt on the fly
- * (time_mode 1: d = timestamp - temporal_pos[row]; 2: d = 0).  accumulate = 1 adds to dW / db (the second evaluation of
- * an MLP in the same call) instead of overwriting.  `partials`: scratch of sgs_deform_wgrad_max_ctas() x
- * sgs_deform_wgrad_partial_floats() floats.  All pointers device memory; A and B 32-byte aligned (256-bit loads).  One GEMM launch + one or
- * two reduction launches on `stream`; deterministic (fixed summation order).  Returns 0 or a negative error code. */
+/* Weight gradients of the training-time deformation: every task is one GEMM over the rows of two operand-plane
+ * matrices (above),   D[m][n] = sum_r A[r][m] * B[r][n]   (A: 16 groups, m < 128; B: groups_b = 2, 6 or 16 groups) and,
+ * when db is given,   db[m] = sum_r A[r][m],   written as dW[m][n] (row stride ldw; m < rows, n < cols) or, with
+ * transposed = 1, dW[n][m] (the last layer: A = the hidden activation h2, B = dL/d out).  Layer 1: A = the backward's
+ * save_b, B = the forward's save_in; layer 2: A = the backward's save_a, B = the forward's save_a; layer 3: A = the
+ * forward's save_b, B = the backward's save_in.  accumulate = 1 adds to dW / db (the second evaluation of an MLP in the
+ * same call).  `partials`: scratch of sgs_deform_wgrad_max_ctas() x sgs_deform_wgrad_partial_floats() floats.  One GEMM
+ * launch + one or two reduction launches on `stream`; deterministic (fixed summation order).  N = the row count the
+ * planes were produced for.  Returns 0 or a negative error code. */
 typedef struct sgs_wgrad_task {
-    const float* A;
-    const float* B;
-    int ldb;
-    int time_mode;
+    const void* A;
+    const void* B;
+    int groups_b;
     float* dW;
     int ldw;
     int rows;
@@ -271,8 +277,7 @@ typedef struct sgs_wgrad_task {
 } sgs_wgrad_task_t;
 int sgs_deform_wgrad_max_ctas(void);
 size_t sgs_deform_wgrad_partial_floats(void);
-int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal_pos, int n_tasks, const sgs_wgrad_task_t* tasks,
-                     float* partials, void* stream);
+int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Densification statistics of one training iteration — replaces the per-view lists and

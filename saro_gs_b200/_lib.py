@@ -55,7 +55,8 @@ ABI = {
     "sgs_deform_train_backward": (_i, [_i, _i, _i, _vp, _vp]),
     "sgs_deform_wgrad_max_ctas": (_i, []),
     "sgs_deform_wgrad_partial_floats": (ctypes.c_size_t, []),
-    "sgs_deform_wgrad": (_i, [_i, _i, _f, _vp, _i, _vp, _vp, _vp]),
+    "sgs_deform_wgrad": (_i, [_i, _i, _vp, _vp, _vp]),
+    "sgs_deform_planes_bytes": (ctypes.c_size_t, [_i, _i]),
     "sgs_densify_add_view": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_densify_attach": (_i, [_i, _vp, _vp, _vp]),
     "sgs_densify_commit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -83,14 +84,13 @@ class PlaneDesc(ctypes.Structure):
 class MLPJob(ctypes.Structure):
     """sgs_mlp_job_t of include/saro_gs_b200.h"""
     _fields_ = [("packed", ctypes.c_void_p), ("inp", ctypes.c_void_p), ("out", ctypes.c_void_p), ("save_a", ctypes.c_void_p),
-                ("save_b", ctypes.c_void_p), ("mask_a", ctypes.c_void_p), ("mask_b", ctypes.c_void_p), ("n_io", ctypes.c_int),
+                ("save_b", ctypes.c_void_p), ("save_in", ctypes.c_void_p), ("mask_a", ctypes.c_void_p), ("mask_b", ctypes.c_void_p), ("n_io", ctypes.c_int),
                 ("zero_time", ctypes.c_int)]
 
 
 class WgradTask(ctypes.Structure):
     """sgs_wgrad_task_t of include/saro_gs_b200.h"""
-    _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("ldb", ctypes.c_int), ("time_mode", ctypes.c_int),
-                ("dW", ctypes.c_void_p), ("ldw", ctypes.c_int), ("rows", ctypes.c_int), ("cols", ctypes.c_int),
+    _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("groups_b", ctypes.c_int), ("dW", ctypes.c_void_p), ("ldw", ctypes.c_int), ("rows", ctypes.c_int), ("cols", ctypes.c_int),
                 ("transposed", ctypes.c_int), ("db", ctypes.c_void_p), ("accumulate", ctypes.c_int)]
 
 

@@ -598,7 +598,9 @@ struct TrainJob {
     const uint8_t* img;            // packed image (forward: from W; backward: from the transposed W)
     const float* in;               // backward: dL/d out [N][n_io]
     float* out;                    // forward: raw outputs [N][n_io]; backward: dL/d feature [N][feat_dim]
-    float* save_a; float* save_b;  // [N][128] float32 or NULL: forward h1, h2; backward d h2, d h1 (after the mask)
+    uint8_t* save_a; uint8_t* save_b;   // operand planes (16 column groups) or NULL: forward h1, h2; backward d h2, d h1 (after the mask)
+    uint8_t* save_in;              // operand planes of the layer-1 operand: forward [feature | embedding | 0] (6 groups),
+                                   // backward dL/d out (6 groups for 48 outputs, 2 for up to 8), or NULL
     uint2* mask_a; uint2* mask_b;  // [N][2]: sign bits of the two hidden layers, 64 columns per entry (forward writes:
                                    // a = layer 1, b = layer 2; backward reads: a = layer 2, b = layer 1)
     int n_io;
@@ -679,11 +681,41 @@ __device__ __forceinline__ void ld_global_nc_v8(const float* src, float4& u, flo
                  "=f"(w.y), "=f"(w.z), "=f"(w.w) : "l"(src));
 }
 
+// "Operand planes": what the weight-gradient kernel consumes.  A [rows][8 G] matrix is stored per 32-row tile as a hi
+// plane then a lo plane (bf16 x = hi + lo), each G groups of [32 rows][8 columns] — i.e. already in the MN-major
+// shared-memory form of tcgen05.mma, so the weight-gradient kernel moves tiles from HBM to the tensor core by TMA alone.
+// The producing kernels have the hi / lo split in registers anyway (it is their own next-layer operand), and a warp's
+// 32 rows of one group are 512 contiguous bytes: perfectly coalesced 16-byte stores.
+// Byte offset of (row R, group g, plane p) = ((R / 32) * 2 + p) * G * 512 + g * 512 + (R % 32) * 16.
+__device__ __forceinline__ uint8_t* planes_row(uint8_t* base, size_t R, int G) {
+    return base ? base + (R >> 5) * (size_t)(2 * G * 512) + (R & 31) * 16 : nullptr;
+}
+
+// store_chunk + optional copy of the two 16-byte plane rows
+__device__ __forceinline__ void store_chunk_save(uint32_t t_hi, uint32_t t_lo, int kc, const float2 (&v)[4], uint8_t* save_row, int G) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __float22bfloat162_rn(v[i]);
+        const float2 lo = __ffma2_rn(__bfloat1622float2(hh), make_float2(-1.f, -1.f), v[i]);
+        const __nv_bfloat162 ll = __float22bfloat162_rn(lo);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    tmem_st4(t_hi + kc * 4, h);
+    tmem_st4(t_lo + kc * 4, l);
+    if (save_row != nullptr) {
+        *reinterpret_cast<uint4*>(save_row + kc * 512) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(save_row + G * 512 + kc * 512) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 // hidden layer epilogue of the training kernels.  Forward: + bias, ReLU, sign bits out.  Backward: multiply by the
-// saved sign bits.  Both: next layer's TMEM operand, optional float32 copy of the row for the weight-gradient kernel.
+// saved sign bits.  Both: next layer's TMEM operand, optional operand planes for the weight-gradient kernel (rows past
+// N are written as zeros: the planes are allocated in whole 128-row tiles).
 template <bool BWD>
 __device__ __forceinline__ void hidden_epilogue_train(uint32_t t_acc, uint32_t t_hi, uint32_t t_lo, const float* __restrict__ bias,
-                                                      int half, bool valid, float* __restrict__ save_row, uint2* __restrict__ mask_slot,
+                                                      int half, bool valid, uint8_t* __restrict__ save_row, uint2* __restrict__ mask_slot,
                                                       uint2 mask_in) {
     const int cbase = half * (HID / 2);
     uint32_t mw[2] = {BWD ? mask_in.x : 0u, BWD ? mask_in.y : 0u};
@@ -704,15 +736,14 @@ __device__ __forceinline__ void hidden_epilogue_train(uint32_t t_acc, uint32_t t
                 if (!BWD) {
                     const float2 b = *reinterpret_cast<const float2*>(bias + c0 + h * 8 + 2 * i);
                     const float2 y = __fadd2_rn(a, b);
-                    x[i] = make_float2(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f));
+                    x[i] = valid ? make_float2(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f)) : make_float2(0.f, 0.f);
                     mw[word] |= (y.x > 0.f ? 1u : 0u) << bit;
                     mw[word] |= (y.y > 0.f ? 1u : 0u) << (bit + 1);
                 } else {
                     x[i] = make_float2((mw[word] >> bit) & 1u ? a.x : 0.f, (mw[word] >> (bit + 1)) & 1u ? a.y : 0.f);
                 }
             }
-            store_chunk(t_hi, t_lo, c0 / 8 + h, x);
-            if (save_row != nullptr && valid) st_global_v8(save_row + c0 + h * 8, x);
+            store_chunk_save(t_hi, t_lo, c0 / 8 + h, x, save_row, HID / 8);
         }
     }
     if (!BWD && mask_slot != nullptr && valid) *mask_slot = make_uint2(mw[0], mw[1]);
@@ -780,6 +811,7 @@ __device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& 
         const size_t jr = (size_t)(valid ? j : N - 1);
 
         // ---- layer-1 operand
+        uint8_t* const in_row = planes_row(job.save_in, (size_t)j, K1STEPS == 3 ? 6 : 2);
         if (!BWD) {
             const float d = job.zero_time ? 0.f : p.timestamp - cur.tpos;       // saro_gaussian.py:788-794
             float emb[TIME_DIMS];
@@ -806,7 +838,11 @@ __device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& 
                     for (int i = 0; i < 4; ++i) x[i] = make_float2(0.f, 0.f);
                     if (kc == nf + 1) x[0].x = emb[8];
                 }
-                store_chunk(t_hi, t_lo, kc, x);
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(0.f, 0.f);
+                }
+                store_chunk_save(t_hi, t_lo, kc, x, in_row, 6);
             }
         } else {
 #pragma unroll
@@ -814,7 +850,11 @@ __device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& 
                 const int kc = 2 * c + half;
                 const float4 u = cur.v[2 * c], w = cur.v[2 * c + 1];
                 float2 x[4] = {make_float2(u.x, u.y), make_float2(u.z, u.w), make_float2(w.x, w.y), make_float2(w.z, w.w)};
-                store_chunk(t_hi, t_lo, kc, x);
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = make_float2(0.f, 0.f);
+                }
+                store_chunk_save(t_hi, t_lo, kc, x, in_row, K1STEPS == 3 ? 6 : 2);
             }
         }
         publish_operand(group);
@@ -834,13 +874,13 @@ __device__ __forceinline__ void run_train(const TrainParams& p, const TrainJob& 
 
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b1, half, valid, job.save_a ? job.save_a + jr * HID : nullptr,
+        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b1, half, valid, planes_row(job.save_a, (size_t)j, HID / 8),
                                    job.mask_a ? job.mask_a + jr * 2 + half : nullptr, m_a);
         publish_operand(group);
         if (issuer) issue_layer<HID / 16>(acc_u, hi_u, lo_u, simg + OFF_W2HI, simg + OFF_W2LO, HID, mbar);
         mbar_wait(mbar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b2, half, valid, job.save_b ? job.save_b + jr * HID : nullptr,
+        hidden_epilogue_train<BWD>(t_acc, t_hi, t_lo, b2, half, valid, planes_row(job.save_b, (size_t)j, HID / 8),
                                    job.mask_b ? job.mask_b + jr * 2 + half : nullptr, m_b);
         publish_operand(group);
         if (issuer) issue_last_layer(acc_u, hi_u, lo_u, simg + OFF_W3, N3P, mbar);
@@ -928,91 +968,76 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) deform_train_kernel(cons
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Weight gradients of the training path: dW = G^T X summed over the N rows, for every (job, layer).  The batch row is
-// the GEMM's K dimension, and both operands sit in HBM row-major as float32 [row][feature] — exactly the MN-major
-// shared-memory operand form of tcgen05.mma (element (mn, k) at (mn % 8) * 2 + (mn / 8) * SBO + (k % 8) * 16 +
-// (k / 8) * 128 bytes; descriptor fields pinned on hardware by tools/microbench/umma_mn_probe.cu), so a thread that
-// loaded 8 consecutive features of a row stores them as ONE 16-byte row of a core matrix: no transposition anywhere.
-// Each CTA owns one task and a contiguous range of 64-row tiles: global float32 -> registers (next tile in flight) ->
-// bf16 hi / lo planes in a two-stage shared-memory ring -> 12 MMAs per tile (hi*hi + hi*lo + lo*hi, f32 accumulate in
-// TMEM across the whole range) -> the CTA's partial [128][N] to global; the host adds the few partials of a task.
-// Bias gradients ride along as a constant-one column of the B operand.  HBM-bound: every operand element is read once.
-constexpr int WG_KT = 32;                       // batch rows per ring stage (2 MMA K-steps)
-constexpr int WG_STAGES = 3;
-constexpr int WG_THREADS = 256;
-constexpr int WG_CTAS_PER_SM = 2;               // 512 TMEM columns / 256; 3 x 34 KB of shared memory each
+// the GEMM's K dimension.  Both operands were emitted by the producing kernels as "operand planes" (above): 32-row
+// tiles whose bytes ARE the MN-major shared-memory operand form of tcgen05.mma (descriptor fields pinned on hardware by
+// tools/microbench/umma_mn_probe.cu), so this kernel has no arithmetic at all: one thread streams tiles HBM -> shared
+// memory with TMA bulk copies (one contiguous block per operand and tile, a six-deep ring), one warp issues per tile
+// 6 MMAs (hi*hi + hi*lo + lo*hi over two K-steps, f32 accumulate in TMEM across the CTA's whole tile range) plus 4 small
+// ones against a constant-one operand (bias gradients), and at the end the CTA's partial [128][144] goes to global;
+// a reduction kernel adds the few partials of a task in a fixed order.  Earlier versions converted float32 operands
+// inside this kernel (through registers, then through a TMA-fed staging ring): both ran at ~3.3 TB/s, bound by the
+// conversion's issue slots and block barriers, not by DRAM (ncu: DRAM 32 %, tensor pipe 4 %).
+constexpr int WG_KT = 32;                       // batch rows per tile (2 MMA K-steps)
+constexpr int WG_STAGES = 6;
+constexpr int WG_THREADS = 128;
+constexpr int WG_CTAS_PER_SM = 1;
 constexpr int WG_MAX_TASKS = 24;
-constexpr int WG_NG_MAX = 18;                   // B column groups of 8: 16 real + the ones group, N = 144
-constexpr int WG_A_PLANE = 16 * WG_KT * 16;     // 8 KB: 128 features x 32 rows x bf16
-constexpr int WG_B_PLANE = WG_NG_MAX * WG_KT * 16;
-constexpr int WG_STAGE_BYTES = 2 * WG_A_PLANE + 2 * WG_B_PLANE;       // 34 816
-constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 64;
-constexpr int WG_OUT_STRIDE = WG_NG_MAX * 8;    // floats per row of a partial
+constexpr int WG_GROUP_BYTES = WG_KT * 16;      // 512: one column group of one plane
+constexpr int WG_A_BYTES = 2 * 16 * WG_GROUP_BYTES;          // 16 384: hi + lo planes of a 128-column operand
+constexpr int WG_STAGE_BYTES = 2 * WG_A_BYTES;  // A tile + B tile (<= 128 columns)
+constexpr int WG_ONES_BYTES = 2 * WG_GROUP_BYTES;            // N = 16 operand: column 0 = 1, the rest 0
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 128;     // 197 760
+constexpr int WG_BIAS_COL = 128;                // accumulator column of the bias gradient
+constexpr int WG_OUT_STRIDE = 144;              // floats per row of a partial
 
 struct WTask {
-    const float* A;          // [N][128] float32: becomes the M dimension
-    const float* B;          // [N][ldb] float32, ldb a multiple of 8
-    const float* tpos;       // time mode (B = plane feature rows): the MLP input [feature | embedding(d) | 0] is rebuilt on the fly
-    float timestamp;
-    int time_mode;           // 0 plain, 1 d = timestamp - tpos[row], 2 d = 0
+    const uint8_t* A;        // operand planes, 16 groups: becomes the M dimension
+    const uint8_t* B;        // operand planes, gb groups (2, 6 or 16)
     float* partial;          // [cta_count][128][WG_OUT_STRIDE]
-    int ldb;
-    int real_groups;         // column groups filled per tile (ldb / 8, + 2 in time mode)
-    int ngroups;             // B column groups the MMA covers (even): the real ones, then constants
-    int ones_group;          // index of the group whose column 0 is the constant 1 (bias gradient), or -1
+    int gb;
+    int bias;                // also accumulate sum_r A[r][m] into column WG_BIAS_COL
     int cta_first, cta_count;
 };
 struct WParams {
-    int N, n_tasks;
+    int tiles, n_tasks;      // 32-row tiles of the (padded) operands
     WTask tasks[WG_MAX_TASKS];
 };
 
-__device__ __forceinline__ void wg_split8(const float4& u, const float4& w, uint4& hi, uint4& lo) {
-    const float2 v[4] = {make_float2(u.x, u.y), make_float2(u.z, u.w), make_float2(w.x, w.y), make_float2(w.z, w.w)};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 hh = __float22bfloat162_rn(v[i]);
-        const float2 rest = __ffma2_rn(__bfloat1622float2(hh), make_float2(-1.f, -1.f), v[i]);
-        const __nv_bfloat162 ll = __float22bfloat162_rn(rest);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
+// 1-D bulk copy global -> shared (TMA), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void wg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t wg_desc(uint32_t saddr) {      // MN-major, no swizzle: LBO = 128 (k-blocks), SBO = 512 (column groups)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(WG_GROUP_BYTES >> 4) << 32) | ((uint64_t)1 << 46);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, WG_CTAS_PER_SM) deform_wgrad_kernel(const __grid_constant__ WParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_p + WG_STAGES);
+    uint8_t* ones = smem + WG_STAGES * WG_STAGE_BYTES;
+    uint64_t* full_p = reinterpret_cast<uint64_t*>(ones + WG_ONES_BYTES);      // [WG_STAGES] "tile landed"
+    uint64_t* done_p = full_p + WG_STAGES;                                      // [WG_STAGES] "MMAs of this stage finished"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_p + WG_STAGES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int ti = 0;
     while (ti + 1 < p.n_tasks && (int)blockIdx.x >= p.tasks[ti].cta_first + p.tasks[ti].cta_count) ++ti;
     const WTask& task = p.tasks[ti];
     const int local = (int)blockIdx.x - task.cta_first;
-    const int tiles = (p.N + WG_KT - 1) / WG_KT;
-    const int t0 = (int)((long long)tiles * local / task.cta_count), t1 = (int)((long long)tiles * (local + 1) / task.cta_count);
-    const int real_groups = task.real_groups, data_groups = task.ldb >> 3;
-    const int nmma = task.ngroups * 8;
+    const int t0 = (int)((long long)p.tiles * local / task.cta_count), t1 = (int)((long long)p.tiles * (local + 1) / task.cta_count);
+    const int n_t = t1 - t0;
+    const uint32_t b_bytes = (uint32_t)task.gb * 2 * WG_GROUP_BYTES;
+    const int nmma = task.gb * 8;
 
-    // constant column groups of B (zero padding, the ones column): written once per stage
-    for (int s = 0; s < WG_STAGES; ++s) {
-        uint8_t* st = smem + s * WG_STAGE_BYTES + 2 * WG_A_PLANE;
-        for (int u = tid; u < (task.ngroups - real_groups) * WG_KT; u += WG_THREADS) {
-            const int g = real_groups + u / WG_KT, k = u % WG_KT;
-            const uint32_t one = g == task.ones_group ? 0x3F80u : 0u;          // bf16(1.0) in element 0
-            const uint32_t off = g * (WG_KT * 16) + (k >> 3) * 128 + (k & 7) * 16;
-            *reinterpret_cast<uint4*>(st + off) = make_uint4(one, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(st + WG_B_PLANE + off) = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
+    for (int u = tid; u < WG_ONES_BYTES / 16; u += WG_THREADS)                  // group 0: column 0 = bf16(1.0) in every row
+        reinterpret_cast<uint4*>(ones)[u] = make_uint4(u < WG_KT ? 0x3F80u : 0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar_p + s)), "r"(1u));
+        for (int s = 0; s < 2 * WG_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(full_p + s)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1020,124 +1045,72 @@ __global__ void __launch_bounds__(WG_THREADS, WG_CTAS_PER_SM) deform_wgrad_kerne
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    // load units: (row k of the tile, group g of 8 features).  Within a warp the 8 rows of a k-block vary fastest and 4
-    // groups next, so each quarter-warp of a 16-byte shared store covers one contiguous 128-byte core matrix.
-    // 8 warps = 4 k-blocks x 2 halves of the group quads; i picks the quad within the half.
-    const int k_in = lane & 7, g_in = lane >> 3;
-    const int kb = warp & 3, qh = warp >> 2;
-    // two register sets: the loads of tiles t + 1 and t + 2 are in flight while tile t is converted (the kernel is bound
-    // by HBM latency, not by issue or by the tensor core: ~150 instructions and 6 MMAs per thread and tile)
-    float4 ra0[2][2], rb0[2][2], ra1[2][2], rb1[2][2];
-    auto load_tile = [&](int t, float4 (&ra)[2][2], float4 (&rb)[2][2]) {
-        const int row = t * WG_KT + kb * 8 + k_in;
-        const bool in = row < p.N;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = (qh + 2 * i) * 4 + g_in;
-            ra[i][0] = ra[i][1] = rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in) {
-                ld_global_nc_v8(task.A + (size_t)row * 128 + g * 8, ra[i][0], ra[i][1]);
-                if (g < data_groups) ld_global_nc_v8(task.B + (size_t)row * task.ldb + g * 8, rb[i][0], rb[i][1]); else if (g < real_groups) {                 // time mode: the embedding columns (saro_gaussian.py:939-969)
-                    rb[i][0].x = task.time_mode == 1 ? __ldg(task.tpos + row) : 0.f;     // raw; expanded in store_tile
-                }
-            }
+    if (warp == 1 && lane == 0) {
+        // ---- producer: tile t0 + it into stage it % WG_STAGES, as soon as the MMAs that read the stage have finished
+        for (int it = 0; it < n_t; ++it) {
+            const int s = it % WG_STAGES;
+            if (it >= WG_STAGES) mbar_wait(smem_u32(done_p + s), (uint32_t)(it / WG_STAGES - 1) & 1u);
+            const uint32_t bar = smem_u32(full_p + s);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)WG_A_BYTES + b_bytes) : "memory");
+            const uint32_t dst = smem_u32(smem + s * WG_STAGE_BYTES);
+            wg_bulk_load(dst, task.A + (size_t)(t0 + it) * WG_A_BYTES, WG_A_BYTES, bar);
+            wg_bulk_load(dst + WG_A_BYTES, task.B + (size_t)(t0 + it) * b_bytes, b_bytes, bar);
         }
-    };
-    auto store_tile = [&](int s, int t, const float4 (&ra)[2][2], const float4 (&rb)[2][2]) {
-        uint8_t* st = smem + s * WG_STAGE_BYTES;
-        const bool in = t * WG_KT + kb * 8 + k_in < p.N;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = (qh + 2 * i) * 4 + g_in;
-            const uint32_t off = g * (WG_KT * 16) + kb * 128 + k_in * 16;
-            uint4 hi, lo;
-            wg_split8(ra[i][0], ra[i][1], hi, lo);
-            *reinterpret_cast<uint4*>(st + off) = hi;
-            *reinterpret_cast<uint4*>(st + WG_A_PLANE + off) = lo;
-            if (g < real_groups) {
-                float4 u = rb[i][0], w = rb[i][1];
-                if (g >= data_groups) {
-                    float e[TIME_DIMS];
-                    const float d = task.time_mode == 1 ? task.timestamp - u.x : 0.f;
-                    e[0] = d;
-                    sincosf(d, &e[1], &e[2]);
-#pragma unroll
-                    for (int f = 1; f < 4; ++f) {
-                        e[1 + 2 * f] = 2.f * e[2 * f - 1] * e[2 * f];
-                        e[2 + 2 * f] = 1.f - 2.f * e[2 * f - 1] * e[2 * f - 1];
-                    }
-                    if (!in) { u = w = make_float4(0.f, 0.f, 0.f, 0.f); }
-                    else if (g == data_groups) { u = make_float4(e[0], e[1], e[2], e[3]); w = make_float4(e[4], e[5], e[6], e[7]); }
-                    else { u = make_float4(e[8], 0.f, 0.f, 0.f); w = make_float4(0.f, 0.f, 0.f, 0.f); }
-                }
-                wg_split8(u, w, hi, lo);
-                *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + off) = hi;
-                *reinterpret_cast<uint4*>(st + 2 * WG_A_PLANE + WG_B_PLANE + off) = lo;
-            }
-        }
-    };
-
-    // D = f32, A = B = bf16, both MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) | ((128u >> 4) << 24);
-    if (t0 < t1) load_tile(t0, ra0, rb0);
-    if (t0 + 1 < t1) load_tile(t0 + 1, ra1, rb1);
-    uint32_t phases = 0;                                     // bit s = parity to wait for on stage s
-    int s = 0;
-    auto issue_tile = [&](int t) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (warp == 0) {
+    } else if (warp == 0) {
+        // ---- consumer: all lanes run the sequence, one elected lane issues (single predicated UTCHMMA per instruction)
+        // D = f32, A = B = bf16, both MN-major (bits 15, 16), N at bit 17, M = 128 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t one_addr = smem_u32(ones);
+        for (int it = 0; it < n_t; ++it) {
+            const int s = it % WG_STAGES;
+            mbar_wait(smem_u32(full_p + s), (uint32_t)(it / WG_STAGES) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES), a_lo = a_hi + WG_A_PLANE;
-            const uint32_t b_hi = a_hi + 2 * WG_A_PLANE, b_lo = b_hi + WG_B_PLANE;
+            const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES), a_lo = a_hi + 16 * WG_GROUP_BYTES;
+            const uint32_t b_hi = a_hi + WG_A_BYTES, b_lo = b_hi + task.gb * WG_GROUP_BYTES;
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
                 const uint32_t a = prod == 2 ? a_lo : a_hi, b = prod == 1 ? b_lo : b_hi;
 #pragma unroll
                 for (int ks = 0; ks < WG_KT / 16; ++ks) {
-                    const uint64_t da = (uint64_t)(((a + ks * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-                                        ((uint64_t)((WG_KT * 16) >> 4) << 32) | ((uint64_t)1 << 46);
-                    const uint64_t db = (uint64_t)(((b + ks * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-                                        ((uint64_t)((WG_KT * 16) >> 4) << 32) | ((uint64_t)1 << 46);
-                    const uint32_t acc = (t > t0 || prod > 0 || ks > 0) ? 1u : 0u;
+                    const uint32_t acc = (it > 0 || prod > 0 || ks > 0) ? 1u : 0u;
                     asm volatile("{\n\t.reg .pred pe, pa;\n\tsetp.ne.b32 pa, %4, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
                                  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
-                                 :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                                 :: "r"(tmem), "l"(wg_desc(a + ks * 256)), "l"(wg_desc(b + ks * 256)), "r"(idesc), "r"(acc) : "memory");
                 }
+            }
+            if (task.bias) {
+#pragma unroll
+                for (int prod = 0; prod < 2; ++prod)
+#pragma unroll
+                    for (int ks = 0; ks < WG_KT / 16; ++ks) {
+                        const uint32_t acc = (it > 0 || prod > 0 || ks > 0) ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred pe, pa;\n\tsetp.ne.b32 pa, %4, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                                     "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+                                     :: "r"(tmem + WG_BIAS_COL), "l"(wg_desc((prod ? a_lo : a_hi) + ks * 256)), "l"(wg_desc(one_addr + ks * 256)),
+                                        "r"(idesc_b), "r"(acc) : "memory");
+                    }
             }
             asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
                          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-                         :: "r"(smem_u32(mbar_p + s)) : "memory");
+                         :: "r"(smem_u32(done_p + s)) : "memory");
             __syncwarp();
         }
-        s = s + 1 == WG_STAGES ? 0 : s + 1;
-    };
-#pragma unroll 1
-    for (int t = t0; t < t1; t += 2) {
-        if (t - t0 >= WG_STAGES) { mbar_wait(smem_u32(mbar_p + s), (phases >> s) & 1u); phases ^= 1u << s; }   // stage free again
-        store_tile(s, t, ra0, rb0);
-        if (t + 2 < t1) load_tile(t + 2, ra0, rb0);
-        issue_tile(t);
-        if (t + 1 < t1) {
-            if (t + 1 - t0 >= WG_STAGES) { mbar_wait(smem_u32(mbar_p + s), (phases >> s) & 1u); phases ^= 1u << s; }
-            store_tile(s, t + 1, ra1, rb1);
-            if (t + 3 < t1) load_tile(t + 3, ra1, rb1);
-            issue_tile(t + 1);
+        // every commit the producer did not consume must still be observed before the accumulator is read
+        for (int back = n_t < WG_STAGES ? n_t : WG_STAGES; back >= 1; --back) {
+            const int it = n_t - back;
+            mbar_wait(smem_u32(done_p + it % WG_STAGES), (uint32_t)(it / WG_STAGES) & 1u);
         }
     }
-    // drain: the last min(tiles, stages) commits are still unconsumed; walk them oldest first
-    const int n_t = t1 - t0;
-    for (int back = n_t < WG_STAGES ? n_t : WG_STAGES; back >= 1; --back) {
-        const int sd = (n_t - back) % WG_STAGES;
-        mbar_wait(smem_u32(mbar_p + sd), (phases >> sd) & 1u);
-        phases ^= 1u << sd;
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // partial [128][N]: warp w reads TMEM lanes 32 (w % 4) ..., the two warps of a lane quarter split the columns
-    float* out = task.partial + (size_t)local * 128 * WG_OUT_STRIDE + (size_t)((warp & 3) * 32 + lane) * WG_OUT_STRIDE;
-    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c0 = (warp >> 2) * 8; c0 < nmma; c0 += 16) {
+    // partial [128][144]: warp w reads TMEM lanes 32 w ...; columns [0, nmma) and the bias block
+    float* out = task.partial + (size_t)local * 128 * WG_OUT_STRIDE + (size_t)(warp * 32 + lane) * WG_OUT_STRIDE;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < WG_OUT_STRIDE; c0 += 8) {
+        if (c0 >= nmma && !(task.bias && c0 == WG_BIAS_COL)) continue;
         float v[8];
         if (n_t > 0) tmem_ld8(t_row + c0, v);
         else {
@@ -1353,12 +1326,15 @@ static int sgs_deform_train_launch(bool backward, int N, int feat_dim, float tim
         if (backward && (!j.in || !j.mask_a || !j.mask_b)) return SGS_ERR_INVALID_ARGUMENT;
         if ((reinterpret_cast<size_t>(j.in) | reinterpret_cast<size_t>(j.mask_a) | reinterpret_cast<size_t>(j.mask_b)) & 15)
             return SGS_ERR_INVALID_ARGUMENT;
-        if ((reinterpret_cast<size_t>(j.save_a) | reinterpret_cast<size_t>(j.save_b) |
-             ((backward || j.n_io > 8) ? reinterpret_cast<size_t>(j.out) : 0)) & 31)            // 256-bit stores
+        if ((reinterpret_cast<size_t>(j.save_a) | reinterpret_cast<size_t>(j.save_b) | reinterpret_cast<size_t>(j.save_in)) & 15)
+            return SGS_ERR_INVALID_ARGUMENT;
+        if (((backward || j.n_io > 8) ? reinterpret_cast<size_t>(j.out) : 0) & 31)            // 256-bit stores
             return SGS_ERR_INVALID_ARGUMENT;
         TrainJob& t = p.jobs[i];
         t.img = reinterpret_cast<const uint8_t*>(j.packed);
-        t.in = j.in; t.out = j.out; t.save_a = j.save_a; t.save_b = j.save_b;
+        t.in = j.in; t.out = j.out;
+        t.save_a = reinterpret_cast<uint8_t*>(j.save_a); t.save_b = reinterpret_cast<uint8_t*>(j.save_b);
+        t.save_in = reinterpret_cast<uint8_t*>(j.save_in);
         t.mask_a = reinterpret_cast<uint2*>(j.mask_a); t.mask_b = reinterpret_cast<uint2*>(j.mask_b);
         t.n_io = j.n_io; t.n3p = backward ? 32 : (j.n_io <= 8 ? 16 : 48); t.zero_time = j.zero_time;
         cost[i] = (j.n_io > 8 ? COST_SHS : COST_ROT) + ((j.save_a || j.save_b) ? 2.f : 0.f);
@@ -1406,11 +1382,14 @@ int sgs_deform_wgrad_max_ctas(void) {
 
 size_t sgs_deform_wgrad_partial_floats(void) { return (size_t)128 * sgs_deform::WG_OUT_STRIDE; }
 
-int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal_pos, int n_tasks, const sgs_wgrad_task_t* tasks,
-                     float* partials, void* stream) {
+size_t sgs_deform_planes_bytes(int N, int groups) {
+    if (N <= 0 || groups <= 0) return 0;
+    return (size_t)((N + sgs_deform::ROWS - 1) / sgs_deform::ROWS) * 4 * 2 * (size_t)groups * 512;
+}
+
+int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, void* stream) {
     using namespace sgs_deform;
-    if (N <= 0 || n_tasks <= 0 || n_tasks > WG_MAX_TASKS || !tasks || !partials || feat_dim <= 0 || (feat_dim & 7) || feat_dim > 32)
-        return SGS_ERR_INVALID_ARGUMENT;
+    if (N <= 0 || n_tasks <= 0 || n_tasks > WG_MAX_TASKS || !tasks || !partials) return SGS_ERR_INVALID_ARGUMENT;
     static bool attr_set = false;
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -1420,27 +1399,23 @@ int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal
             attr_set = true;
         }
     }
-    const int tiles = (N + WG_KT - 1) / WG_KT;
+    const int tiles = (N + ROWS - 1) / ROWS * (ROWS / WG_KT);          // the planes are allocated in whole 128-row tiles
     int grid = sgs_deform_wgrad_max_ctas();
     if (grid < n_tasks) return SGS_ERR_INVALID_ARGUMENT;
     if ((long long)grid > (long long)n_tasks * tiles) grid = n_tasks * tiles;
     WParams p;
-    p.N = N; p.n_tasks = n_tasks;
+    p.tiles = tiles; p.n_tasks = n_tasks;
     float cost[WG_MAX_TASKS], total = 0.f;
     for (int i = 0; i < n_tasks; ++i) {
         const sgs_wgrad_task_t& t = tasks[i];
-        const int ldb = t.time_mode ? feat_dim : t.ldb;
-        if (!t.A || !t.B || ldb <= 0 || (ldb & 7) || ldb > 128 || t.time_mode < 0 || t.time_mode > 2 ||
-            (t.time_mode == 1 && !temporal_pos) || ((reinterpret_cast<size_t>(t.A) | reinterpret_cast<size_t>(t.B)) & 31) ||
-            !t.dW || t.rows <= 0 || t.rows > 128)
+        if (!t.A || !t.B || (t.groups_b != 2 && t.groups_b != 6 && t.groups_b != 16) ||
+            ((reinterpret_cast<size_t>(t.A) | reinterpret_cast<size_t>(t.B)) & 15) || !t.dW || t.rows <= 0 || t.rows > 128 ||
+            t.cols <= 0 || t.cols > t.groups_b * 8)
             return SGS_ERR_INVALID_ARGUMENT;
         WTask& w = p.tasks[i];
-        w.A = t.A; w.B = t.B; w.ldb = ldb; w.tpos = temporal_pos; w.timestamp = timestamp; w.time_mode = t.time_mode;
-        w.real_groups = (ldb >> 3) + (t.time_mode ? 2 : 0);
-        w.ones_group = t.db ? w.real_groups : -1;
-        w.ngroups = (w.real_groups + (t.db ? 1 : 0) + 1) & ~1;
-        if (w.ngroups > WG_NG_MAX || t.cols > w.real_groups * 8) return SGS_ERR_INVALID_ARGUMENT;
-        cost[i] = 128.f + (float)ldb;
+        w.A = reinterpret_cast<const uint8_t*>(t.A); w.B = reinterpret_cast<const uint8_t*>(t.B);
+        w.gb = t.groups_b; w.bias = t.db != nullptr;
+        cost[i] = 16.f + (float)t.groups_b + 4.f;      // bytes per tile, plus a constant for the per-tile MMA issue
         total += cost[i];
     }
     int given = 0;
@@ -1473,7 +1448,7 @@ int sgs_deform_wgrad(int N, int feat_dim, float timestamp, const float* temporal
             WReduceTask& q = r.tasks[r.n_tasks++];
             q.partial = p.tasks[i].partial; q.count = p.tasks[i].cta_count;
             q.dW = tasks[i].dW; q.ldw = tasks[i].ldw; q.rows = tasks[i].rows; q.cols = tasks[i].cols; q.transposed = tasks[i].transposed;
-            q.db = tasks[i].db; q.bias_col = p.tasks[i].ones_group * 8; q.accumulate = pass;
+            q.db = tasks[i].db; q.bias_col = WG_BIAS_COL; q.accumulate = pass;
         }
         if (r.n_tasks > 0) deform_wgrad_reduce_kernel<<<r.n_tasks * 128, 160, 0, s>>>(r);
     }

@@ -11,8 +11,6 @@ and ``renderer/__init__.py:190`` runs on the fused tcgen05 kernel unchanged.  Al
 memory and the current stream only.  There is no PyTorch fallback: CPU tensors, other dtypes or an unsupported
 configuration raise.
 """
-import ctypes
-
 import torch
 
 from . import _lib
@@ -245,14 +243,6 @@ class TrainImages:
         self.versions = cur
 
 
-def _time_embedding(d):
-    """get_embedder(4) on d [N,1] (saro_gaussian.py:922-969): [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d]"""
-    cols = [d]
-    for f in (1.0, 2.0, 4.0, 8.0):
-        cols += [torch.sin(d * f), torch.cos(d * f)]
-    return torch.cat(cols, dim=1)
-
-
 _phase_marks = None      # bench.py sets this to a list to collect (name, CUDA event) marks of the backward's phases
 
 
@@ -279,25 +269,31 @@ class _TrainMLPs(torch.autograd.Function):
         outs, keep = [], []
         arr = (_lib.MLPJob * len(jobs))()
         f32 = dict(dtype=torch.float32, device=dev)
+        planes = lambda groups: torch.empty(lib.sgs_deform_planes_bytes(n, groups), dtype=torch.uint8, device=dev)
+        x_planes = {}                                        # the MLP input is the same for every job of a time mode
         for k, (m, zero_time, diff) in enumerate(jobs):
             n_out = images.shapes[m][2]
             out = torch.empty((n, n_out), **f32)
             outs.append(out)
-            save = want and diff
-            h1 = torch.empty((n, HIDDEN), **f32) if save else None
-            h2 = torch.empty((n, HIDDEN), **f32) if save else None
+            save = want and diff and n > 0
+            h1 = planes(16) if save else None
+            h2 = planes(16) if save else None
             m1 = torch.empty((n, 4), dtype=torch.int32, device=dev) if save else None
             m2 = torch.empty((n, 4), dtype=torch.int32, device=dev) if save else None
-            keep.append((h1, h2, m1, m2))
+            xin = None
+            if save and bool(zero_time) not in x_planes:
+                xin = x_planes[bool(zero_time)] = planes(6)
+            keep.append((h1, h2, m1, m2, bool(zero_time)))
             p0 = lambda t: t.data_ptr() if t is not None else None
-            arr[k] = _lib.MLPJob(images.image(m, 0), None, out.data_ptr(), p0(h1), p0(h2), p0(m1), p0(m2), n_out, int(zero_time))
+            arr[k] = _lib.MLPJob(images.image(m, 0), None, out.data_ptr(), p0(h1), p0(h2), p0(xin), p0(m1), p0(m2), n_out,
+                                 int(zero_time))
         if n > 0:
             with torch.cuda.device(dev):
                 rc = lib.sgs_deform_train_forward(n, F, float(timestamp), tpos_c.data_ptr(), feat_c.data_ptr(), len(jobs), arr,
                                                   torch.cuda.current_stream(dev).cuda_stream)
             if rc != 0:
                 raise RuntimeError(f"sgs_deform_train_forward failed ({rc}): {_lib.last_error()}")
-        ctx.jobs, ctx.images, ctx.keep, ctx.timestamp = jobs, images, keep, float(timestamp)
+        ctx.jobs, ctx.images, ctx.keep, ctx.x_planes = jobs, images, keep, x_planes
         ctx.save_for_backward(feat_c, tpos_c, *params)
         ctx.mark_non_differentiable(*[o for o, (_, _, diff) in zip(outs, jobs) if not diff])
         return tuple(outs)
@@ -315,17 +311,18 @@ class _TrainMLPs(torch.autograd.Function):
         if not live or n == 0:
             return (torch.zeros_like(feat) if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
         _mark("bwd_begin")
+        planes = lambda groups: torch.empty(lib.sgs_deform_planes_bytes(n, groups), dtype=torch.uint8, device=dev)
         arr = (_lib.MLPJob * len(live))()
         slabs = torch.empty((len(live), n, F), **f32)
         work = []
         for i, k in enumerate(live):
             m, zero_time, _ = jobs[k]
-            h1, h2, m1, m2 = keep[k]
+            h1, h2, m1, m2, zt = keep[k]
             dy = gouts[k].contiguous()
-            dh2 = torch.empty((n, HIDDEN), **f32)
-            dh1 = torch.empty((n, HIDDEN), **f32)
-            work.append((m, zero_time, dy, h1, h2, dh1, dh2))
-            arr[i] = _lib.MLPJob(images.image(m, 1), dy.data_ptr(), slabs[i].data_ptr(), dh2.data_ptr(), dh1.data_ptr(),
+            dh2, dh1 = planes(16), planes(16)
+            dyp = planes(6 if dy.shape[1] > 8 else 2)
+            work.append((m, zt, dy, dyp, h1, h2, dh1, dh2))
+            arr[i] = _lib.MLPJob(images.image(m, 1), dy.data_ptr(), slabs[i].data_ptr(), dh2.data_ptr(), dh1.data_ptr(), dyp.data_ptr(),
                                  m2.data_ptr(), m1.data_ptr(), dy.shape[1], 0)
         with torch.cuda.device(dev):
             rc = lib.sgs_deform_train_backward(n, F, len(live), arr, torch.cuda.current_stream(dev).cuda_stream)
@@ -333,32 +330,28 @@ class _TrainMLPs(torch.autograd.Function):
             raise RuntimeError(f"sgs_deform_train_backward failed ({rc}): {_lib.last_error()}")
         _mark("data_gradient_kernel")
         dfeat = slabs.sum(dim=0) if len(live) > 1 else slabs[0]
-        # weight gradients: one tcgen05 launch for all (job, layer) GEMMs dW = G^T X over the rows (the first layer's X =
-        # [feature | time embedding] is rebuilt inside the kernel; bias gradients ride along as a constant-one column),
-        # then a deterministic reduction of the per-CTA partials straight into parameter-shaped tensors.  A second
-        # evaluation of the same MLP (base feature) accumulates.
+        # weight gradients: one TMA + tcgen05 launch for all (job, layer) GEMMs dW = G^T X over the rows — both operands
+        # of every GEMM are operand planes the forward / data-gradient kernels emitted — then a deterministic reduction
+        # of the per-CTA partials straight into parameter-shaped tensors.  A second evaluation of the same MLP (base
+        # feature) accumulates.
         out = {}
-        tasks, hold = [], []
-        for m, zero_time, dy, h1, h2, dh1, dh2 in work:
+        tasks = []
+        for m, zt, dy, dyp, h1, h2, dh1, dh2 in work:
             w_in, hid2, n_out = images.shapes[m]
             acc = int(m in out)
             if not acc:
                 out[m] = [torch.empty((HIDDEN, w_in), **f32), torch.empty(HIDDEN, **f32), torch.empty((hid2, HIDDEN), **f32),
                           torch.empty(hid2, **f32), torch.empty((n_out, hid2), **f32), None]
             dW1, db1, dW2, db2, dW3, _ = out[m]
-            dyp = dy if n_out == 48 else torch.nn.functional.pad(dy, (0, 8 - n_out))
-            hold.append(dyp)
-            mode = 0 if w_in == F else (2 if zero_time else 1)
-            tasks += [_lib.WgradTask(dh1.data_ptr(), feat.data_ptr(), F, mode, dW1.data_ptr(), w_in, HIDDEN, w_in, 0, db1.data_ptr(), acc),
-                      _lib.WgradTask(dh2.data_ptr(), h1.data_ptr(), HIDDEN, 0, dW2.data_ptr(), HIDDEN, hid2, HIDDEN, 0, db2.data_ptr(), acc),
-                      _lib.WgradTask(h2.data_ptr(), dyp.data_ptr(), dyp.shape[1], 0, dW3.data_ptr(), hid2, hid2, n_out, 1, None, acc)]
+            tasks += [_lib.WgradTask(dh1.data_ptr(), ctx.x_planes[zt].data_ptr(), 6, dW1.data_ptr(), w_in, HIDDEN, w_in, 0, db1.data_ptr(), acc),
+                      _lib.WgradTask(dh2.data_ptr(), h1.data_ptr(), 16, dW2.data_ptr(), HIDDEN, hid2, HIDDEN, 0, db2.data_ptr(), acc),
+                      _lib.WgradTask(h2.data_ptr(), dyp.data_ptr(), 6 if n_out > 8 else 2, dW3.data_ptr(), hid2, hid2, n_out, 1, None, acc)]
             db3 = dy.sum(0)
             out[m][5] = db3 if out[m][5] is None else out[m][5] + db3
         arr_w = (_lib.WgradTask * len(tasks))(*tasks)
         partials = torch.empty(lib.sgs_deform_wgrad_max_ctas() * lib.sgs_deform_wgrad_partial_floats(), **f32)
         with torch.cuda.device(dev):
-            rc = lib.sgs_deform_wgrad(n, F, ctx.timestamp, tpos.data_ptr(), len(tasks), arr_w, partials.data_ptr(),
-                                      torch.cuda.current_stream(dev).cuda_stream)
+            rc = lib.sgs_deform_wgrad(n, len(tasks), arr_w, partials.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"sgs_deform_wgrad failed ({rc}): {_lib.last_error()}")
         for m, gs in out.items():

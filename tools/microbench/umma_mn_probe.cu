@@ -5,7 +5,11 @@
 // (an 8 x 8 core matrix = 8 k-rows of 16 bytes, 8 consecutive mn each), MNSTRIDE = K * 16.
 // Pins which descriptor field carries which stride, and the two "major" bits of the instruction descriptor.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o umma_mn_probe umma_mn_probe.cu
-//   ./umma_mn_probe N K variant      variant 0: LBO field = k-block stride (128), SBO field = mn-block stride; 1: swapped
+//   ./umma_mn_probe N K variant [reps]
+//      variant 0: no swizzle, LBO field = k-block stride (128), SBO field = mn-block stride; 1: the two swapped
+//      variant 2: 128-byte swizzle — element (mn, k) at (mn % 8) * 2 + (((mn / 8) % 8) ^ (k % 8)) * 16 + (k % 8) * 128 +
+//                 (k / 8) * 1024 + (mn / 64) * (K / 8) * 1024, LBO field = 64-column block stride, SBO field = 1024; 3: swapped
+//      reps > 1 prints the clocks of one K/16-step MMA chain + commit + wait
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -24,21 +28,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // A: [K][128] row-major bf16 (k = row), B: [K][N] row-major bf16
 __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
-                                             float* __restrict__ D, int N, int K, int variant) {
+                                             float* __restrict__ D, int N, int K, int variant, int reps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t mnstride = (uint32_t)K * 16;
+    const bool sw = variant >= 2;
+    const uint32_t mnstride = (uint32_t)K * 16;          // no swizzle: bytes between groups of 8 columns
+    const uint32_t blk = (uint32_t)(K / 8) * 1024;       // swizzled: bytes between blocks of 64 columns
     uint8_t* sA = smem;
-    uint8_t* sB = smem + 16 * mnstride;
+    uint8_t* sB = smem + (sw ? 2 * blk : 16 * mnstride);
+    auto offset = [&](int k, int g) -> uint32_t {
+        return sw ? (uint32_t)(g / 8) * blk + (k / 8) * 1024 + (k % 8) * 128 + ((g % 8) ^ (k % 8)) * 16
+                  : (uint32_t)g * mnstride + (k / 8) * 128 + (k % 8) * 16;
+    };
     for (int u = tid; u < K * 16; u += 128) {          // unit = (row k, group of 8 columns)
         const int k = u / 16, g = u % 16;
-        *reinterpret_cast<uint4*>(sA + g * mnstride + (k / 8) * 128 + (k % 8) * 16) = *reinterpret_cast<const uint4*>(A + (size_t)k * 128 + g * 8);
+        *reinterpret_cast<uint4*>(sA + offset(k, g)) = *reinterpret_cast<const uint4*>(A + (size_t)k * 128 + g * 8);
     }
     for (int u = tid; u < K * (N / 8); u += 128) {
         const int k = u / (N / 8), g = u % (N / 8);
-        *reinterpret_cast<uint4*>(sB + g * mnstride + (k / 8) * 128 + (k % 8) * 16) = *reinterpret_cast<const uint4*>(B + (size_t)k * N + g * 8);
+        *reinterpret_cast<uint4*>(sB + offset(k, g)) = *reinterpret_cast<const uint4*>(B + (size_t)k * N + g * 8);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
@@ -55,23 +65,33 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* __restrict__ A
     const uint32_t tmem = tmem_base_s;
     // D = f32, A = B = bf16, A and B MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    if (tid == 0) {
-        for (int ks = 0; ks < K / 16; ++ks) {
-            const uint32_t a = smem_u32(sA) + ks * 256, b = smem_u32(sB) + ks * 256;      // 16 k = two 128-byte k-blocks
-            const uint64_t da = variant == 0 ? make_desc(a, 128, mnstride) : make_desc(a, mnstride, 128);
-            const uint64_t db = variant == 0 ? make_desc(b, 128, mnstride) : make_desc(b, mnstride, 128);
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                         :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+    uint32_t phase = 0;
+    const long long c_start = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+        if (tid == 0) {
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t step = sw ? 2048u : 256u;                       // 16 k = two k-blocks
+                const uint32_t a = smem_u32(sA) + ks * step, b = smem_u32(sB) + ks * step;
+                uint64_t da, db;
+                if (variant == 0) { da = make_desc(a, 128, mnstride); db = make_desc(b, 128, mnstride); }
+                else if (variant == 1) { da = make_desc(a, mnstride, 128); db = make_desc(b, mnstride, 128); }
+                else if (variant == 2) { da = make_desc(a, blk, 1024) | ((uint64_t)2 << 61); db = make_desc(b, blk, 1024) | ((uint64_t)2 << 61); }
+                else { da = make_desc(a, 1024, blk) | ((uint64_t)2 << 61); db = make_desc(b, 1024, blk) | ((uint64_t)2 << 61); }
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+        uint32_t done = 0;
+        for (long long spin = 0; !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+            if (spin > (1ll << 22)) { if (tid == 0) printf("mbarrier wait timed out\n"); __trap(); }
+        }
+        phase ^= 1;
     }
-    uint32_t done = 0;
-    for (long long spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
-        if (spin > (1ll << 22)) { if (tid == 0) printf("mbarrier wait timed out\n"); __trap(); }
-    }
+    if (tid == 0 && reps > 1) printf("  clocks per %d-MMA chain + commit + wait: %.1f\n", K / 16, double(clock64() - c_start) / reps);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int c0 = 0; c0 < N; c0 += 8) {
         uint32_t v[8];
@@ -88,6 +108,7 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* __restrict__ A
 
 int main(int argc, char** argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 128, K = argc > 2 ? atoi(argv[2]) : 64, variant = argc > 3 ? atoi(argv[3]) : 0;
+    const int reps = argc > 4 ? atoi(argv[4]) : 1;
     std::vector<__nv_bfloat16> hA(K * 128), hB(K * N);
     std::vector<float> fA(K * 128), fB(K * N);
     srand(11);
@@ -98,9 +119,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemset(dD, 0xFF, 128 * N * 4));
-    const size_t smem = (size_t)(16 + N / 8) * K * 16 + 1024;
+    const size_t smem = variant >= 2 ? (size_t)(2 + (N + 63) / 64) * (K / 8) * 1024 + 1024 : (size_t)(16 + N / 8) * K * 16 + 1024;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    probe<<<1, 128, smem>>>(dA, dB, dD, N, K, variant);
+    probe<<<1, 128, smem>>>(dA, dB, dD, N, K, variant, reps);
     CK(cudaGetLastError());
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N=%d K=%d variant=%d: kernel failed: %s\n", N, K, variant, cudaGetErrorString(e)); return 1; }
