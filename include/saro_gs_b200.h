@@ -279,6 +279,25 @@ int sgs_deform_wgrad_max_ctas(void);
 size_t sgs_deform_wgrad_partial_floats(void);
 int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* partials, void* stream);
 
+/* Elementwise epilogues of the training-time deformation (scene/saro_gaussian.py:782-831), forward and backward, one
+ * launch each instead of ~25 PyTorch kernels: lifespan = (1 - min_scale) (1 - sigmoid(life_raw)) + min_scale;
+ * opacity = sigmoid(opacity) exp(-4 ((timestamp - temporal_pos) / lifespan)^2); rotations = normalize(rotation +
+ * rot_raw[:, :4]) (eps 1e-12); scales = exp(scaling + rot_raw[:, 4:]); means3D = xyz + motion_raw; real_xyz = xyz +
+ * motion_base_raw (skipped when motion_base_raw is NULL).  Raw MLP outputs are [N][1], [N][3], [N][7], [N][3].
+ * Backward: gradients of the five outputs (any g_* may be NULL = no gradient) -> d life_raw [N], d rot_raw [N][7],
+ * d rotation [N][4], d scaling [N][3], d opacity [N], d temporal_pos [N]; the gradients of xyz and motion_raw are the
+ * incoming means3D gradient itself.  Device float32, contiguous.  Return 0 or a negative error code. */
+int sgs_deform_train_epilogue_forward(int N, float timestamp, float min_scale, const float* life_raw, const float* motion_raw,
+                                      const float* rot_raw, const float* motion_base_raw, const float* xyz, const float* rotation,
+                                      const float* scaling, const float* opacity, const float* temporal_pos, float* out_means3D,
+                                      float* out_rotations, float* out_scales, float* out_opacity, float* out_lifespan,
+                                      float* out_real_xyz, void* stream);
+int sgs_deform_train_epilogue_backward(int N, float timestamp, float min_scale, const float* life_raw, const float* rot_raw,
+                                       const float* rotation, const float* scaling, const float* opacity, const float* temporal_pos,
+                                       const float* g_rotations, const float* g_scales, const float* g_opacity,
+                                       const float* g_lifespan, float* d_life_raw, float* d_rot_raw, float* d_rotation,
+                                       float* d_scaling, float* d_opacity, float* d_temporal_pos, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Densification statistics of one training iteration — replaces the per-view lists and
  * the batch reduction of the reference's train.py:192-218 and :281-292 (with scene/saro_gaussian.py:745-747).

@@ -57,6 +57,8 @@ ABI = {
     "sgs_deform_wgrad_partial_floats": (ctypes.c_size_t, []),
     "sgs_deform_wgrad": (_i, [_i, _i, _vp, _vp, _vp]),
     "sgs_deform_planes_bytes": (ctypes.c_size_t, [_i, _i]),
+    "sgs_deform_train_epilogue_forward": (_i, [_i, _f, _f] + [_vp] * 15 + [_vp]),
+    "sgs_deform_train_epilogue_backward": (_i, [_i, _f, _f] + [_vp] * 16 + [_vp]),
     "sgs_densify_add_view": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_densify_attach": (_i, [_i, _vp, _vp, _vp]),
     "sgs_densify_commit": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1149,6 +1149,95 @@ __global__ void __launch_bounds__(160) deform_wgrad_reduce_kernel(const __grid_c
     *dst = t.accumulate ? *dst + sum : sum;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Elementwise epilogues of the training path (scene/saro_gaussian.py:782-831), one thread per Gaussian, forward and
+// backward: lifespan from the opacity_mlp output, survival state, opacity, rotation, scale, position, real_xyz.  In the
+// reference these are ~25 PyTorch kernels forward and as many in autograd's backward, each over a few bytes per Gaussian.
+struct EpiParams {
+    int N;
+    float timestamp, min_scale;
+    const float *life_raw, *motion_raw, *rot_raw, *motion_base_raw;      // MLP outputs [N][1], [N][3], [N][7], [N][3] (may be NULL)
+    const float *xyz, *rotation, *scaling, *opacity, *tpos;              // model parameters / get_temporalpos
+    float *o_motion, *o_rot, *o_scale, *o_opacity, *o_lifespan, *o_real_xyz;
+    // backward
+    const float *g_motion, *g_rot, *g_scale, *g_opacity, *g_lifespan;    // any may be NULL (no gradient arrived)
+    float *d_life_raw, *d_rot_raw, *d_rotation, *d_scaling, *d_opacity, *d_tpos;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) deform_epilogue_fwd_kernel(const __grid_constant__ EpiParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N) return;
+    // :782-785  lifespan = (1 - min_scale) * (1 - sigmoid(z)) + min_scale
+    const float life = (1.f - p.min_scale) * (1.f - sigmoidf_(p.life_raw[i])) + p.min_scale;
+    p.o_lifespan[i] = life;
+    // :788-789, :757-759  state = exp(-4 ((t - tpos) / lifespan)^2);  :830-831 opacity = sigmoid(o) * state
+    const float u = (p.timestamp - p.tpos[i]) / life;
+    p.o_opacity[i] = sigmoidf_(p.opacity[i]) * expf(-4.f * (u * u));
+    float q[4], nrm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float x = p.xyz[(size_t)i * 3 + c];
+        p.o_motion[(size_t)i * 3 + c] = x + p.motion_raw[(size_t)i * 3 + c];                               // :807-809
+        if (p.motion_base_raw) p.o_real_xyz[(size_t)i * 3 + c] = x + p.motion_base_raw[(size_t)i * 3 + c];  // :803-804
+        p.o_scale[(size_t)i * 3 + c] = expf(p.scaling[(size_t)i * 3 + c] + p.rot_raw[(size_t)i * 7 + 4 + c]);   // :819-821
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        q[c] = p.rotation[(size_t)i * 4 + c] + p.rot_raw[(size_t)i * 7 + c];                               // :813-817
+        nrm += q[c] * q[c];
+    }
+    nrm = fmaxf(sqrtf(nrm), 1e-12f);                                                                        // F.normalize eps
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p.o_rot[(size_t)i * 4 + c] = q[c] / nrm;
+}
+
+__global__ void __launch_bounds__(256) deform_epilogue_bwd_kernel(const __grid_constant__ EpiParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N) return;
+    // ---- opacity / lifespan / temporal position
+    const float sz = sigmoidf_(p.life_raw[i]);
+    const float life = (1.f - p.min_scale) * (1.f - sz) + p.min_scale;
+    const float d = p.timestamp - p.tpos[i];
+    const float u = d / life;
+    const float state = expf(-4.f * (u * u));
+    const float so = sigmoidf_(p.opacity[i]);
+    const float g_op = p.g_opacity ? p.g_opacity[i] : 0.f;
+    p.d_opacity[i] = g_op * state * so * (1.f - so);
+    const float g_u = g_op * so * state * (-8.f * u);
+    p.d_tpos[i] = -(g_u / life);
+    const float g_life = -g_u * u / life + (p.g_lifespan ? p.g_lifespan[i] : 0.f);
+    p.d_life_raw[i] = g_life * (1.f - p.min_scale) * (-(sz * (1.f - sz)));
+    // ---- rotation: y = q / max(|q|, eps)  ->  dq = (g - (g . y) y) / |q|
+    float q[4], g[4], nrm = 0.f, gy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        q[c] = p.rotation[(size_t)i * 4 + c] + p.rot_raw[(size_t)i * 7 + c];
+        g[c] = p.g_rot ? p.g_rot[(size_t)i * 4 + c] : 0.f;
+        nrm += q[c] * q[c];
+    }
+    nrm = sqrtf(nrm);
+    const float den = fmaxf(nrm, 1e-12f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gy += g[c] * (q[c] / den);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float dq = nrm > 1e-12f ? (g[c] - gy * (q[c] / den)) / den : g[c] / den;     // below eps the divisor is the constant
+        p.d_rotation[(size_t)i * 4 + c] = dq;
+        p.d_rot_raw[(size_t)i * 7 + c] = dq;
+    }
+    // ---- scale: y = exp(s)  ->  ds = g y
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float y = expf(p.scaling[(size_t)i * 3 + c] + p.rot_raw[(size_t)i * 7 + 4 + c]);
+        const float ds = (p.g_scale ? p.g_scale[(size_t)i * 3 + c] : 0.f) * y;
+        p.d_scaling[(size_t)i * 3 + c] = ds;
+        p.d_rot_raw[(size_t)i * 7 + 4 + c] = ds;
+    }
+}
+
 std::mutex g_mu;
 int* g_pinned_count = nullptr;
 cudaEvent_t g_count_ready = nullptr;
@@ -1452,6 +1541,49 @@ int sgs_deform_wgrad(int N, int n_tasks, const sgs_wgrad_task_t* tasks, float* p
         }
         if (r.n_tasks > 0) deform_wgrad_reduce_kernel<<<r.n_tasks * 128, 160, 0, s>>>(r);
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
+}
+
+
+int sgs_deform_train_epilogue_forward(int N, float timestamp, float min_scale, const float* life_raw, const float* motion_raw,
+                                      const float* rot_raw, const float* motion_base_raw, const float* xyz, const float* rotation,
+                                      const float* scaling, const float* opacity, const float* temporal_pos, float* out_means3D,
+                                      float* out_rotations, float* out_scales, float* out_opacity, float* out_lifespan,
+                                      float* out_real_xyz, void* stream) {
+    using namespace sgs_deform;
+    if (N < 0) return SGS_ERR_INVALID_ARGUMENT;
+    if (N == 0) return 0;
+    if (!life_raw || !motion_raw || !rot_raw || !xyz || !rotation || !scaling || !opacity || !temporal_pos || !out_means3D ||
+        !out_rotations || !out_scales || !out_opacity || !out_lifespan || (motion_base_raw && !out_real_xyz))
+        return SGS_ERR_INVALID_ARGUMENT;
+    EpiParams p = {};
+    p.N = N; p.timestamp = timestamp; p.min_scale = min_scale;
+    p.life_raw = life_raw; p.motion_raw = motion_raw; p.rot_raw = rot_raw; p.motion_base_raw = motion_base_raw;
+    p.xyz = xyz; p.rotation = rotation; p.scaling = scaling; p.opacity = opacity; p.tpos = temporal_pos;
+    p.o_motion = out_means3D; p.o_rot = out_rotations; p.o_scale = out_scales; p.o_opacity = out_opacity;
+    p.o_lifespan = out_lifespan; p.o_real_xyz = out_real_xyz;
+    deform_epilogue_fwd_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
+}
+
+int sgs_deform_train_epilogue_backward(int N, float timestamp, float min_scale, const float* life_raw, const float* rot_raw,
+                                       const float* rotation, const float* scaling, const float* opacity, const float* temporal_pos,
+                                       const float* g_rotations, const float* g_scales, const float* g_opacity,
+                                       const float* g_lifespan, float* d_life_raw, float* d_rot_raw, float* d_rotation,
+                                       float* d_scaling, float* d_opacity, float* d_temporal_pos, void* stream) {
+    using namespace sgs_deform;
+    if (N < 0) return SGS_ERR_INVALID_ARGUMENT;
+    if (N == 0) return 0;
+    if (!life_raw || !rot_raw || !rotation || !scaling || !opacity || !temporal_pos || !d_life_raw || !d_rot_raw || !d_rotation ||
+        !d_scaling || !d_opacity || !d_temporal_pos)
+        return SGS_ERR_INVALID_ARGUMENT;
+    EpiParams p = {};
+    p.N = N; p.timestamp = timestamp; p.min_scale = min_scale;
+    p.life_raw = life_raw; p.rot_raw = rot_raw; p.rotation = rotation; p.scaling = scaling; p.opacity = opacity; p.tpos = temporal_pos;
+    p.g_rot = g_rotations; p.g_scale = g_scales; p.g_opacity = g_opacity; p.g_lifespan = g_lifespan;
+    p.d_life_raw = d_life_raw; p.d_rot_raw = d_rot_raw; p.d_rotation = d_rotation; p.d_scaling = d_scaling; p.d_opacity = d_opacity;
+    p.d_tpos = d_temporal_pos;
+    deform_epilogue_bwd_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : SGS_ERR_CUDA;
 }
 

@@ -363,12 +363,65 @@ class _TrainMLPs(torch.autograd.Function):
         return (dfeat if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
+class _TrainEpilogue(torch.autograd.Function):
+    """The elementwise statements between the MLP outputs and the rasterizer's inputs (scene/saro_gaussian.py:782-831)
+    as one kernel forward and one backward.  Returns (means3D, rotations, scales, opacity, lifespan, real_xyz)."""
+
+    @staticmethod
+    def forward(ctx, timestamp, min_scale, life_raw, motion_raw, rot_raw, motion_base_raw, xyz, rotation, scaling, opacity, tpos):
+        lib = _lib.load()
+        n = xyz.shape[0]
+        dev = xyz.device
+        c = lambda t, name, tail: _check(t, name, tail, n)
+        ins = (c(life_raw, "lifespan MLP output", [(1,)]), c(motion_raw, "motion MLP output", [(3,)]), c(rot_raw, "rot MLP output", [(7,)]),
+               c(motion_base_raw, "motion MLP output (base)", [(3,)]), c(xyz, "xyz", [(3,)]), c(rotation, "rotation", [(4,)]),
+               c(scaling, "scaling", [(3,)]), c(opacity, "opacity", [(1,), ()]), c(tpos, "temporal_pos", [(1,), ()]))
+        f32 = dict(dtype=torch.float32, device=dev)
+        outs = (torch.empty((n, 3), **f32), torch.empty((n, 4), **f32), torch.empty((n, 3), **f32), torch.empty((n, 1), **f32),
+                torch.empty((n, 1), **f32), torch.empty((n, 3), **f32))
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = lib.sgs_deform_train_epilogue_forward(n, float(timestamp), float(min_scale), *[t.data_ptr() for t in ins],
+                                                           *[t.data_ptr() for t in outs], torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"sgs_deform_train_epilogue_forward failed ({rc}): {_lib.last_error()}")
+        ctx.consts = (float(timestamp), float(min_scale), tuple(opacity.shape), tuple(tpos.shape))
+        ctx.save_for_backward(ins[0], ins[2], ins[5], ins[6], ins[7], ins[8])
+        ctx.mark_non_differentiable(outs[5])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_motion, g_rot, g_scale, g_op, g_life, _g_real):
+        lib = _lib.load()
+        life_raw, rot_raw, rotation, scaling, opacity, tpos = ctx.saved_tensors
+        timestamp, min_scale, op_shape, tpos_shape = ctx.consts
+        n = rotation.shape[0]
+        dev = rotation.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_life, d_rot_raw = torch.empty((n, 1), **f32), torch.empty((n, 7), **f32)
+        d_rotation, d_scaling = torch.empty((n, 4), **f32), torch.empty((n, 3), **f32)
+        d_opacity, d_tpos = torch.empty(op_shape, **f32), torch.empty(tpos_shape, **f32)
+        gs = [None if g is None else g.contiguous() for g in (g_rot, g_scale, g_op, g_life)]
+        if n > 0:
+            with torch.cuda.device(dev):
+                rc = lib.sgs_deform_train_epilogue_backward(
+                    n, timestamp, min_scale, life_raw.data_ptr(), rot_raw.data_ptr(), rotation.data_ptr(), scaling.data_ptr(),
+                    opacity.data_ptr(), tpos.data_ptr(), *[None if g is None else g.data_ptr() for g in gs], d_life.data_ptr(),
+                    d_rot_raw.data_ptr(), d_rotation.data_ptr(), d_scaling.data_ptr(), d_opacity.data_ptr(), d_tpos.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"sgs_deform_train_epilogue_backward failed ({rc}): {_lib.last_error()}")
+        # means3D = xyz + motion_raw: both gradients are the incoming one
+        return (None, None, d_life, g_motion, d_rot_raw, None, g_motion, d_rotation, d_scaling, d_opacity, d_tpos)
+
+
 def get_deformation(self, timestamp, rays=None):
     """Drop-in for GaussianModel.get_deformation (scene/saro_gaussian.py:779-847): same side effects (`_lifespan`,
     `scale_residual`, `shs_residual`, `motion_residual`, `real_xyz`), same return order.  The plane field is whatever
     module the model carries (`saro_gs_b200.hexplane.ScaleAwareResField` for the native sampler); the seven MLP
-    evaluations and their backward run in the tcgen05 kernels of csrc/sgs_deform.cu; the residual adds and activations
-    are the reference's own elementwise statements."""
+    evaluations and their backward run in the tcgen05 kernels of csrc/sgs_deform.cu, the elementwise statements between
+    them and the returned tensors in one kernel forward and one backward (`_TrainEpilogue`); only the SH residual add
+    (`cat` + add) is left to PyTorch."""
     args = self.args
     if not (args.dx and args.drot and args.dopacity and args.dsh):
         raise UnsupportedDeformationConfig(
@@ -394,24 +447,21 @@ def get_deformation(self, timestamp, rays=None):
     outs = dict(zip(names, _TrainMLPs.apply(hexplane_feature, self.get_temporalpos.detach(), timestamp, tuple(jobs), images,
                                             *images.params())))
 
-    lifespan = 1 - torch.sigmoid(outs["life"])                                            # :782 (opacity_mlp ends in Sigmoid)
-    min_scale = self.args.min_interval / (self.duration)
-    lifespan = (1 - min_scale) * lifespan + min_scale
+    if self.rotation_activation is not torch.nn.functional.normalize or self.scaling_activation is not torch.exp or \
+            self.opacity_activation is not torch.sigmoid:
+        raise UnsupportedDeformationConfig("the fused epilogue implements the reference's activations (normalize, exp, sigmoid; "
+                                           "scene/saro_gaussian.py:39-47)")
+    min_scale = self.args.min_interval / (self.duration)                                  # :783
+    motion, rot, scale, opacity, lifespan, real_xyz = _TrainEpilogue.apply(
+        timestamp, min_scale, outs["life"], outs["motion"], outs["rot"], outs["motion_base"], self._xyz, self._rotation,
+        self._scaling, self._opacity, self.get_temporalpos)                               # :782-831 in one kernel
     self._lifespan = lifespan
-    distance = timestamp - self.get_temporalpos                                           # :788
-    trbfoutput = self.get_survival_state(distance / lifespan)
     if args.scale_reg:
         self.scale_residual = outs["rot_base"][:, 4:]
     if args.shs_reg:
         self.shs_residual = outs["shs_base"].reshape(-1, 16, 3)
     if args.motion_reg:
         self.motion_residual = outs["motion_base"]
-    with torch.no_grad():
-        self.real_xyz = self._xyz + outs["motion_base"].detach()                          # :803-804
-    motion = self._xyz + outs["motion"]                                                   # :807-809
-    rot_residual = outs["rot"]
-    rot = self.rotation_activation(self._rotation + rot_residual[:, :4])                  # :813-817
-    scale = self.scaling_activation(self._scaling + rot_residual[:, 4:])                  # :819-821
-    opacity = self.opacity_activation(self._opacity) * trbfoutput                         # :830-831
+    self.real_xyz = real_xyz                                                              # :803-804 (no gradient)
     shs = torch.cat((self._features_dc, self._features_rest), dim=1) + outs["shs"].reshape(-1, 16, 3)   # :837-841
     return motion, rot, scale, opacity, shs
