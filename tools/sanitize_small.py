@@ -83,3 +83,20 @@ with torch.no_grad():
 _lib.load().sgs_debug_set_capacity(-1)
 torch.cuda.synchronize()
 print("relaunch ok", float(img.sum()))
+
+# training-time deformation (round 2c): tcgen05 job kernels forward + data gradients, TMA -> tcgen05 weight gradients,
+# fused epilogues, on small clouds (ragged tail, all regularisers / none)
+from oracle import deform_torch
+for P, F, flags in ((700, 32, (1, 0, 0)), (129, 16, (1, 1, 1)), (31, 8, (0, 0, 0))):
+    g = torch.Generator().manual_seed(P)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    t = dict(xyz=rn(P, 3) * 2, rotation=rn(P, 4), scaling=rn(P, 3) * 0.5 - 3.5, opacity=rn(P, 1) * 2, features_dc=rn(P, 1, 3) * 0.5,
+             features_rest=rn(P, 15, 3) * 0.1, temporal_pos=torch.rand(P, 1, generator=g), hexplane_feature=rn(P, F) * 0.5)
+    lv = {k: v.to(dev).requires_grad_(True) for k, v in t.items()}
+    mlps = deform_torch.make_train_mlps(F, device=dev, seed=P)
+    tpc = deform_torch.TrainModelStandIn(lv, mlps, flags, 6.0, 300.0)
+    outs = deformation.get_deformation(tpc, 0.4)
+    w = [torch.ones_like(o) for o in outs]
+    deform_torch.train_objective(tpc, outs, w, (0.3, 0.2, 0.1)).backward()
+    torch.cuda.synchronize()
+    print("deform train ok", P, F, float(lv["hexplane_feature"].grad.abs().sum()), float(mlps["shs"][2].weight.grad.abs().sum()))
