@@ -1,0 +1,95 @@
+"""The whole dynamic training iteration of SaRO-GS on native kernels (renderer/__init__.py:92-140 + train.py:199-226,
+helper_train.py:50-70): scale-aware plane sampler -> get_deformation -> rasterizer -> L1 + D-SSIM loss + the scale
+regulariser -> backward to the planes, the four MLPs and the Gaussians -> Adam.  Run twice from identical
+initialisation: once all native, once with the training-time deformation and the loss as the PyTorch ops the reference
+runs (oracle/deform_torch.py, pinned on the reference's own source; oracle/ssim_torch.py) — the plane sampler and the
+rasterizer are the native ones in both arms (nvdiffrast is not in this image; the rasterizer has its own loop test).
+The loss curves must agree: this is the in-situ check that the tcgen05 forward / data-gradient / weight-gradient
+kernels deliver the same training signal as autograd over the reference's statements."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(dev, P=4000, seed=5):
+    from saro_gs_b200 import synthetic
+    from saro_gs_b200.hexplane import ScaleAwareResField
+    from oracle import deform_torch
+    W, H, fx = 160, 120, 140.0
+    scene, _ = synthetic.small_scene(P=P, seed=seed, width=W, height=H, fx=fx)
+    g = torch.Generator().manual_seed(seed)
+    op = scene.opacities.clamp(1e-4, 1 - 1e-4)
+    leaves = dict(xyz=scene.means3D.clone(), rotation=scene.rotations.clone(), scaling=torch.log(scene.scales),
+                  opacity=torch.log(op / (1 - op)).reshape(P, 1), features_dc=scene.shs[:, :1, :].contiguous(),
+                  features_rest=scene.shs[:, 1:, :].contiguous(), temporal_pos=torch.rand(P, 1, generator=g))
+    leaves = {k: v.to(dev).requires_grad_(True) for k, v in leaves.items()}
+    cfg = {"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 16, "resolution": [32, 32, 32, 12]}
+    field = ScaleAwareResField(cfg, [1]).to(dev)
+    with torch.no_grad():
+        for p in field.grids[0]:
+            p.copy_((torch.randn(p.shape, generator=g) * 0.3).to(dev))
+    lo, hi = scene.means3D.min(0).values - 0.5, scene.means3D.max(0).values + 0.5
+    field.set_aabb(hi.tolist(), lo.tolist(), 30)
+    mlps = deform_torch.make_train_mlps(16, device=dev, seed=seed + 1)
+    with torch.no_grad():                                   # small residuals, as after the reference's initialisation
+        for name in ("motion", "rot", "shs"):
+            mlps[name][4].weight.mul_(0.05)
+            mlps[name][4].bias.mul_(0.05)
+    pc = deform_torch.TrainModelStandIn(leaves, mlps, (1, 0, 0), 6.0, 30.0, hexplane=field)
+    cams = [synthetic.yaw_camera(W, H, fx, yaw=0.06 * (k - 1), pivot=(0.0, 0.0, 3.0)) for k in range(3)]
+    return pc, leaves, mlps, field, cams
+
+
+def _run(deform_fn, loss_fn, dev, iters):
+    import saro_gs_b200 as sgs
+    pc, leaves, mlps, field, cams = _make(dev)
+    bg = torch.zeros(3, device=dev)
+    stamps = [0.2, 0.5, 0.8]
+
+    def render(model, cam, t, fn):
+        m, rot, sc, op, shs = fn(model, t)
+        rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix.to(dev),
+                                               cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+        return sgs.GaussianRasterizer(rs)(means3D=m, means2D=torch.zeros_like(m), opacities=op, shs=shs, scales=sc, rotations=rot)[0]
+
+    # targets: the same model with shifted colours and positions, rendered with the PyTorch-ops deformation
+    from oracle import deform_torch
+    tgt = _make(dev)[0]
+    with torch.no_grad():
+        tgt._xyz.add_(0.03 * torch.randn_like(tgt._xyz))
+        tgt._features_dc.add_(0.2)
+        targets = [render(tgt, c, t, deform_torch.torch_get_deformation).clone() for c, t in zip(cams, stamps)]
+    params = list(leaves.values()) + [p for m in mlps.values() for p in m.parameters()] + list(field.parameters())
+    opt = torch.optim.Adam([{"params": list(leaves.values()), "lr": 2e-3},
+                            {"params": [p for m in mlps.values() for p in m.parameters()], "lr": 1e-3},
+                            {"params": list(field.parameters()), "lr": 5e-3}], eps=1e-15)
+    curve = []
+    for it in range(iters):
+        k = it % 3
+        image = render(pc, cams[k], stamps[k], deform_fn)
+        loss = loss_fn(image, targets[k]) + 8e-6 * torch.linalg.vector_norm(pc.scale_residual, ord=2)     # helper_train.py:68-70
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        assert all(p.grad is not None for p in params), [i for i, p in enumerate(params) if p.grad is None]
+        opt.step()
+        curve.append(float(loss))
+    return curve
+
+
+def test_dynamic_training_iterations_native_vs_pytorch_ops(native_lib):
+    from saro_gs_b200 import deformation, loss_utils
+    from oracle import deform_torch
+    from oracle.ssim_torch import torch_l1_dssim_loss
+    dev = torch.device("cuda:0")
+    iters = 90
+    native = _run(deformation.get_deformation, lambda a, b: loss_utils.l1_dssim_loss(a, b, 0.2), dev, iters)
+    ops = _run(deform_torch.torch_get_deformation, lambda a, b: torch_l1_dssim_loss(a, b, 0.2), dev, iters)
+    first, last = sum(native[:3]) / 3, sum(native[-3:]) / 3
+    assert last < 0.8 * first, (first, last)                                  # the loop actually fits
+    assert abs(native[0] - ops[0]) <= 1e-5 * abs(ops[0]), (native[0], ops[0])  # identical start: same forward
+    # Adam amplifies rounding differences over the iterations (and the rasterizer's float atomics reorder): the curves
+    # must stay together, not bit-equal
+    worst = max(abs(a - b) / b for a, b in zip(native, ops))
+    assert worst < 0.02, (worst, native[-5:], ops[-5:])
+    assert abs(last - sum(ops[-3:]) / 3) < 0.01 * last
