@@ -18,6 +18,10 @@ SRC_DEFORM = os.path.join(ROOT, "tests", "abi", "deform_driver.c")
 EXE_DEFORM = os.path.join(ROOT, "tests", "abi", "_build", "deform_driver")
 
 
+SRC_TRAIN = os.path.join(ROOT, "tests", "abi", "deform_train_driver.c")
+EXE_TRAIN = os.path.join(ROOT, "tests", "abi", "_build", "deform_train_driver")
+
+
 def build_driver(SRC=SRC, EXE=EXE):
     from saro_gs_b200 import build as native_build
     lib = native_build.build(verbose=False)
@@ -38,6 +42,7 @@ def test_c_driver_compiles_against_the_header():
     """CPU: the header is valid C99 and every entry point the drivers use links against the built library."""
     assert os.path.exists(build_driver())
     assert os.path.exists(build_driver(SRC_DEFORM, EXE_DEFORM))
+    assert os.path.exists(build_driver(SRC_TRAIN, EXE_TRAIN))
 
 
 @pytest.mark.gpu
@@ -145,3 +150,59 @@ def test_c_driver_widened_rows_match_python_host_layer(tmp_path):
     stats.commit(m)
     for a, b in zip(c_stats, (m.max_radii2D, m.xyz_gradient_accum, m.denom)):
         assert np.array_equal(a, b.cpu().numpy().ravel())
+
+
+@pytest.mark.gpu
+def test_c_driver_training_deformation_matches_python_host_layer(tmp_path):
+    """One MLP evaluation of the training-time deformation from plain C — forward, data gradients, weight gradients,
+    with the operand planes and sign bits carried between the calls — == the Python host layer's autograd Function on
+    the same inputs (bit-equal: every kernel on this path is deterministic)."""
+    from oracle import deform_torch
+    from saro_gs_b200 import deformation
+    exe = build_driver(SRC_TRAIN, EXE_TRAIN)
+    dev = torch.device("cuda:0")
+    N, F, t = 1111, 32, 0.45
+    g = torch.Generator().manual_seed(17)
+    tpos = torch.rand(N, 1, generator=g)
+    feat = torch.randn(N, F, generator=g) * 0.5
+    dy = torch.randn(N, 7, generator=g)
+    mlps = deform_torch.make_train_mlps(F, seed=18)
+    rot = mlps["rot"]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<2if", N, F, t))
+        f.write(tpos.numpy().astype("<f4").tobytes())
+        f.write(feat.numpy().astype("<f4").tobytes())
+        for layer in (rot[0], rot[2], rot[4]):
+            f.write(layer.weight.detach().contiguous().numpy().astype("<f4").tobytes())
+            f.write(layer.bias.detach().contiguous().numpy().astype("<f4").tobytes())
+        f.write(dy.numpy().astype("<f4").tobytes())
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    raw = open(fout, "rb").read()
+    off = 0
+
+    def take(*shape):
+        nonlocal off
+        a = np.frombuffer(raw, dtype="<f4", count=int(np.prod(shape)), offset=off).reshape(shape)
+        off += a.nbytes
+        return a
+
+    c = dict(out=take(N, 7), dfeat=take(N, F), W1=take(128, F + 9), b1=take(128), W2=take(128, 128), b2=take(128), W3=take(7, 128))
+    assert off == len(raw)
+    # the same evaluation through the Python host layer
+    dmlps = {k: m.to(dev) for k, m in mlps.items()}
+    images = deformation.TrainImages(dmlps["motion"], dmlps["rot"], dmlps["shs"], dmlps["opacity"])
+    feat_d = feat.to(dev).requires_grad_(True)
+    (out,) = deformation._TrainMLPs.apply(feat_d, tpos.to(dev), t, ((1, False, True),), images, *images.params())
+    (out * dy.to(dev)).sum().backward()
+    layers = (dmlps["rot"][0], dmlps["rot"][2], dmlps["rot"][4])
+    py = dict(out=out.detach(), dfeat=feat_d.grad, W1=layers[0].weight.grad, b1=layers[0].bias.grad, W2=layers[1].weight.grad,
+              b2=layers[1].bias.grad, W3=layers[2].weight.grad)
+    for k, v in c.items():
+        assert np.array_equal(v, py[k].cpu().numpy()), k
+    # and against float64 autograd of the same MLP: outputs and the feature gradient (rows away from a ReLU kink)
+    rot64 = __import__("copy").deepcopy(mlps["rot"]).double().cpu()
+    x = torch.cat([feat.double(), deform_torch.time_embedding((t - tpos).double())], dim=1).requires_grad_(True)
+    ref = rot64(x)
+    assert np.abs(c["out"] - ref.detach().numpy()).max() <= 1e-4 * float(ref.abs().max())
