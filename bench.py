@@ -462,6 +462,7 @@ def run_native_or_ref(args, impl):
                 line["loss_path"] = loss_path_timing(dev, H, W)
                 line["deform_path"] = deform_path_timing(dev)
                 line["deform_train_path"] = deform_train_path_timing(dev)
+                line["train_view_path"] = train_view_path_timing(dev)
                 line["densify_path"] = densify_path_timing(dev)
                 line["plane_path"] = plane_path_timing(dev)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -638,6 +639,91 @@ def deform_train_path_timing(dev, N=300_000, iters=8):
                     "autograd of those epilogues, one tcgen05 launch for the five data-gradient chains, weight gradients; "
                     "gradient agreement on random rows is limited by ReLU kinks (tests/test_deform_train_gpu.py), not by "
                     "arithmetic"}
+
+
+def train_view_path_timing(dev, iters=6):
+    """One training view of the dynamic model end to end — everything between the parameters and their gradients
+    (renderer/__init__.py:92-140, train.py:199-226, helper_train.py:50-70): scale-aware plane sampler ->
+    get_deformation (six MLP evaluations) -> rasterizer -> L1 + D-SSIM + scale regulariser -> backward to the planes,
+    the four MLPs and the Gaussians.  Native arm: this repo's kernels for all four stages.  Reference-ops arm: the same
+    functions as the PyTorch ops SaRO-GS runs (oracle/plane_torch.py — grid_sample / avg_pool2d stand-in for the
+    un-vendored nvdiffrast op —, oracle/deform_torch.py, oracle/ssim_torch.py) around the compiled reference rasterizer
+    when oracle/_ref is present (else the native one; `reference_rasterizer` says which).  configs[1] cloud and camera,
+    planes [512, 512, 512, 256] x 32 features (configs/neural_3D/*.json).  CUDA events, inputs resident."""
+    import saro_gs_b200 as sgs
+    from saro_gs_b200 import synthetic, deformation, loss_utils
+    from saro_gs_b200.hexplane import ScaleAwareResField
+    from oracle import deform_torch, plane_torch, ref_loader
+    from oracle.ssim_torch import torch_l1_dssim_loss
+    scene, cam = synthetic.config2_scene()
+    P = scene.means3D.shape[0]
+    g = torch.Generator().manual_seed(21)
+    op = scene.opacities.clamp(1e-4, 1 - 1e-4)
+    # lifespans are learned: bias the lifespan MLP so that most Gaussians are alive at the rendered timestamps
+    t = dict(xyz=scene.means3D.clone(), rotation=scene.rotations.clone(), scaling=torch.log(scene.scales),
+             opacity=torch.log(op / (1 - op)).reshape(P, 1), features_dc=scene.shs[:, :1, :].contiguous(),
+             features_rest=scene.shs[:, 1:, :].contiguous(), temporal_pos=torch.rand(P, 1, generator=g))
+    leaves = {k: v.to(dev).requires_grad_(True) for k, v in t.items()}
+    cfg = {"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 32, "resolution": [512, 512, 512, 256]}
+    field = ScaleAwareResField(cfg, [1]).to(dev)
+    with torch.no_grad():
+        for p in field.grids[0]:
+            p.copy_((torch.randn(p.shape, generator=g) * 0.2).to(dev))
+    lo, hi = scene.means3D.min(0).values - 0.5, scene.means3D.max(0).values + 0.5
+    field.set_aabb(hi.tolist(), lo.tolist(), 300)
+    mlps = deform_torch.make_train_mlps(32, device=dev, seed=22)
+    with torch.no_grad():
+        for name in ("motion", "rot", "shs"):
+            mlps[name][4].weight.mul_(0.02)
+            mlps[name][4].bias.mul_(0.02)
+        mlps["opacity"][4].bias.fill_(-4.0)               # lifespan = 1 - sigmoid(.) close to 1: everything is alive
+    pc = deform_torch.TrainModelStandIn(leaves, mlps, (1, 0, 0), 6.0, 300.0, hexplane=field)
+    torch_field = lambda pts, ts, sc: plane_torch.field_forward(field, pts, ts, sc)
+    rs = sgs.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=dev), 1.0,
+                                           cam.viewmatrix.to(dev), cam.projmatrix.to(dev), 3, cam.campos.to(dev), False)
+    native_rast = sgs.GaussianRasterizer(rs)
+    ref_rast = ref_loader.ref_api()[1](rs) if ref_loader.available() else None
+    gt = torch.rand(3, cam.height, cam.width, generator=g).to(dev)
+    params = list(leaves.values()) + [p for m in mlps.values() for p in m.parameters()] + list(field.parameters())
+
+    def run(native, steps):
+        pc.hexplane = field if native else torch_field
+        deform = deformation.get_deformation if native else deform_torch.torch_get_deformation
+        rast = native_rast if native or ref_rast is None else ref_rast
+        loss_fn = loss_utils.l1_dssim_loss if native else torch_l1_dssim_loss
+        ms, parts = [], [0.0] * 4
+        for i in range(steps + 2):
+            for p in params:
+                p.grad = None
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            m, rot, sc, opa, shs = deform(pc, 0.35 + 0.01 * i)
+            ev[1].record()
+            image = rast(means3D=m, means2D=torch.zeros_like(m), opacities=opa, shs=shs, scales=sc, rotations=rot)[0]
+            ev[2].record()
+            loss = loss_fn(image, gt, 0.2) + 8e-6 * torch.linalg.vector_norm(pc.scale_residual, ord=2)
+            ev[3].record()
+            loss.backward()
+            ev[4].record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(ev[0].elapsed_time(ev[4]))
+                for k in range(4):
+                    parts[k] += ev[k].elapsed_time(ev[k + 1]) / steps
+        assert all(p.grad is not None for p in params)
+        return sum(ms) / len(ms), parts, float(loss)
+
+    n_ms, n_parts, n_loss = run(True, iters)
+    r_ms, r_parts, r_loss = run(False, 3)
+    names = ("plane_sampler_and_deformation_forward", "rasterizer_forward", "loss_forward", "backward_of_everything")
+    return {"what": "one training view of the dynamic model: plane sampler -> get_deformation -> rasterizer -> loss -> backward "
+                    "(%d Gaussians @%dx%d)" % (P, cam.width, cam.height),
+            "native_ms": n_ms, "reference_ops_ms": r_ms, "speedup": r_ms / n_ms,
+            "native_parts_ms": dict(zip(names, n_parts)), "reference_ops_parts_ms": dict(zip(names, r_parts)),
+            "reference_rasterizer": "compiled reference (oracle/_ref)" if ref_rast is not None else "native (oracle/_ref absent)",
+            "loss_native": n_loss, "loss_reference_ops": r_loss,
+            "note": "the reference-ops plane sampler is a grid_sample / avg_pool2d composition (nvdiffrast is not in this image; "
+                    "its own kernel would be faster than this stand-in): plane_path separates that stage"}
 
 
 def plane_path_timing(dev, N=300_000, iters=10):
