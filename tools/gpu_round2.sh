@@ -2,7 +2,7 @@
 # Developer tool (GPU box, via gpurun): everything one round-2 iteration needs from a single GPU slot.
 #   usage: tools/gpu_round2.sh [tag] [stages]     stages: any of "quick golden tests bench ncu" (default: all)
 TAG=${1:-r2}
-STAGES=${2:-"quick golden tests bench ncu"}
+STAGES=${2:-"quick golden tests bench ncu train"}
 OUT=gpurun_out
 mkdir -p $OUT $OUT/golden
 has() { [[ " $STAGES " == *" $1 "* ]]; }
@@ -47,4 +47,16 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"(binning_fused|tile_count|tile_fill_sorted)_kernel" -s 9 -c 3 \
       -f -o $OUT/${TAG}_binning python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sequence > $OUT/${TAG}_ncu_binning.log 2>&1
   ls -la $OUT | tail -12
+fi
+if has train; then
+  echo "=== training-time deformation: launch list of one forward + backward, full ncu of the tcgen05 kernels"
+  timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file $OUT/${TAG}_deform_train_launches.csv python tools/deform_train_launches.py > $OUT/${TAG}_dt.log 2>&1
+  python tools/deform_train_launches.py --summarise $OUT/${TAG}_deform_train_launches.csv | head -12
+  timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"deform_(wgrad|train|epilogue)" \
+      -f -o $OUT/${TAG}_deform_train python tools/deform_train_launches.py > $OUT/${TAG}_ncu_dt.log 2>&1
+  echo "=== plane sampler: launch list"
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:"plane_" -c 60 \
+      --log-file $OUT/${TAG}_plane_launches.csv python tools/plane_ab.py > $OUT/${TAG}_plane.log 2>&1
+  python tools/deform_train_launches.py --summarise $OUT/${TAG}_plane_launches.csv | head -12
 fi
