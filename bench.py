@@ -476,7 +476,7 @@ def run_native_or_ref(args, impl):
 
 
 # newest `ncu --set full` capture of the render kernels on this exact workload (tools/ncu_summary.py output)
-NCU_SUMMARIES = ["profiles/r2m_render_ncu_summary.csv", "profiles/r2_render_ncu_summary.csv",
+NCU_SUMMARIES = ["profiles/r2r_render_ncu_summary.csv", "profiles/r2m_render_ncu_summary.csv", "profiles/r2_render_ncu_summary.csv",
                  "profiles/r02f_render_ncu_summary.csv"]
 
 

@@ -465,3 +465,47 @@ def get_deformation(self, timestamp, rays=None):
     self.real_xyz = real_xyz                                                              # :803-804 (no gradient)
     shs = torch.cat((self._features_dc, self._features_rest), dim=1) + outs["shs"].reshape(-1, 16, 3)   # :837-841
     return motion, rot, scale, opacity, shs
+
+
+def _lifespan_native(self, hexplane_feature):
+    """lifespan = (1 - min_scale) * (1 - opacity_mlp(feature)) + min_scale  (scene/saro_gaussian.py:782-784) with the MLP as
+    one job of the tcgen05 forward kernel; differentiable (planes, opacity_mlp) when gradients are enabled."""
+    cache = getattr(self, "_sgs_train_cache", None)
+    key = tuple(id(getattr(self, k)) for k in _TRAIN_MLPS)
+    if cache is None or cache["key"] != key:
+        cache = {"key": key, "images": TrainImages(*[getattr(self, k) for k in _TRAIN_MLPS])}
+        self._sgs_train_cache = cache
+    images = cache["images"]
+    (raw,) = _TrainMLPs.apply(hexplane_feature, self.get_temporalpos.detach(), 0.0, ((3, True, True),), images, *images.params())
+    min_scale = self.args.min_interval / (self.duration)
+    return (1 - min_scale) * (1 - torch.sigmoid(raw)) + min_scale
+
+
+def get_deformfeature(self):
+    """Drop-in for GaussianModel.get_deformfeature (scene/saro_gaussian.py:863-869), called once before the test-time
+    render loop (test.py:199): caches `hexplane_feature` and `_lifespan` for get_deformation_eval."""
+    if not self._xyz.is_cuda:
+        raise RuntimeError("get_deformfeature: the model must live on a CUDA device (there is no CPU path)")
+    self.hexplane_feature = self.hexplane(self._xyz.detach(), self.get_temporalpos.detach(), self.get_scaling.detach())
+    self._lifespan = _lifespan_native(self, self.hexplane_feature)
+
+
+def get_intergral(self, start=0.0, end=1.0):
+    """Drop-in for GaussianModel.get_intergral (scene/saro_gaussian.py:761-777, Eq. 22 of the paper; used by the
+    densification masks at :349 and :720): the plane sample and the lifespan MLP run natively under no_grad, the closed
+    form Q is the reference's own statement."""
+    import numpy as np
+    if not self._xyz.is_cuda:
+        raise RuntimeError("get_intergral: the model must live on a CUDA device (there is no CPU path)")
+    with torch.no_grad():
+        feature = self.hexplane(self._xyz.detach(), self.get_temporalpos.detach(), self.get_scaling.detach())
+        lifespan = _lifespan_native(self, feature)
+
+    def Q(x):
+        a1 = torch.tensor([0.070565902], device=x.device)
+        a2 = torch.tensor([1.5976], device=x.device)
+        return 1 - 1 / (1 + torch.exp(a1 * x ** 3 + a2 * x))
+
+    p1 = Q(2 * np.sqrt(2) * (end - self.get_temporalpos) / lifespan)
+    p2 = Q(2 * np.sqrt(2) * (start - self.get_temporalpos) / lifespan)
+    return lifespan * np.sqrt(np.pi) / 2 * (p1 - p2)

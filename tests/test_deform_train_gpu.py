@@ -78,7 +78,8 @@ def _smooth_rows(tensors, mlps, flags, timestamp, margin=2e-4):
     return torch.nonzero(kink[0].cpu() > margin).reshape(-1)
 
 
-@pytest.mark.parametrize("n,feat_dim,flags", [(100_000, 32, (1, 0, 0)), (40_001, 16, (1, 1, 1)), (127, 8, (0, 0, 0)), (129, 24, (1, 0, 1))])
+@pytest.mark.parametrize("n,feat_dim,flags", [(100_000, 32, (1, 0, 0)), (40_001, 16, (1, 1, 1)), (127, 8, (0, 0, 0)), (129, 24, (1, 0, 1)),
+                                               (1, 32, (1, 1, 0)), (4_097, 24, (0, 1, 0)), (33, 16, (0, 0, 1))])
 def test_at_scale_against_float64_restatement(n, feat_dim, flags):
     """ReLU is not differentiable at 0: on a row where some hidden pre-activation is within rounding of 0, two
     arithmetics may take different sides of the kink, that row's feature gradient then differs by one hidden unit's
@@ -131,3 +132,30 @@ def test_loud_failures():
     pc.args.dsh = False
     with pytest.raises(deformation.UnsupportedDeformationConfig):
         deformation.get_deformation(pc, 0.4)
+
+
+def test_get_deformfeature_and_get_intergral_mirrors():
+    """The two small callers around the lifespan MLP (scene/saro_gaussian.py:761-777, :863-869) against their PyTorch
+    restatement in float64 (same statements; the MLP is what differs: tcgen05 job vs nn.Sequential)."""
+    import math
+    z = np.load(GOLDEN[0])
+    pc, leaves, mlps, _ = build(z, DEV, torch.float32)
+    with torch.no_grad():
+        deformation.get_deformfeature(pc)
+        got_int = deformation.get_intergral(pc, 0.1, 0.8)
+    assert torch.equal(pc.hexplane_feature, leaves["hexplane_feature"])
+    pc64, leaves64, mlps64, _ = build(z, DEV, torch.float64)
+    with torch.no_grad():
+        ms = pc64.args.min_interval / pc64.duration
+        life = (1 - ms) * (1 - mlps64["opacity"](leaves64["hexplane_feature"])) + ms
+        Q = lambda x: 1 - 1 / (1 + torch.exp(0.070565902 * x ** 3 + 1.5976 * x))
+        tp = leaves64["temporal_pos"]
+        want_int = life * math.sqrt(math.pi) / 2 * (Q(2 * math.sqrt(2) * (0.8 - tp) / life) - Q(2 * math.sqrt(2) * (0.1 - tp) / life))
+    assert maxrel(pc._lifespan.cpu().numpy(), life.cpu().numpy()) <= TOL
+    assert maxrel(pc._lifespan.cpu().numpy(), z["f64_lifespan"]) <= TOL          # and the reference's own get_deformation value
+    assert maxrel(got_int.cpu().numpy(), want_int.cpu().numpy()) <= TOL
+    # the cached pair feeds the test-time hand-off
+    pc.hexplane_feature = pc.hexplane_feature.detach()
+    pc._lifespan = pc._lifespan.detach()
+    out = deformation.get_deformation_eval(pc, float(z["timestamp"]))
+    assert out[0].shape[0] > 0
