@@ -711,7 +711,7 @@ def train_view_path_timing(dev, iters=6):
                 for k in range(4):
                     parts[k] += ev[k].elapsed_time(ev[k + 1]) / steps
         assert all(p.grad is not None for p in params)
-        return sum(ms) / len(ms), parts, float(loss)
+        return sum(ms) / len(ms), parts, float(loss.detach())
 
     n_ms, n_parts, n_loss = run(True, iters)
     r_ms, r_parts, r_loss = run(False, 3)
