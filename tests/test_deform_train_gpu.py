@@ -159,3 +159,20 @@ def test_get_deformfeature_and_get_intergral_mirrors():
     pc._lifespan = pc._lifespan.detach()
     out = deformation.get_deformation_eval(pc, float(z["timestamp"]))
     assert out[0].shape[0] > 0
+
+
+def test_empty_cloud():
+    """No Gaussians (everything pruned): empty outputs of the right shapes, backward is a no-op that still reaches
+    the parameters with zero / absent gradients — the reference's PyTorch ops behave the same way."""
+    tensors, weights = _random_case(0, 32, (1, 0, 0), seed=3)
+    mlps = deform_torch.make_train_mlps(32, seed=4)
+    leaves = {k: v.to(DEV).requires_grad_(True) for k, v in tensors.items()}
+    dm = {k: m.to(DEV) for k, m in mlps.items()}
+    pc = deform_torch.TrainModelStandIn(leaves, dm, (1, 0, 0), 6.0, 300.0)
+    outs = deformation.get_deformation(pc, 0.5)
+    assert [tuple(o.shape) for o in outs] == [(0, 3), (0, 4), (0, 3), (0, 1), (0, 16, 3)]
+    assert tuple(pc._lifespan.shape) == (0, 1) and tuple(pc.real_xyz.shape) == (0, 3) and tuple(pc.scale_residual.shape) == (0, 3)
+    sum(o.sum() for o in outs).backward()
+    torch.cuda.synchronize()
+    g = dm["shs"][0].weight.grad
+    assert g is None or float(g.abs().sum()) == 0.0
