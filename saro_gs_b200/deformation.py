@@ -73,7 +73,7 @@ class PackedMLPs:
                 "plane feature widths 8, 16, 24 and 32 (every shipped config uses 16 or 32)")
         self.in_dim = in_dim
         self.feat_dim = in_dim - TIME_DIMS
-        self.buffer = torch.empty(lib.sgs_deform_packed_bytes(), dtype=torch.uint8, device=dev)
+        self.buffer = torch.zeros(lib.sgs_deform_packed_bytes(), dtype=torch.uint8, device=dev)   # the kernel copies whole images: no stale bytes
         self.versions = None
         # modules are re-read on every refresh (they may swap their parameters); plain tuples are fixed
         self._layers = [None if isinstance(m, (tuple, list)) else [l for l in m if hasattr(l, "weight")]
@@ -215,7 +215,7 @@ class TrainImages:
             self.shapes.append((w_in, hid2, n_out))
         nbytes = lib.sgs_deform_image_bytes()
         self.stride = (nbytes + 255) // 256 * 256
-        self.buffer = torch.empty(8 * self.stride, dtype=torch.uint8, device=dev)      # [mlp][forward | backward]
+        self.buffer = torch.zeros(8 * self.stride, dtype=torch.uint8, device=dev)      # [mlp][forward | backward]; zeroed: the kernels copy whole images
         self.versions = None
 
     def params(self):
