@@ -1,3 +1,4 @@
+"""Developer tool (GPU box): host-to-device bandwidth from pinned memory at a few sizes (one stream / two streams)."""
 import torch, time
 dev = torch.device("cuda:0")
 for mb in (1, 4, 16, 64, 256):
